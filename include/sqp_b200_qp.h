@@ -1,0 +1,171 @@
+/*
+ * sqp_b200_qp.h -- C-ABI of the B200-native batched QP-subproblem solver.
+ *
+ * This is the drop-in boundary for ONE path of msplr/sqp_solver: the OSQP-style ADMM solver
+ * `qp_solver::QPSolver<Scalar>` (reference include/solvers/qp.hpp:113-250, src/qp.cpp:11-157).
+ * The reference has no FFI of its own (it is a header+static-lib C++ library); the entry
+ * points below are exactly what a binding of that class would need, batched over B independent
+ * problem instances of identical (n, m):
+ *
+ *   sqpb200_qp_batch_create      <->  B x `QPSolver<double> solver;`            qp.hpp:148
+ *   sqpb200_qp_batch_setup       <->  QPSolver::setup(qp)                        qp.hpp:151, qp.cpp:11-44
+ *   sqpb200_qp_batch_update_qp   <->  QPSolver::update_qp(qp)                    qp.hpp:154, qp.cpp:46-62
+ *   sqpb200_qp_batch_solve       <->  QPSolver::solve(qp)                        qp.hpp:157, qp.cpp:64-157
+ *   sqpb200_qp_batch_setup_solve <->  setup(qp); solve(qp);  (the only in-library call site,
+ *                                     SQP<T>::run_solve_qp)                      sqp.cpp:221-222
+ *   sqpb200_qp_batch_get         <->  primal_solution() / dual_solution() / info()  qp.hpp:159-169
+ *   sqpb200_qp_settings          <->  QPSolverSettings<double>                   qp.hpp:36-53
+ *   sqpb200_qp_status            <->  QPSolverStatus                             qp.hpp:70
+ *   sqpb200_constr_type_init     <->  static QPSolver::constr_type_init(l,u,out) qp.hpp:173, qp.cpp:283-294
+ *
+ * Data layout (caller-owned buffers, batch-major, each matrix COLUMN-major so one problem is
+ * bit-compatible with Eigen::MatrixXd::data() / VectorXd::data() of QuadraticProblem, qp.hpp:19-34):
+ *   P[B][n*n]  q[B][n]  A[B][m*n]  l[B][m]  u[B][m]   (fp64; +-inf and |bound| > 1e16 pass through)
+ *   x[B][n]    y[B][m]  z[B][m]    status[B] iter[B] rho_updates[B] rho_estimate[B] res_prim[B] res_dual[B]
+ *
+ * Plain pointers and sizes only; no C++/torch types; nothing throws across this boundary.
+ * Every function returns 0 on success or an sqpb200_error code; sqpb200_last_error() gives text.
+ */
+#ifndef SQP_B200_QP_H
+#define SQP_B200_QP_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQPB200_ABI_VERSION 1
+
+/* mirrors QPSolverSettings<double>, include/solvers/qp.hpp:36-53 (same names, same defaults) */
+typedef struct sqpb200_qp_settings {
+    double rho;                    /* 1e-1 */
+    double sigma;                  /* 1e-6 */
+    double alpha;                  /* 1.0  */
+    double eps_rel;                /* 1e-3 */
+    double eps_abs;                /* 1e-3 */
+    int max_iter;                  /* 1000 */
+    int check_termination;         /* 25, 0 disables */
+    int warm_start;                /* false; a no-op in the reference (qp.cpp:78-82) and here */
+    int adaptive_rho;              /* false */
+    double adaptive_rho_tolerance; /* 5 */
+    int adaptive_rho_interval;     /* 25 */
+    int verbose;                   /* false */
+} sqpb200_qp_settings;
+
+/* QPSolverStatus, include/solvers/qp.hpp:70 */
+typedef enum sqpb200_qp_status {
+    SQPB200_SOLVED = 0,
+    SQPB200_MAX_ITER_EXCEEDED = 1,
+    SQPB200_UNSOLVED = 2,
+    SQPB200_NUMERICAL_ISSUES = 3,
+    SQPB200_UNINITIALIZED = 4
+} sqpb200_qp_status;
+
+/* QPSolver::ConstraintType, include/solvers/qp.hpp:134 */
+typedef enum sqpb200_constr_type {
+    SQPB200_INEQUALITY_CONSTRAINT = 0,
+    SQPB200_EQUALITY_CONSTRAINT = 1,
+    SQPB200_LOOSE_BOUNDS = 2
+} sqpb200_constr_type;
+
+typedef enum sqpb200_error {
+    SQPB200_OK = 0,
+    SQPB200_ERR_INVALID = 1,     /* bad argument / size */
+    SQPB200_ERR_CUDA = 2,        /* CUDA runtime failure (no device, launch error, ...) */
+    SQPB200_ERR_UNSUPPORTED = 3, /* shape outside what the kernels cover */
+    SQPB200_ERR_NOMEM = 4
+} sqpb200_error;
+
+/* pointer-space flags for the data arguments of one call */
+#define SQPB200_HOST_PTRS 0u   /* caller passes host buffers; the call copies and synchronises */
+#define SQPB200_DEVICE_PTRS 1u /* caller passes device buffers; the call is asynchronous on `stream` */
+/* `stream` is a cudaStream_t passed as void*; NULL is the CUDA legacy default stream. */
+
+/* context options for sqpb200_ctx_set_option */
+#define SQPB200_OPT_KERNEL 1       /* 0 = auto (default), 1 = force the generic kernel, 2 = force the register-tiled kernel */
+#define SQPB200_OPT_H2D_CHUNKS 2   /* number of pipeline chunks for HOST_PTRS calls (default 8) */
+#define SQPB200_OPT_CTAS_PER_SM 3  /* 0 = auto */
+
+typedef struct sqpb200_ctx sqpb200_ctx;           /* one per (host thread, GPU) */
+typedef struct sqpb200_qp_batch sqpb200_qp_batch; /* B solver instances: state x,z,y, info, factor */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int sqpb200_abi_version(void);
+int sqpb200_ctx_create(int device, sqpb200_ctx **out);
+int sqpb200_ctx_destroy(sqpb200_ctx *ctx);
+int sqpb200_ctx_set_option(sqpb200_ctx *ctx, int option, int value);
+/* text of the last failure on this context (ctx == NULL: last failure of a create call on this thread) */
+const char *sqpb200_last_error(const sqpb200_ctx *ctx);
+int sqpb200_device_query(const sqpb200_ctx *ctx, int *device, int *sm_count, int *cc_major, int *cc_minor,
+                         size_t *smem_per_block_optin);
+/* number of kernels this context has launched so far (bench.py's "gpu_launches") */
+long long sqpb200_launch_count(const sqpb200_ctx *ctx);
+/* name of the kernel the last solve dispatched to ("generic", "tile<64,128,8>", ...) */
+const char *sqpb200_last_kernel(const sqpb200_ctx *ctx);
+
+void sqpb200_qp_default_settings(sqpb200_qp_settings *s);
+
+/* host-side, no GPU: static QPSolver::constr_type_init (qp.cpp:283-294) */
+int sqpb200_constr_type_init(const double *l, const double *u, int m, int *constr_type);
+
+/* ---- batched solver object ---------------------------------------------------------------- */
+/* `batch` is the capacity; every call below processes the first `count` instances. A new batch
+ * object is B default-constructed solvers: status UNINITIALIZED, iter 0, rho_updates 0 (qp.hpp:72-79). */
+int sqpb200_qp_batch_create(sqpb200_ctx *ctx, int batch, int n, int m, sqpb200_qp_batch **out);
+int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b);
+
+/* setup: zero x,z,y; classify constraints; rho vector from settings->rho (rho_updates += 1);
+ * build and factor the KKT system; status = UNSOLVED or NUMERICAL_ISSUES. qp.cpp:11-44 */
+int sqpb200_qp_batch_setup(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                           const double *q, const double *A, const double *l, const double *u, unsigned flags,
+                           void *stream);
+/* update_qp: same without the x,z,y reset. qp.cpp:46-62 */
+int sqpb200_qp_batch_update_qp(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                               const double *q, const double *A, const double *l, const double *u, unsigned flags,
+                               void *stream);
+/* solve: the ADMM loop from the current x,z,y (always a warm start, see qp.cpp:78-82), using the
+ * factor and constraint classes of the last setup/update_qp. Instances whose status is
+ * UNINITIALIZED or NUMERICAL_ISSUES are left untouched (qp.cpp:68-71). qp.cpp:64-157 */
+int sqpb200_qp_batch_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                           const double *q, const double *A, const double *l, const double *u, unsigned flags,
+                           void *stream);
+/* setup immediately followed by solve in ONE kernel launch (the factor never leaves the SM).
+ * This is the hot path: SQP<T>::run_solve_qp, sqp.cpp:221-222. */
+int sqpb200_qp_batch_setup_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                                 const double *q, const double *A, const double *l, const double *u, unsigned flags,
+                                 void *stream);
+
+/* Read back solutions and info (any pointer may be NULL). primal_solution()/dual_solution()/info(),
+ * qp.hpp:159-169; z is exposed in addition so a caller can checkpoint a warm start. */
+int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,
+                         int *rho_updates, double *rho_estimate, double *res_prim, double *res_dual, unsigned flags,
+                         void *stream);
+/* Overwrite the iterates (warm start from a checkpoint). Any pointer may be NULL. */
+int sqpb200_qp_batch_set_iterates(sqpb200_qp_batch *b, int count, const double *x, const double *y, const double *z,
+                                  unsigned flags, void *stream);
+
+/* Zero-copy view of the device-resident state for device-side consumers. */
+typedef struct sqpb200_qp_device_view {
+    double *x, *y, *z;
+    int *status, *iter, *rho_updates;
+    double *rho_estimate, *res_prim, *res_dual, *rho;
+    long long *total_iters; /* device scalar: sum of ADMM iterations executed by the last solve launch */
+} sqpb200_qp_device_view;
+int sqpb200_qp_batch_device_view(sqpb200_qp_batch *b, sqpb200_qp_device_view *view);
+
+/* Sum of ADMM iterations the last setup/solve call executed over all its instances
+ * (synchronises the call's stream). bench.py converts QP/s into ADMM iterations/s with it. */
+int sqpb200_qp_batch_total_iters(sqpb200_qp_batch *b, long long *total, void *stream);
+
+/* Convenience one-shot: fresh solvers, setup+solve, read back. Equivalent to the five calls
+ * create / setup_solve / get / destroy with HOST or DEVICE pointers. */
+int sqpb200_qp_solve_batch(sqpb200_ctx *ctx, const sqpb200_qp_settings *settings, int batch, int n, int m,
+                           const double *P, const double *q, const double *A, const double *l, const double *u,
+                           double *x, double *y, double *z, int *status, int *iter, int *rho_updates,
+                           double *rho_estimate, double *res_prim, double *res_dual, unsigned flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQP_B200_QP_H */

@@ -1,0 +1,54 @@
+"""In-tree build of the CUDA library (sm_100a only): python -m sqp_solver_b200.build
+
+Produces sqp_solver_b200/libsqp_b200.so from csrc/*.cu with nvcc. The .so is git-ignored but
+travels to the GPU box with the repo snapshot. nvcc cross-compiles here without a GPU."""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsqp_b200.so")
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+         "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-ccbin", "/usr/bin/g++"]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not stale():
+        return LIB
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src in sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        if verbose or pr.returncode:
+            sys.stderr.write(out)
+        if pr.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++", "-Wno-deprecated-gpu-targets"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

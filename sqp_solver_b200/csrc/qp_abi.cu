@@ -1,0 +1,489 @@
+// C-ABI implementation (host side) of include/sqp_b200_qp.h.
+// Owns device state for a batch of solver instances, stages host buffers in pipelined chunks,
+// picks a kernel, and launches it.  No exceptions cross this boundary.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "qp_common.cuh"
+#include "qp_tile.cuh"
+
+using namespace sqpb200;
+
+static thread_local std::string g_create_error;
+
+struct sqpb200_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;       // internal housekeeping stream (state initialisation)
+    cudaStream_t copy_stream = nullptr;  // H2D staging for HOST_PTRS calls
+    int *counters = nullptr;             // ring of work-queue counters, one per launch
+    static constexpr int kCounters = 1024;
+    long long launches = 0;
+    double *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int opt_kernel = 0, opt_chunks = 8, opt_ctas_per_sm = 0;
+    std::string err;
+    char last_kernel[64] = "none";
+    cudaEvent_t chunk_events[64]{};
+};
+
+struct sqpb200_qp_batch {
+    sqpb200_ctx *ctx = nullptr;
+    int batch = 0, n = 0, m = 0;
+    double *x = nullptr, *y = nullptr, *z = nullptr;
+    int *status = nullptr, *iter = nullptr, *rho_updates = nullptr;
+    double *rho_estimate = nullptr, *res_prim = nullptr, *res_dual = nullptr, *rho = nullptr;
+    signed char *ctype = nullptr;
+    double *fact = nullptr;  // lazily allocated
+    bool fused_used = false;
+    bool fact_valid = false;  // a setup()/update_qp()/solve() launch has stored H^-1, rho and classes
+    unsigned long long *total_iters = nullptr;
+    // staging for HOST_PTRS calls (lazily allocated)
+    double *dP = nullptr, *dq = nullptr, *dA = nullptr, *dl = nullptr, *du = nullptr;
+};
+
+static int fail(sqpb200_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess)
+        snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else
+        snprintf(buf, sizeof buf, "%s", what);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+#define CK(ctx, call)                                                        \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return fail((ctx), SQPB200_ERR_CUDA, #call, e__); \
+    } while (0)
+
+extern "C" {
+
+int sqpb200_abi_version(void) { return SQPB200_ABI_VERSION; }
+
+void sqpb200_qp_default_settings(sqpb200_qp_settings *s) {  // qp.hpp:38-53
+    if (!s) return;
+    s->rho = 1e-1;
+    s->sigma = 1e-6;
+    s->alpha = 1.0;
+    s->eps_rel = 1e-3;
+    s->eps_abs = 1e-3;
+    s->max_iter = 1000;
+    s->check_termination = 25;
+    s->warm_start = 0;
+    s->adaptive_rho = 0;
+    s->adaptive_rho_tolerance = 5;
+    s->adaptive_rho_interval = 25;
+    s->verbose = 0;
+}
+
+int sqpb200_constr_type_init(const double *l, const double *u, int m, int *constr_type) {  // qp.cpp:283-294
+    if (!l || !u || !constr_type || m < 0) return SQPB200_ERR_INVALID;
+    for (int i = 0; i < m; i++) {
+        if (l[i] < -LOOSE_BOUNDS_THRESH && u[i] > LOOSE_BOUNDS_THRESH) constr_type[i] = SQPB200_LOOSE_BOUNDS;
+        else if (u[i] - l[i] < RHO_TOL) constr_type[i] = SQPB200_EQUALITY_CONSTRAINT;
+        else constr_type[i] = SQPB200_INEQUALITY_CONSTRAINT;
+    }
+    return SQPB200_OK;
+}
+
+int sqpb200_ctx_create(int device, sqpb200_ctx **out) {
+    if (!out) return fail(nullptr, SQPB200_ERR_INVALID, "sqpb200_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SQPB200_ERR_CUDA, "sqpb200_ctx_create: no CUDA device (this library has no CPU fallback)", e);
+    if (device < 0 || device >= ndev) return fail(nullptr, SQPB200_ERR_INVALID, "sqpb200_ctx_create: bad device index");
+    sqpb200_ctx *c = new (std::nothrow) sqpb200_ctx();
+    if (!c) return fail(nullptr, SQPB200_ERR_NOMEM, "sqpb200_ctx_create: host allocation failed");
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&c->counters, sizeof(int) * sqpb200_ctx::kCounters)) != cudaSuccess) {
+        int rc = fail(nullptr, SQPB200_ERR_CUDA, "sqpb200_ctx_create", e);
+        delete c;
+        return rc;
+    }
+    for (auto &ev : c->chunk_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (c->prop.major < 10) {
+        delete c;
+        return fail(nullptr, SQPB200_ERR_UNSUPPORTED, "sqpb200_ctx_create: kernels are built for sm_100a only");
+    }
+    *out = c;
+    return SQPB200_OK;
+}
+
+int sqpb200_ctx_destroy(sqpb200_ctx *c) {
+    if (!c) return SQPB200_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &ev : c->chunk_events)
+        if (ev) cudaEventDestroy(ev);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->counters) cudaFree(c->counters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return SQPB200_OK;
+}
+
+int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
+    if (!c) return SQPB200_ERR_INVALID;
+    switch (option) {
+        case SQPB200_OPT_KERNEL:
+            if (value < 0 || value > 2) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_KERNEL: value must be 0, 1 or 2");
+            c->opt_kernel = value;
+            return SQPB200_OK;
+        case SQPB200_OPT_H2D_CHUNKS:
+            if (value < 1 || value > 64) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_H2D_CHUNKS: 1..64");
+            c->opt_chunks = value;
+            return SQPB200_OK;
+        case SQPB200_OPT_CTAS_PER_SM:
+            if (value < 0 || value > 32) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_CTAS_PER_SM: 0..32");
+            c->opt_ctas_per_sm = value;
+            return SQPB200_OK;
+    }
+    return fail(c, SQPB200_ERR_INVALID, "sqpb200_ctx_set_option: unknown option");
+}
+
+const char *sqpb200_last_error(const sqpb200_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int sqpb200_device_query(const sqpb200_ctx *c, int *device, int *sm_count, int *cc_major, int *cc_minor,
+                         size_t *smem_per_block_optin) {
+    if (!c) return SQPB200_ERR_INVALID;
+    if (device) *device = c->device;
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (smem_per_block_optin) *smem_per_block_optin = c->prop.sharedMemPerBlockOptin;
+    return SQPB200_OK;
+}
+
+long long sqpb200_launch_count(const sqpb200_ctx *c) { return c ? c->launches : 0; }
+const char *sqpb200_last_kernel(const sqpb200_ctx *c) { return c ? c->last_kernel : "none"; }
+
+int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
+    if (!b) return SQPB200_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaDeviceSynchronize();
+    void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
+                    b->rho, b->ctype, b->fact, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete b;
+    return SQPB200_OK;
+}
+
+int sqpb200_qp_batch_create(sqpb200_ctx *c, int batch, int n, int m, sqpb200_qp_batch **out) {
+    if (!c || !out) return SQPB200_ERR_INVALID;
+    *out = nullptr;
+    if (batch < 1 || n < 1 || m < 0) return fail(c, SQPB200_ERR_INVALID, "sqpb200_qp_batch_create: need batch >= 1, n >= 1, m >= 0");
+    if (!generic_supported(n, m, c->prop.sharedMemPerBlockOptin) && !tile_supported(n, m))
+        return fail(c, SQPB200_ERR_UNSUPPORTED, "sqpb200_qp_batch_create: (n, m) too large for the kernels' shared-memory vectors");
+    CK(c, cudaSetDevice(c->device));
+    sqpb200_qp_batch *b = new (std::nothrow) sqpb200_qp_batch();
+    if (!b) return fail(c, SQPB200_ERR_NOMEM, "host allocation failed");
+    b->ctx = c;
+    b->batch = batch;
+    b->n = n;
+    b->m = m;
+    size_t B = (size_t)batch;
+    size_t mm = m > 0 ? (size_t)m : 1;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    };
+    alloc((void **)&b->x, B * n * sizeof(double));
+    alloc((void **)&b->y, B * mm * sizeof(double));
+    alloc((void **)&b->z, B * mm * sizeof(double));
+    alloc((void **)&b->status, B * sizeof(int));
+    alloc((void **)&b->iter, B * sizeof(int));
+    alloc((void **)&b->rho_updates, B * sizeof(int));
+    alloc((void **)&b->rho_estimate, B * sizeof(double));
+    alloc((void **)&b->res_prim, B * sizeof(double));
+    alloc((void **)&b->res_dual, B * sizeof(double));
+    alloc((void **)&b->rho, B * sizeof(double));
+    alloc((void **)&b->ctype, B * mm);
+    alloc((void **)&b->total_iters, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        int rc = fail(c, e == cudaErrorMemoryAllocation ? SQPB200_ERR_NOMEM : SQPB200_ERR_CUDA, "sqpb200_qp_batch_create: cudaMalloc", e);
+        sqpb200_qp_batch_destroy(b);
+        return rc;
+    }
+    // B default-constructed solvers: QPSolverInfo defaults, qp.hpp:72-79
+    cudaStream_t s = c->stream;
+    cudaMemsetAsync(b->x, 0, B * n * sizeof(double), s);
+    cudaMemsetAsync(b->y, 0, B * mm * sizeof(double), s);
+    cudaMemsetAsync(b->z, 0, B * mm * sizeof(double), s);
+    cudaMemsetAsync(b->iter, 0, B * sizeof(int), s);
+    cudaMemsetAsync(b->rho_updates, 0, B * sizeof(int), s);
+    cudaMemsetAsync(b->rho_estimate, 0, B * sizeof(double), s);
+    cudaMemsetAsync(b->res_prim, 0, B * sizeof(double), s);
+    cudaMemsetAsync(b->res_dual, 0, B * sizeof(double), s);
+    cudaMemsetAsync(b->rho, 0, B * sizeof(double), s);
+    cudaMemsetAsync(b->ctype, 0, B * mm, s);
+    cudaMemsetAsync(b->total_iters, 0, sizeof(unsigned long long), s);
+    // status = UNINITIALIZED (4): byte pattern 0x04040404 is not 4, so fill through a tiny kernel-free path
+    {
+        int *h = (int *)malloc(B * sizeof(int));
+        if (!h) {
+            sqpb200_qp_batch_destroy(b);
+            return fail(c, SQPB200_ERR_NOMEM, "host allocation failed");
+        }
+        for (size_t i = 0; i < B; ++i) h[i] = SQPB200_UNINITIALIZED;
+        e = cudaMemcpyAsync(b->status, h, B * sizeof(int), cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);
+        free(h);
+    }
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        int rc = fail(c, SQPB200_ERR_CUDA, "sqpb200_qp_batch_create: init", e);
+        sqpb200_qp_batch_destroy(b);
+        return rc;
+    }
+    *out = b;
+    return SQPB200_OK;
+}
+
+}  // extern "C"
+
+// ---- launch plumbing -----------------------------------------------------------------------
+
+static int ensure_scratch(sqpb200_ctx *c, size_t bytes) {
+    if (bytes <= c->scratch_bytes) return SQPB200_OK;
+    CK(c, cudaDeviceSynchronize());
+    if (c->scratch) cudaFree(c->scratch);
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&c->scratch, bytes);
+    if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "scratch cudaMalloc", e);
+    c->scratch_bytes = bytes;
+    return SQPB200_OK;
+}
+
+static int ensure_fact(sqpb200_qp_batch *b) {
+    if (b->fact) return SQPB200_OK;
+    cudaError_t e = cudaMalloc(&b->fact, sizeof(double) * (size_t)b->batch * b->n * b->n);
+    if (e != cudaSuccess) return fail(b->ctx, SQPB200_ERR_NOMEM, "factor slab cudaMalloc", e);
+    return SQPB200_OK;
+}
+
+static int ensure_staging(sqpb200_qp_batch *b) {
+    if (b->dP) return SQPB200_OK;
+    size_t B = (size_t)b->batch, n = b->n, m = b->m > 0 ? b->m : 1;
+    cudaError_t e = cudaMalloc(&b->dP, B * n * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->dq, B * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->dA, B * m * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->dl, B * m * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&b->du, B * m * sizeof(double));
+    if (e != cudaSuccess) return fail(b->ctx, SQPB200_ERR_NOMEM, "input staging cudaMalloc", e);
+    return SQPB200_OK;
+}
+
+// One kernel launch over QPs [first, first+count) of the batch arrays.
+static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode, int first, int count,
+                        const double *P, const double *q, const double *A, const double *l, const double *u,
+                        cudaStream_t stream) {
+    sqpb200_ctx *c = b->ctx;
+    KernelParams p{};
+    p.first = first;
+    p.count = count;
+    p.n = b->n;
+    p.m = b->m;
+    p.P = P; p.q = q; p.A = A; p.l = l; p.u = u;
+    p.x = b->x; p.z = b->z; p.y = b->y;
+    p.status = b->status; p.iter = b->iter; p.rho_updates = b->rho_updates;
+    p.rho_estimate = b->rho_estimate; p.res_prim = b->res_prim; p.res_dual = b->res_dual; p.rho = b->rho;
+    p.ctype = b->ctype;
+    p.total_iters = b->total_iters;
+    p.mode = mode;
+    p.s = *st;
+    int slot = (int)(c->launches % sqpb200_ctx::kCounters);
+    p.work_counter = c->counters + slot;
+    CK(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
+
+    const bool want_tile = c->opt_kernel != 1 && tile_supported(b->n, b->m);
+    if (c->opt_kernel == 2 && !want_tile) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
+    const bool needs_fact = !want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR));
+    if (needs_fact) {
+        int rc = ensure_fact(b);
+        if (rc) return rc;
+    }
+    p.fact = b->fact;
+    cudaError_t e;
+    if (want_tile) {
+        e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, stream, c->last_kernel, sizeof c->last_kernel);
+    } else {
+        if (!generic_supported(b->n, b->m, c->prop.sharedMemPerBlockOptin))
+            return fail(c, SQPB200_ERR_UNSUPPORTED, "(n, m) too large for the generic kernel");
+        int grid = generic_grid(count, c->prop.multiProcessorCount);
+        int rc = ensure_scratch(c, generic_scratch_bytes(b->n, grid));
+        if (rc) return rc;
+        p.scratch = c->scratch;
+        e = launch_generic(p, c->prop.multiProcessorCount, c->prop.sharedMemPerBlockOptin, stream, nullptr);
+        snprintf(c->last_kernel, sizeof c->last_kernel, "generic");
+    }
+    if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "kernel launch", e);
+    c->launches += 1;
+    return SQPB200_OK;
+}
+
+static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode, int count, const double *P,
+               const double *q, const double *A, const double *l, const double *u, unsigned flags, void *stream_) {
+    if (!b) return SQPB200_ERR_INVALID;
+    sqpb200_ctx *c = b->ctx;
+    if (!st) return fail(c, SQPB200_ERR_INVALID, "settings is NULL");
+    if (count < 0 || count > b->batch) return fail(c, SQPB200_ERR_INVALID, "count outside [0, batch]");
+    if (count == 0) return SQPB200_OK;
+    if (!P || !q || !A || ((!l || !u) && b->m > 0)) return fail(c, SQPB200_ERR_INVALID, "NULL problem array");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;  // NULL is the CUDA legacy default stream
+    CK(c, cudaMemsetAsync(b->total_iters, 0, sizeof(unsigned long long), stream));
+    const size_t n = b->n, m = b->m;
+    if (flags & SQPB200_DEVICE_PTRS) return launch_range(b, st, mode, 0, count, P, q, A, l, u, stream);
+
+    // HOST_PTRS: stage in chunks on the copy stream, overlap each chunk's H2D with the previous chunk's solve
+    int rc = ensure_staging(b);
+    if (rc) return rc;
+    int chunks = c->opt_chunks;
+    if (chunks > count) chunks = count;
+    // the compute stream may still be reading the staging buffers from an earlier call
+    CK(c, cudaEventRecord(c->chunk_events[63], stream));
+    CK(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_events[63], 0));
+    for (int k = 0; k < chunks; ++k) {
+        size_t lo = (size_t)count * k / chunks, hi = (size_t)count * (k + 1) / chunks, cnt = hi - lo;
+        CK(c, cudaMemcpyAsync(b->dP + lo * n * n, P + lo * n * n, cnt * n * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        CK(c, cudaMemcpyAsync(b->dA + lo * m * n, A + lo * m * n, cnt * m * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        CK(c, cudaMemcpyAsync(b->dq + lo * n, q + lo * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        if (m > 0) {
+            CK(c, cudaMemcpyAsync(b->dl + lo * m, l + lo * m, cnt * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+            CK(c, cudaMemcpyAsync(b->du + lo * m, u + lo * m, cnt * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        CK(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
+        CK(c, cudaStreamWaitEvent(stream, c->chunk_events[k], 0));
+        rc = launch_range(b, st, mode, (int)lo, (int)cnt, b->dP, b->dq, b->dA, b->dl, b->du, stream);
+        if (rc) return rc;
+    }
+    CK(c, cudaStreamSynchronize(stream));
+    return SQPB200_OK;
+}
+
+extern "C" {
+
+int sqpb200_qp_batch_setup(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P, const double *q,
+                           const double *A, const double *l, const double *u, unsigned flags, void *stream) {
+    int rc = run(b, s, MODE_RESET | MODE_FACTOR | MODE_STORE_FACTOR, count, P, q, A, l, u, flags, stream);
+    if (!rc && b) b->fact_valid = true;
+    return rc;
+}
+int sqpb200_qp_batch_update_qp(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P,
+                               const double *q, const double *A, const double *l, const double *u, unsigned flags, void *stream) {
+    int rc = run(b, s, MODE_FACTOR | MODE_STORE_FACTOR, count, P, q, A, l, u, flags, stream);
+    if (!rc && b) b->fact_valid = true;
+    return rc;
+}
+int sqpb200_qp_batch_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P, const double *q,
+                           const double *A, const double *l, const double *u, unsigned flags, void *stream) {
+    // Without a stored factor every instance is still UNINITIALIZED (solve is a no-op, qp.cpp:68-71)
+    // or was last run through the fused setup_solve, which keeps the factor on-chip only.
+    if (b && !b->fact_valid) {
+        bool fresh = true;  // never set up at all: run the launch so the no-op semantics are exercised on device
+        if (b->fused_used) fresh = false;
+        if (!fresh)
+            return fail(b->ctx, SQPB200_ERR_INVALID,
+                        "sqpb200_qp_batch_solve: the last setup was the fused setup_solve, which does not keep the factor; call setup() first");
+    }
+    return run(b, s, MODE_LOAD_FACTOR | MODE_SOLVE | MODE_STORE_FACTOR, count, P, q, A, l, u, flags, stream);
+}
+int sqpb200_qp_batch_setup_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P,
+                                 const double *q, const double *A, const double *l, const double *u, unsigned flags, void *stream) {
+    if (b) {
+        b->fact_valid = false;
+        b->fused_used = true;
+    }
+    return run(b, s, MODE_RESET | MODE_FACTOR | MODE_SOLVE, count, P, q, A, l, u, flags, stream);
+}
+
+int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,
+                         int *rho_updates, double *rho_estimate, double *res_prim, double *res_dual, unsigned flags,
+                         void *stream_) {
+    if (!b) return SQPB200_ERR_INVALID;
+    sqpb200_ctx *c = b->ctx;
+    if (count < 0 || count > b->batch) return fail(c, SQPB200_ERR_INVALID, "count outside [0, batch]");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;  // NULL is the CUDA legacy default stream
+    const cudaMemcpyKind kind = (flags & SQPB200_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    size_t B = count, n = b->n, m = b->m;
+    if (x) CK(c, cudaMemcpyAsync(x, b->x, B * n * sizeof(double), kind, stream));
+    if (y && m) CK(c, cudaMemcpyAsync(y, b->y, B * m * sizeof(double), kind, stream));
+    if (z && m) CK(c, cudaMemcpyAsync(z, b->z, B * m * sizeof(double), kind, stream));
+    if (status) CK(c, cudaMemcpyAsync(status, b->status, B * sizeof(int), kind, stream));
+    if (iter) CK(c, cudaMemcpyAsync(iter, b->iter, B * sizeof(int), kind, stream));
+    if (rho_updates) CK(c, cudaMemcpyAsync(rho_updates, b->rho_updates, B * sizeof(int), kind, stream));
+    if (rho_estimate) CK(c, cudaMemcpyAsync(rho_estimate, b->rho_estimate, B * sizeof(double), kind, stream));
+    if (res_prim) CK(c, cudaMemcpyAsync(res_prim, b->res_prim, B * sizeof(double), kind, stream));
+    if (res_dual) CK(c, cudaMemcpyAsync(res_dual, b->res_dual, B * sizeof(double), kind, stream));
+    if (!(flags & SQPB200_DEVICE_PTRS)) CK(c, cudaStreamSynchronize(stream));
+    return SQPB200_OK;
+}
+
+int sqpb200_qp_batch_set_iterates(sqpb200_qp_batch *b, int count, const double *x, const double *y, const double *z,
+                                  unsigned flags, void *stream_) {
+    if (!b) return SQPB200_ERR_INVALID;
+    sqpb200_ctx *c = b->ctx;
+    if (count < 0 || count > b->batch) return fail(c, SQPB200_ERR_INVALID, "count outside [0, batch]");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;  // NULL is the CUDA legacy default stream
+    const cudaMemcpyKind kind = (flags & SQPB200_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    size_t B = count, n = b->n, m = b->m;
+    if (x) CK(c, cudaMemcpyAsync(b->x, x, B * n * sizeof(double), kind, stream));
+    if (y && m) CK(c, cudaMemcpyAsync(b->y, y, B * m * sizeof(double), kind, stream));
+    if (z && m) CK(c, cudaMemcpyAsync(b->z, z, B * m * sizeof(double), kind, stream));
+    if (!(flags & SQPB200_DEVICE_PTRS)) CK(c, cudaStreamSynchronize(stream));
+    return SQPB200_OK;
+}
+
+int sqpb200_qp_batch_device_view(sqpb200_qp_batch *b, sqpb200_qp_device_view *v) {
+    if (!b || !v) return SQPB200_ERR_INVALID;
+    v->x = b->x; v->y = b->y; v->z = b->z;
+    v->status = b->status; v->iter = b->iter; v->rho_updates = b->rho_updates;
+    v->rho_estimate = b->rho_estimate; v->res_prim = b->res_prim; v->res_dual = b->res_dual; v->rho = b->rho;
+    v->total_iters = (long long *)b->total_iters;
+    return SQPB200_OK;
+}
+
+int sqpb200_qp_batch_total_iters(sqpb200_qp_batch *b, long long *total, void *stream_) {
+    if (!b || !total) return SQPB200_ERR_INVALID;
+    sqpb200_ctx *c = b->ctx;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;  // NULL is the CUDA legacy default stream
+    unsigned long long v = 0;
+    CK(c, cudaMemcpyAsync(&v, b->total_iters, sizeof v, cudaMemcpyDeviceToHost, stream));
+    CK(c, cudaStreamSynchronize(stream));
+    *total = (long long)v;
+    return SQPB200_OK;
+}
+
+int sqpb200_qp_solve_batch(sqpb200_ctx *ctx, const sqpb200_qp_settings *settings, int batch, int n, int m, const double *P,
+                           const double *q, const double *A, const double *l, const double *u, double *x, double *y,
+                           double *z, int *status, int *iter, int *rho_updates, double *rho_estimate, double *res_prim,
+                           double *res_dual, unsigned flags, void *stream) {
+    sqpb200_qp_batch *b = nullptr;
+    int rc = sqpb200_qp_batch_create(ctx, batch, n, m, &b);
+    if (rc) return rc;
+    rc = sqpb200_qp_batch_setup_solve(b, settings, batch, P, q, A, l, u, flags, stream);
+    if (!rc) rc = sqpb200_qp_batch_get(b, batch, x, y, z, status, iter, rho_updates, rho_estimate, res_prim, res_dual, flags, stream);
+    if (!rc && (flags & SQPB200_DEVICE_PTRS)) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);  // the state is freed next
+        if (e != cudaSuccess) rc = fail(ctx, SQPB200_ERR_CUDA, "cudaStreamSynchronize", e);
+    }
+    sqpb200_qp_batch_destroy(b);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Shared host/device definitions of the batched QP-subproblem solver (sm_100a).
+//
+// Algorithm (per QP, fp64) -- the OSQP-style ADMM of reference src/qp.cpp:64-157, with the KKT
+// solve of qp.cpp:90 carried out by eliminating the diagonal (2,2) block of
+//     K = [[P + sigma I, A^T], [A, -diag(1/rho)]]                       (qp.hpp:177-188)
+// first.  That is an exact block LDL^T of a symmetric permutation of K:
+//     H = P_sym + sigma I + A^T diag(rho) A          (n x n Schur complement, SPD for convex QPs)
+//     H x~ = sigma x - q + A^T (rho .* z - y)        (rhs of qp.cpp:272-276 pushed through the block)
+//     nu   = rho .* (A x~ - z) + y   =>   z~ = z_prev + (nu - y) ./ rho = A x~      (qp.cpp:93)
+// H is factored as L D L^T in shared memory (no pivoting; NUMERICAL_ISSUES on a zero/NaN pivot,
+// which is when Eigen::LDLT::info() != Success), the unit factor is inverted once and
+// H^-1 = L^-T D^-1 L^-1 is applied per iteration as one dense symmetric mat-vec, so the ADMM
+// iteration has no serial substitution chain.  Like Eigen::LDLT<Lower> only the LOWER triangle
+// of P enters the factor, while P*x in the residuals (qp.cpp:323, :359) uses all of P.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sqp_b200_qp.h"
+
+namespace sqpb200 {
+
+// include/solvers/qp.hpp:136-141
+constexpr double RHO_MIN = 1e-6;
+constexpr double RHO_MAX = 1e+6;
+constexpr double RHO_TOL = 1e-4;
+constexpr double RHO_EQ_FACTOR = 1e+3;
+constexpr double LOOSE_BOUNDS_THRESH = 1e+16;
+constexpr double DIV_BY_ZERO_REGUL = 2.220446049250313e-16;  // numeric_limits<double>::epsilon()
+
+// what one launch does for every QP it processes
+enum : unsigned {
+    MODE_RESET = 1u,         // x = z = y = 0                                   (qp.cpp:16-18)
+    MODE_FACTOR = 2u,        // classify, rho vec from settings.rho, factor      (qp.cpp:31-43 / 48-61)
+    MODE_SOLVE = 4u,         // ADMM loop                                        (qp.cpp:64-157)
+    MODE_STORE_FACTOR = 8u,  // keep H^-1, rho, constraint classes for a later solve() launch
+    MODE_LOAD_FACTOR = 16u,  // solve() after a separate setup()/update_qp()
+};
+
+struct KernelParams {
+    int first;  // index of the first QP of this launch inside the batch arrays
+    int count;  // QPs in this launch
+    int n, m;
+    const double *P, *q, *A, *l, *u;  // batch-major inputs (already offset-free; kernels add first)
+    double *x, *z, *y;
+    int *status, *iter, *rho_updates;
+    double *rho_estimate, *res_prim, *res_dual, *rho;
+    signed char *ctype;  // [B][m] constraint classes of the last setup/update_qp
+    double *fact;        // [B][n*n] H^-1 (column-major, full symmetric); may be null when fused
+    double *scratch;     // generic kernel: per-CTA n*n workspace
+    int *work_counter;   // persistent-CTA work queue
+    unsigned long long *total_iters;
+    unsigned mode;
+    sqpb200_qp_settings s;
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ int classify(double l, double u) {  // qp.cpp:283-294
+    if (l < -LOOSE_BOUNDS_THRESH && u > LOOSE_BOUNDS_THRESH) return SQPB200_LOOSE_BOUNDS;
+    if (u - l < RHO_TOL) return SQPB200_EQUALITY_CONSTRAINT;
+    return SQPB200_INEQUALITY_CONSTRAINT;
+}
+__device__ __forceinline__ double rho_of(int type, double rho0) {  // qp.cpp:296-310
+    return type == SQPB200_LOOSE_BOUNDS ? RHO_MIN : (type == SQPB200_EQUALITY_CONSTRAINT ? RHO_EQ_FACTOR * rho0 : rho0);
+}
+// Eigen's z.cwiseMax(l).cwiseMin(u): std::max then std::min comparison forms (qp.cpp:278-281)
+__device__ __forceinline__ double box_project(double z, double l, double u) {
+    z = (z < l) ? l : z;
+    z = (u < z) ? u : z;
+    return z;
+}
+__device__ __forceinline__ double absmax(double r, double v) {
+    v = fabs(v);
+    return v > r ? v : r;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+// rho_estimate + clamp, qp.cpp:130-132 and :333-341
+__device__ __forceinline__ double rho_estimate_clamped(double rho, double rp, double rd, double sc_p, double sc_d) {
+    double rp_norm = rp / (sc_p + DIV_BY_ZERO_REGUL);
+    double rd_norm = rd / (sc_d + DIV_BY_ZERO_REGUL);
+    double r = rho * sqrt(rp_norm / (rd_norm + DIV_BY_ZERO_REGUL));
+    return fmax(RHO_MIN, fmin(r, RHO_MAX));
+}
+
+#endif  // __CUDACC__
+
+// launchers implemented in the kernel translation units
+cudaError_t launch_generic(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, int *grid_out);
+size_t generic_scratch_bytes(int n, int grid);
+int generic_grid(int count, int sm_count);
+bool generic_supported(int n, int m, size_t smem_optin);
+
+}  // namespace sqpb200

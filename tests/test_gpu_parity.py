@@ -1,0 +1,326 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes), against the CPU oracle on
+the same seeded inputs. Bar (BASELINE.json north_star): identical termination status (and, because
+termination is only tested every check_termination iterations, identical iteration count) and
+primal solution within 1e-6 relative. Every kernel variant is exercised."""
+import numpy as np
+import pytest
+
+from helpers import assert_parity, is_approx, oracle_settings_from
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from sqp_solver_b200 import api
+
+    return api
+
+
+@pytest.fixture(scope="module")
+def ctx(api):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+KERNELS = ["generic", "tile"]
+
+
+def select_kernel(api, ctx, kernel, n, m):
+    ctx.set_option(api.OPT_KERNEL, api.KERNEL_GENERIC if kernel == "generic" else api.KERNEL_TILE)
+
+
+@pytest.fixture(autouse=True)
+def _reset_kernel_option(api, ctx):
+    yield
+    ctx.set_option(api.OPT_KERNEL, api.KERNEL_AUTO)
+
+
+def run_fused(api, ctx, d, settings, kernel):
+    select_kernel(api, ctx, kernel, d["n"], d["m"])
+    b = api.QPBatch(ctx, d["batch"], d["n"], d["m"])
+    b.settings = settings
+    try:
+        b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"])
+    except api.SolverError as e:
+        if kernel == "tile" and "outside its range" in str(e):
+            pytest.skip("shape not covered by the register-tiled kernel")
+        raise
+    out = b.get()
+    out["kernel"] = ctx.last_kernel
+    out["total_iters"] = b.total_iters()
+    b.close()
+    return out
+
+
+def simple_qp_batch(golden, copies=1):
+    g = golden["simple_qp"]
+    P = np.array(g["P"], dtype=np.float64).reshape(-1, order="F")
+    A = np.array(g["A"], dtype=np.float64).reshape(-1, order="F")
+    rep = lambda v: np.ascontiguousarray(np.tile(np.asarray(v, dtype=np.float64), (copies, 1)))
+    return dict(P=rep(P), q=rep(g["q"]), A=rep(A), l=rep(g["l"]), u=rep(g["u"]), n=2, m=3, batch=copies)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_simple_qp_reference_cases(api, ctx, oracle, golden, kernel):
+    """tests/qp_solver_test.cpp:43-100 through the CUDA path, plus exact agreement with the oracle."""
+    d = simple_qp_batch(golden, copies=3)
+    e4 = float(np.float32(1e-4))
+    cases = {
+        "testSimpleQP": api.default_settings(max_iter=1000),
+        "testConstraintViolation": api.default_settings(eps_rel=e4, eps_abs=e4),
+        "testAdaptiveRho": api.default_settings(adaptive_rho=1, adaptive_rho_interval=10),
+        "sqp_ctor": api.sqp_ctor_settings(),
+    }
+    for name, s in cases.items():
+        out = run_fused(api, ctx, d, s, kernel)
+        ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+        assert_parity(out, ref, what=name)
+        for i in range(3):
+            assert out["status"][i] == api.SOLVED
+            assert out["iter"][i] < s.max_iter
+            assert is_approx(out["x"][i], golden["simple_qp"]["solution"], 1e-2)
+        if name == "testConstraintViolation":
+            A = np.array(golden["simple_qp"]["A"], dtype=float)
+            assert (A @ out["x"][0] - np.array(golden["simple_qp"]["l"])).min() >= -1e-3
+            assert (A @ out["x"][0] - np.array(golden["simple_qp"]["u"])).max() <= 1e-3
+        np.testing.assert_allclose(out["res_prim"], ref["res_prim"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(out["res_dual"], ref["res_dual"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(out["rho_estimate"], ref["rho_estimate"], rtol=1e-6)
+
+
+SHAPES = [(32, 64, 96), (64, 128, 48), (5, 7, 16), (17, 3, 8), (1, 1, 4), (40, 100, 8), (64, 20, 8), (3, 128, 8)]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n,m,batch", SHAPES)
+def test_synthetic_defaults_S1(api, ctx, oracle, kernel, n, m, batch):
+    """Reference default settings (S1 of SURVEY.md section 8d), configs 2 and 3 shapes plus ragged ones."""
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(batch, n, m, seed0=1000)
+    s = api.default_settings()
+    out = run_fused(api, ctx, d, s, kernel)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    worst = assert_parity(out, ref, what="S1 n=%d m=%d %s" % (n, m, out["kernel"]))
+    executed = np.minimum(ref["iter"], s.max_iter).sum()
+    assert out["total_iters"] == executed
+    print("S1", n, m, out["kernel"], "worst x rel err %.2e" % worst)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n,m,batch", [(32, 64, 96), (64, 128, 48), (5, 7, 16)])
+def test_synthetic_adaptive_S2(api, ctx, oracle, kernel, n, m, batch):
+    """alpha = 1.6 + adaptive rho every 25 iterations (S2): exercises in-kernel refactorisation."""
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(batch, n, m, seed0=2000)
+    s = api.default_settings(alpha=1.6, adaptive_rho=1)
+    out = run_fused(api, ctx, d, s, kernel)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    assert_parity(out, ref, what="S2 n=%d m=%d" % (n, m))
+    assert (ref["rho_updates"] > 1).any()
+    np.testing.assert_allclose(out["rho_estimate"], ref["rho_estimate"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_sqp_ctor_settings_interval_mismatch(api, ctx, oracle, kernel):
+    """check_termination=10 with adaptive_rho_interval=50 and max_iter=100 (src/sqp.cpp:16-23):
+    the adaptive block runs on iterations where a check also ran, and MAX_ITER gives iter=101."""
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(32, 16, 24, seed0=3000)
+    s = api.sqp_ctor_settings()
+    out = run_fused(api, ctx, d, s, kernel)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    assert_parity(out, ref, what="sqp ctor settings")
+    s2 = api.default_settings(adaptive_rho=1, adaptive_rho_interval=7, check_termination=5, max_iter=60)
+    out = run_fused(api, ctx, d, s2, kernel)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s2))
+    assert_parity(out, ref, what="interval 7 / check 5")
+    assert (ref["status"] == api.MAX_ITER_EXCEEDED).any() and (ref["iter"][ref["status"] == 1] == 61).all()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_object_api_setup_solve_solve_update(api, ctx, oracle, golden, kernel):
+    """setup(); solve(); solve() (warm, fact 0.4); update_qp(); solve() -- against the oracle object API,
+    mirroring tests/qp_solver_test.cpp:102-125 and the dead update_qp case of qp_solver_sparse_test.cpp."""
+    from sqp_solver_b200.synth import make_batch
+
+    select_kernel(api, ctx, kernel, 12, 20)
+    B, n, m = 6, 12, 20
+    d = make_batch(B, n, m, seed0=4000)
+    d2 = make_batch(B, n, m, seed0=5000)
+    b = api.QPBatch(ctx, B, n, m)
+    sols = [oracle.QPSolver() for _ in range(B)]
+    qps = [oracle.QuadraticProblem(d["P"][i].reshape(n, n, order="F"), d["q"][i], d["A"][i].reshape(m, n, order="F"),
+                                   d["l"][i], d["u"][i]) for i in range(B)]
+    qps2 = [oracle.QuadraticProblem(d2["P"][i].reshape(n, n, order="F"), d2["q"][i], d2["A"][i].reshape(m, n, order="F"),
+                                    d2["l"][i], d2["u"][i]) for i in range(B)]
+
+    def ref_state():
+        return dict(x=np.array([s.primal_solution() for s in sols]), y=np.array([s.dual_solution() for s in sols]),
+                    status=np.array([s.info().status for s in sols]), iter=np.array([s.info().iter for s in sols]),
+                    rho_updates=np.array([s.info().rho_updates for s in sols]))
+
+    args = (d["P"], d["q"], d["A"], d["l"], d["u"])
+    args2 = (d2["P"], d2["q"], d2["A"], d2["l"], d2["u"])
+    # solve() before setup(): silent no-op, status stays UNINITIALIZED (qp.cpp:68-71)
+    try:
+        b.solve(*args)
+    except api.SolverError as e:
+        if kernel == "tile" and "outside its range" in str(e):
+            pytest.skip("shape not covered by the register-tiled kernel")
+        raise
+    info = b.info()
+    assert (info["status"] == api.UNINITIALIZED).all() and (info["iter"] == 0).all()
+
+    b.settings.max_iter = 40  # first solve stops early: MAX_ITER_EXCEEDED with iter 41
+    b.setup(*args)
+    assert (b.info()["status"] == api.UNSOLVED).all()
+    for s, qp in zip(sols, qps):
+        s.settings().max_iter = 40
+        s.setup(qp)
+    b.solve(*args)
+    for s, qp in zip(sols, qps):
+        s.solve(qp)
+    assert_parity(b.get(), ref_state(), what="first solve")
+    # second solve warm-starts from the first (reference fact 0.4) with adaptive rho switched on
+    b.settings.max_iter = 1000
+    b.settings.adaptive_rho = 1
+    b.settings.adaptive_rho_interval = 10
+    b.solve(*args)
+    for s, qp in zip(sols, qps):
+        s.settings().max_iter = 1000
+        s.settings().adaptive_rho = 1
+        s.settings().adaptive_rho_interval = 10
+        s.solve(qp)
+    assert_parity(b.get(), ref_state(), what="second (warm) solve")
+    # third solve continues with the adapted rho and factor kept from the second
+    b.solve(*args)
+    for s, qp in zip(sols, qps):
+        s.solve(qp)
+    assert_parity(b.get(), ref_state(), what="third solve")
+    # update_qp with a different problem: no reset of x,z,y; rho back to settings.rho; rho_updates accumulates
+    b.update_qp(*args2)
+    assert (b.info()["status"] == api.UNSOLVED).all()
+    b.solve(*args2)
+    for s, qp in zip(sols, qps2):
+        s.update_qp(qp)
+        s.solve(qp)
+    assert_parity(b.get(), ref_state(), what="update_qp + solve")
+    b.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_numerical_issues_and_nan_inputs(api, ctx, oracle, kernel):
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(8, 6, 9, seed0=6000)
+    d["P"][2, 6 * 6 - 1] = np.nan  # NaN on the diagonal -> LDLT failure -> NUMERICAL_ISSUES (qp.cpp:39-43)
+    d["P"][5, 1] = np.nan  # NaN in the lower triangle
+    d["l"][3, 0] = -np.inf  # infinities pass through unchanged (tests/sqp_test_autodiff.cpp:97)
+    d["u"][3, 0] = 0.0
+    d["l"][4, 1] = -np.inf
+    d["u"][4, 1] = np.inf
+    s = api.default_settings()
+    out = run_fused(api, ctx, d, s, kernel)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    assert ref["status"][2] == api.NUMERICAL_ISSUES and ref["status"][5] == api.NUMERICAL_ISSUES
+    np.testing.assert_array_equal(out["status"], ref["status"])
+    np.testing.assert_array_equal(out["iter"], ref["iter"])
+    ok = ref["status"] != api.NUMERICAL_ISSUES
+    sub = lambda o: {k: (v[ok] if isinstance(v, np.ndarray) and v.shape[:1] == (8,) else v) for k, v in o.items()}
+    assert_parity(sub(out), sub(ref), what="finite instances next to NaN ones")
+    assert (out["x"][~ok] == 0).all()  # untouched cold-start iterates
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_max_iter_edge_cases(api, ctx, oracle, kernel):
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(4, 8, 10, seed0=7000)
+    for kw in (dict(max_iter=0), dict(max_iter=1), dict(check_termination=0, max_iter=30), dict(max_iter=25)):
+        s = api.default_settings(**kw)
+        out = run_fused(api, ctx, d, s, kernel)
+        ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+        assert_parity(out, ref, what=str(kw))
+
+
+def test_device_pointers_match_host_pointers(api, ctx):
+    import torch
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(40, 32, 64, seed0=8000)
+    s = api.default_settings()
+    host = run_fused(api, ctx, d, s, "auto")
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")}
+    b = api.QPBatch(ctx, 40, 32, 64)
+    b.setup_solve(dev["P"], dev["q"], dev["A"], dev["l"], dev["u"])
+    x = torch.empty(40, 32, dtype=torch.float64, device="cuda")
+    st = torch.empty(40, dtype=torch.int32, device="cuda")
+    it = torch.empty(40, dtype=torch.int32, device="cuda")
+    b.get_into(x=x, status=st, iter=it)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(x.cpu().numpy(), host["x"])
+    np.testing.assert_array_equal(st.cpu().numpy(), host["status"])
+    np.testing.assert_array_equal(it.cpu().numpy(), host["iter"])
+    # count < batch only touches the leading instances
+    b2 = api.QPBatch(ctx, 40, 32, 64)
+    b2.setup_solve(dev["P"], dev["q"], dev["A"], dev["l"], dev["u"], count=10)
+    o2 = b2.get()
+    np.testing.assert_array_equal(o2["x"][:10], host["x"][:10])
+    assert (o2["status"][10:] == api.UNINITIALIZED).all() and (o2["x"][10:] == 0).all()
+    b.close()
+    b2.close()
+
+
+def test_fused_then_solve_is_rejected(api, ctx):
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(2, 4, 4, seed0=1)
+    b = api.QPBatch(ctx, 2, 4, 4)
+    b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"])
+    with pytest.raises(api.SolverError, match="setup\\(\\) first"):
+        b.solve(d["P"], d["q"], d["A"], d["l"], d["u"])
+    b.close()
+
+
+def test_full_size_properties_config3(api, ctx, oracle):
+    """BASELINE config 3 at full size (batch 8192, n=64, m=128): size-independent properties on every
+    instance plus oracle parity on a seeded sample of 64."""
+    import torch
+    from sqp_solver_b200.synth import make_batch
+
+    B, n, m = 8192, 64, 128
+    d = make_batch(B, n, m, seed0=0)
+    s = api.default_settings()
+    out = run_fused(api, ctx, d, s, "auto")
+    assert set(np.unique(out["status"])) <= {api.SOLVED, api.MAX_ITER_EXCEEDED}
+    assert ((out["iter"] % 25 == 0) | (out["iter"] == 1001)).all()
+    assert (out["iter"][out["status"] == api.MAX_ITER_EXCEEDED] == 1001).all()
+    # recompute the termination test independently (torch fp64 on the GPU) from the returned x, z, y
+    P = torch.from_numpy(d["P"]).cuda().view(B, n, n).transpose(1, 2)  # column-major -> [B, row, col]
+    A = torch.from_numpy(d["A"]).cuda().view(B, n, m).transpose(1, 2)
+    q = torch.from_numpy(d["q"]).cuda()
+    x, y, z = (torch.from_numpy(out[k]).cuda() for k in ("x", "y", "z"))
+    Ax = torch.bmm(A, x.unsqueeze(2)).squeeze(2)
+    Px = torch.bmm(P, x.unsqueeze(2)).squeeze(2)
+    Aty = torch.bmm(A.transpose(1, 2), y.unsqueeze(2)).squeeze(2)
+    rp = (Ax - z).abs().amax(1)
+    rd = (Px + q + Aty).abs().amax(1)
+    ep = s.eps_abs + s.eps_rel * torch.maximum(Ax.abs().amax(1), z.abs().amax(1))
+    ed = s.eps_abs + s.eps_rel * torch.maximum(torch.maximum(Px.abs().amax(1), Aty.abs().amax(1)), q.abs().amax(1))
+    solved = torch.from_numpy(out["status"] == api.SOLVED).cuda()
+    ok = (rp <= ep * (1 + 1e-9)) & (rd <= ed * (1 + 1e-9))
+    assert bool((ok == solved).all()), "termination test disagrees on %d instances" % int((ok != solved).sum())
+    np.testing.assert_allclose(out["res_prim"], rp.cpu().numpy(), rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(out["res_dual"], rd.cpu().numpy(), rtol=1e-6, atol=1e-12)
+    # z is inside the box, y obeys the sign pattern of an active-set multiplier
+    l, u = torch.from_numpy(d["l"]).cuda(), torch.from_numpy(d["u"]).cuda()
+    assert bool(((z >= l) & (z <= u)).all())
+    idx = np.random.default_rng(123).choice(B, 64, replace=False)
+    ref = oracle.solve_batch(d["P"][idx], d["q"][idx], d["A"][idx], d["l"][idx], d["u"][idx], oracle_settings_from(oracle, s))
+    sub = {k: v[idx] for k, v in out.items() if isinstance(v, np.ndarray)}
+    assert_parity(sub, ref, what="config 3 sample")
