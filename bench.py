@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched QP-subproblem hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores (oracle)
+
+A "step" is one pass of the hot path (fresh setup + ADMM solve, reference src/sqp.cpp:221-222)
+over one batch of synthetic QPs: BASELINE.json configs[2], batch=8192 dense QPs n=64 m=128 fp64,
+reference default settings. One process per GPU (torchrun for N>1); the batch axis is sharded
+with no data-path collective (weak scaling: every rank solves its own 8192 QPs).
+
+Prints ONE JSON line (rank 0). Keys follow the driver's contract; see DESIGN.md section
+"Measurement" for how `roofline.achieved` is formed from the algorithmic bytes of SURVEY.md 8(d).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "QP-subproblems/sec (batch=8192, n=64, m=128)"
+UNIT = "QP/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--n", type=int, default=64)
+    ap.add_argument("--m", type=int, default=128)
+    ap.add_argument("--settings", default="S1", choices=["S1", "S2"],
+                    help="S1 = reference defaults (headline); S2 = alpha 1.6 + adaptive rho (SURVEY.md 8d)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tile"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(n, m, iters_executed, checks, factorizations, count):
+    """SURVEY.md 8(d) canonical accounting (fp64): per ADMM iteration A twice + packed chol(H) twice,
+    per termination check P and A once, per QP compulsory I/O, per (re)factorisation P and A once."""
+    b_iter = 16 * m * n + 8 * n * (n + 1)
+    b_check = 8 * (n * n + m * n)
+    b_io = 8 * (n * n + n + m * n + 2 * m) + 8 * (n + m) + 16
+    b_fact = 8 * (n * n + m * n)
+    return count * b_io + iters_executed * b_iter + checks * b_check + factorizations * b_fact
+
+
+def settings_kwargs(name):
+    return {} if name == "S1" else dict(alpha=1.6, adaptive_rho=1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]  # upper half: samples taken under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(d, settings_name, sample, steps=1):
+    """The reference algorithm (oracle restatement -- Eigen is absent, so kind='port') on this box's
+    host cores, OpenMP dynamic schedule over a bounded sample of the same workload."""
+    from oracle import qp_oracle as O
+
+    O.build()
+    cores = O.num_procs()
+    if sample <= 0:
+        sample = min(d["batch"], 64 * cores)
+    sl = slice(0, sample)
+    st = O.default_settings(**settings_kwargs(settings_name))
+    best, its = None, 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = O.solve_batch(d["P"][sl], d["q"][sl], d["A"][sl], d["l"][sl], d["u"][sl], st, nthreads=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        its = int(np.minimum(out["iter"], st.max_iter).sum())
+    return {"value": sample / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "first %d QPs of the same batch, %s, gcc -O2 oracle restatement of src/qp.cpp (Eigen absent), "
+                      "OpenMP schedule(dynamic) over %d threads, %.2f s" % (sample, settings_name, out["threads"], best),
+            "admm_iters_per_s": its / best, "seconds": best}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from sqp_solver_b200.synth import make_batch
+    from oracle import qp_oracle as O
+
+    O.build()
+    cores = O.num_procs()
+    sample = args.cpu_sample or min(args.batch, 64 * cores)
+    d = make_batch(sample, args.n, args.m, seed0=0)
+    st = O.default_settings(**settings_kwargs(args.settings))
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], st, nthreads=cores)
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        out = O.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], st, nthreads=cores)
+        its += int(np.minimum(out["iter"], st.max_iter).sum())
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: batch=8192 dense QPs n=%d m=%d fp64, settings %s; each step is a bounded "
+                                   "sample of %d QPs of that batch on host cores" % (args.n, args.m, args.settings, sample)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d QPs per step, gcc -O2 oracle restatement of src/qp.cpp (Eigen absent from the image, "
+                                       "so the reference cannot be compiled), OpenMP over %d threads" % (sample, out["threads"])},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "admm_iters_per_s": its / dt, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from sqp_solver_b200 import api
+    from sqp_solver_b200.synth import make_batch
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = api.Context(local_rank)
+    ctx.set_option(api.OPT_KERNEL, {"auto": 0, "generic": 1, "tile": 2}[args.kernel])
+    B, n, m = args.batch, args.n, args.m
+    d = make_batch(B, n, m, seed0=rank * B)  # every rank owns a disjoint shard of the seed sequence
+    settings = api.default_settings(**settings_kwargs(args.settings))
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")}
+    qb = api.QPBatch(ctx, B, n, m)
+    qb.settings = settings
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        qb.setup_solve(dev["P"], dev["q"], dev["A"], dev["l"], dev["u"], stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    total_iters = qb.total_iters()
+    info = qb.get(fields=("status", "iter", "rho_updates"))
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([float(total_iters), float(B)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    all_iters, all_qps = float(agg[0].item()), float(agg[1].item())
+
+    # ---- end to end: host (pinned) buffers through the C-ABI, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ("P", "q", "A", "l", "u")}
+        hp = {k: v.numpy() for k, v in pin.items()}
+        ox = torch.empty(B, n, dtype=torch.float64).pin_memory()
+        oy = torch.empty(B, m, dtype=torch.float64).pin_memory()
+        ost = torch.empty(B, dtype=torch.int32).pin_memory()
+        oit = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def step_host():
+            qb.setup_solve(hp["P"], hp["q"], hp["A"], hp["l"], hp["u"])
+            qb.get_into(x=ox.numpy(), y=oy.numpy(), status=ost.numpy(), iter=oit.numpy())
+
+        for _ in range(min(args.warmup, 2)):
+            step_host()
+        barrier()
+        l0 = ctx.launch_count
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_launches = ctx.launch_count - l0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        assert (ost.numpy() == info["status"]).all() and (oit.numpy() == info["iter"]).all()
+        e2e = {"value": all_qps * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": 8 * B * (n * n + n + m * n + 2 * m), "d2h_bytes_per_step": B * (8 * (n + m) + 8),
+               "ms_per_step": 1e3 * dt / args.steps, "launches": e2e_launches,
+               "how": "pinned host buffers -> sqpb200_qp_batch_setup_solve(HOST_PTRS) (chunked H2D overlapped with the solve) "
+                      "-> sqpb200_qp_batch_get to pinned host; wall clock between device synchronisations, max over ranks"}
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    executed = np.minimum(info["iter"], settings.max_iter).astype(np.int64)
+    executed[info["status"] == api.NUMERICAL_ISSUES] = 0
+    ct = settings.check_termination
+    checks = int((executed // ct).sum()) if ct > 0 else 0
+    facts = int(info["rho_updates"].sum())
+    bytes_per_launch = algorithmic_bytes(n, m, int(executed.sum()), checks, facts, B)
+    sec_per_launch = ms / 1e3 / args.steps  # rank 0's own kernel time
+    peak, peak_src = peaks()
+    achieved = bytes_per_launch / sec_per_launch / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("%s_%dx%d_b%d_%s" % (ctx.last_kernel, n, m, B, args.settings))
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": all_qps * args.steps / (ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: batch=%d dense QPs n=%d m=%d fp64 per GPU, settings %s (%s), fresh setup+solve per step"
+                               % (B, n, m, args.settings, "reference defaults qp.hpp:38-53" if args.settings == "S1" else
+                                  "alpha=1.6 adaptive_rho"),
+                   "batch_per_gpu": B, "n": n, "m": m, "kernel": ctx.last_kernel, "parallelism": "batch-sharded x%d, no collective on the data path" % world,
+                   "l2": "inputs are %.0f MB per step, larger than the 126 MB L2" % (8 * B * (n * n + n + m * n + 2 * m) / 1e6)},
+        "admm_iters_per_s": all_iters / (ms_max / 1e3 / args.steps),
+        "admm_iters_per_step": all_iters,
+        "status_histogram": {api.STATUS_NAMES[k]: int((info["status"] == k).sum()) for k in np.unique(info["status"])},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "kernel_ms": 1e3 * sec_per_launch,
+                     "note": "algorithmic bytes of SURVEY.md 8(d); the working set is register/shared-memory resident, so measured "
+                             "DRAM traffic is far below this and frac can exceed 1 (see DESIGN.md)"},
+        "clocks": clocks,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(d, args.settings, args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
