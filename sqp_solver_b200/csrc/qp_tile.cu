@@ -1,5 +1,628 @@
+// Register-tiled batched ADMM QP kernel for sm_100a: the fast path for n <= 64, m <= 128.
+//
+// One CTA (NW warps) per QP, persistent CTAs on an atomic work queue.  Per QP:
+//   * A (m x n) lives in REGISTERS for the whole solve: warp w owns MP/NW consecutive rows, a lane
+//     owns an R x C tile (R rows, C interleaved column pairs).  Both per-iteration mat-vecs,
+//     g = A^T w (reduce over rows) and z~ = A x~ (reduce over columns), run from registers;
+//     partial sums are combined with warp-shuffle reduce-scatter trees, so after A x~ each row's
+//     z, y, l, u, rho live in the registers of the lane that owns the row.
+//   * H^-1 = (P_sym + sigma I + A^T diag(rho) A)^-1 lives in shared memory (padded columns,
+//     conflict-free LDS.128); x~ = H^-1 b is one dense symmetric mat-vec with a 3-step shuffle tree.
+//     H is formed by a register-blocked SYRK from a shared-memory staging copy of A and is
+//     factored in registers by symmetric pivot-by-pivot elimination (the pivots are exactly the D of
+//     the LDL^T of H; a zero/NaN pivot reports NUMERICAL_ISSUES) that is carried through to the
+//     inverse, so the ADMM loop has no serial substitution chain.
+//   * P lives in shared memory for the residual checks (P*x uses all of P, qp.cpp:323).
+// Reference functions covered: identical list to qp_generic.cu (all of src/qp.cpp:11-371).
+#include <cstdio>
+
 #include "qp_tile.cuh"
+
 namespace sqpb200 {
-bool tile_supported(int, int) { return false; }
-cudaError_t launch_tile(const KernelParams &, int, int, cudaStream_t, char *, size_t) { return cudaErrorNotSupported; }
+
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int NP_, int MP_, int NW_, int LC_, int MINB_>
+struct TileCfg {
+    static constexpr int NP = NP_, MP = MP_, NW = NW_, LC = LC_, MINB = MINB_;
+    static constexpr int T = 32 * NW;
+    static constexpr int LR = 32 / LC;   // lanes along the row direction inside a warp
+    static constexpr int RW = MP / NW;   // rows per warp
+    static constexpr int R = RW / LR;    // rows per lane
+    static constexpr int C = NP / LC;    // columns per lane
+    static constexpr int RO = (R >= LC) ? R / LC : 1;  // rows a lane owns after the A x~ reduce-scatter
+    static constexpr int CO = (C >= LR) ? C / LR : 1;  // columns a lane holds after the A^T w reduce-scatter
+    static constexpr int CG = T / (NP / 2);             // lanes sharing a row pair in the symmetric mat-vec
+    static constexpr int HC = NP / CG;                  // columns per lane there
+    static constexpr int HS = NP + 16 / CG;             // padded column stride of H^-1 / P in smem
+    static constexpr int LS = MP + 2;                   // padded column stride of the A staging copy
+    static_assert(MP % NW == 0 && RW % LR == 0 && R >= 1, "row tiling");
+    static_assert(NP % LC == 0 && C >= 2 && C % 2 == 0, "column tiling");
+    static_assert(CG >= 2 && CG <= 16 && (CG & (CG - 1)) == 0 && NP % CG == 0, "symmetric mat-vec tiling");
+    static_assert(R == 1 || R % 2 == 0, "row tile must be vectorisable");
+    static_assert(NP * LS <= 2 * NP * HS, "A staging must fit in the H^-1 + P regions");
+    static_assert(T >= NP, "b stage needs one thread per variable");
+    // shared memory carve-up (doubles)
+    static constexpr int OFF_H = 0;
+    static constexpr int OFF_P = OFF_H + NP * HS;
+    static constexpr int OFF_PART = OFF_P + NP * HS;
+    static constexpr int OFF_X = OFF_PART + NW * NP;
+    static constexpr int OFF_XT = OFF_X + NP;
+    static constexpr int OFF_B = OFF_XT + NP;
+    static constexpr int OFF_Q = OFF_B + NP;
+    static constexpr int OFF_PX = OFF_Q + NP;
+    static constexpr int OFF_W = OFF_PX + NP;
+    static constexpr int OFF_RHO = OFF_W + MP;
+    static constexpr int OFF_PIV = OFF_RHO + MP;
+    static constexpr int OFF_RED = OFF_PIV + 2 * NP;
+    static constexpr int SMEM_DOUBLES = OFF_RED + 8 * NW;
+    static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
+};
+
+template <int NW>
+__device__ __forceinline__ void cta_sync() {
+    if constexpr (NW == 1) __syncwarp();
+    else __syncthreads();
+}
+
+// Reduce-scatter over the lanes whose ids differ in the bits HI..LO (powers of two): every step
+// halves the number of live values per lane; once one value is left the remaining steps are a
+// plain butterfly (the result is then duplicated over those lanes).
+template <int V, int HI, int LO>
+struct Halve {
+    static __device__ __forceinline__ void run(double *v, int lane) {
+        if constexpr (HI >= LO && HI >= 1) {
+            if constexpr (V > 1) {
+                const bool up = (lane & HI) != 0;
+#pragma unroll
+                for (int k = 0; k < V / 2; ++k) {
+                    const double send = up ? v[k] : v[k + V / 2];
+                    const double keep = up ? v[k + V / 2] : v[k];
+                    v[k] = keep + __shfl_xor_sync(FULL, send, HI);
+                }
+                Halve<V / 2, HI / 2, LO>::run(v, lane);
+            } else {
+                v[0] += __shfl_xor_sync(FULL, v[0], HI);
+                Halve<1, HI / 2, LO>::run(v, lane);
+            }
+        }
+    }
+};
+// index (into the original V values) of the first value this lane ends up with, and whether this
+// lane is the primary copy among duplicates
+template <int V, int HI, int LO>
+__device__ __forceinline__ int halve_base(int lane, bool &primary) {
+    int base = 0, v = V;
+    primary = true;
+#pragma unroll
+    for (int mask = HI; mask >= LO && mask >= 1; mask >>= 1) {
+        if (v > 1) {
+            v >>= 1;
+            if (lane & mask) base += v;
+        } else if (lane & mask) {
+            primary = false;
+        }
+    }
+    return base;
+}
+template <class Cfg>
+struct Tile {
+    static constexpr int NP = Cfg::NP, MP = Cfg::MP, NW = Cfg::NW, LC = Cfg::LC, LR = Cfg::LR, T = Cfg::T;
+    static constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CO = Cfg::CO, CG = Cfg::CG, HC = Cfg::HC;
+    static constexpr int HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
+
+    // column (0..NP) of the kk-th entry of this lane's A tile: interleaved pairs so that the x~ loads
+    // of one warp form contiguous 16-byte chunks
+    static __device__ __forceinline__ int colA(int lc, int kk) { return 2 * lc + 2 * LC * (kk >> 1) + (kk & 1); }
+
+    // ---- z~ = A v (v in shared memory); result: RO fully reduced rows per lane -----------------
+    static __device__ __forceinline__ void mv_A(const double (&a)[R][C], const double *sv, int lc, int lane, double (&out)[RO]) {
+        double acc[R];
+#pragma unroll
+        for (int kr = 0; kr < R; ++kr) acc[kr] = 0.0;
+#pragma unroll
+        for (int t = 0; t < C / 2; ++t) {
+            const double2 xv = *reinterpret_cast<const double2 *>(sv + 2 * lc + 2 * LC * t);
+#pragma unroll
+            for (int kr = 0; kr < R; ++kr) {
+                acc[kr] = fma(a[kr][2 * t], xv.x, acc[kr]);
+                acc[kr] = fma(a[kr][2 * t + 1], xv.y, acc[kr]);
+            }
+        }
+        Halve<R, LC / 2, 1>::run(acc, lane);
+#pragma unroll
+        for (int t = 0; t < RO; ++t) out[t] = acc[t];
+    }
+
+    // ---- partial g = A^T v over this warp's rows -> part[warp][*] -------------------------------
+    // v for the lane's R rows is read from sw (written by the row owners just before)
+    static __device__ __forceinline__ void mv_At(const double (&a)[R][C], const double *sw, double *part_w, int row0,
+                                                 int lc, int lane) {
+        double wv[R];
+        if constexpr (R >= 2) {
+#pragma unroll
+            for (int kr = 0; kr < R; kr += 2) {
+                const double2 t2 = *reinterpret_cast<const double2 *>(sw + row0 + kr);
+                wv[kr] = t2.x;
+                wv[kr + 1] = t2.y;
+            }
+        } else {
+            wv[0] = sw[row0];
+        }
+        double acc[C];
+#pragma unroll
+        for (int kk = 0; kk < C; ++kk) {
+            double s = 0.0;
+#pragma unroll
+            for (int kr = 0; kr < R; ++kr) s = fma(a[kr][kk], wv[kr], s);
+            acc[kk] = s;
+        }
+        Halve<C, 16, LC>::run(acc, lane);
+        bool primary;
+        const int kb = halve_base<C, 16, LC>(lane, primary);
+        if (primary) {
+            if constexpr (CO >= 2) {
+#pragma unroll
+                for (int t = 0; t < CO; t += 2)
+                    *reinterpret_cast<double2 *>(part_w + colA(lc, kb + t)) = make_double2(acc[t], acc[t + 1]);
+            } else {
+                part_w[colA(lc, kb)] = acc[0];
+            }
+        }
+    }
+
+    // ---- y = M v for a padded column-major NP x NP matrix in smem; each row ends on CG/2 lanes ---
+    static __device__ __forceinline__ double mv_sym(const double *sM, const double *sv, int rp, int cg, int lane, int &row,
+                                                    bool &primary) {
+        double acc[2] = {0.0, 0.0};
+#pragma unroll
+        for (int s = 0; s < HC; ++s) {
+            const int k = cg + CG * s;
+            const double2 mv = *reinterpret_cast<const double2 *>(sM + 2 * rp + HS * k);
+            const double bv = sv[k];
+            acc[0] = fma(mv.x, bv, acc[0]);
+            acc[1] = fma(mv.y, bv, acc[1]);
+        }
+        Halve<2, CG / 2, 1>::run(acc, lane);
+        const int kb = halve_base<2, CG / 2, 1>(lane, primary);
+        row = 2 * rp + kb;
+        return acc[0];
+    }
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams p) {
+    using TL = Tile<Cfg>;
+    constexpr int NP = Cfg::NP, MP = Cfg::MP, NW = Cfg::NW, LC = Cfg::LC, T = Cfg::T;
+    constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CG = Cfg::CG, HC = Cfg::HC, HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_qp, s_fail;
+    double *sH = smem + Cfg::OFF_H, *sP = smem + Cfg::OFF_P, *sA = smem + Cfg::OFF_H;  // sA aliases sH+sP
+    double *part = smem + Cfg::OFF_PART, *sx = smem + Cfg::OFF_X, *sxt = smem + Cfg::OFF_XT, *sb = smem + Cfg::OFF_B;
+    double *sq = smem + Cfg::OFF_Q, *spx = smem + Cfg::OFF_PX, *sw = smem + Cfg::OFF_W, *srho = smem + Cfg::OFF_RHO;
+    double *piv = smem + Cfg::OFF_PIV, *red = smem + Cfg::OFF_RED;
+
+    const int n = p.n, m = p.m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lc = lane % LC, lr = lane / LC;
+    const int row0 = warp * RW + lr * R;  // first row of this lane's A tile
+    bool row_primary;
+    const int own0 = row0 + halve_base<R, LC / 2, 1>(lane, row_primary);  // first owned row after A x~
+    const int rp = tid / CG, cg = tid % CG;                                // symmetric mat-vec coordinates
+    const sqpb200_qp_settings st = p.s;
+    const double sigma = st.sigma, alpha = st.alpha;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (;;) {
+        cta_sync<NW>();
+        if (tid == 0) s_qp = atomicAdd(p.work_counter, 1);
+        cta_sync<NW>();
+        const int local = s_qp;
+        if (local >= p.count) break;
+        const size_t b = (size_t)p.first + local;
+        const double *__restrict__ gP = p.P + b * n * n;
+        const double *__restrict__ gA = p.A + b * m * n;
+        const double *__restrict__ gq = p.q + b * n;
+        const double *__restrict__ gl = p.l + b * m;
+        const double *__restrict__ gu = p.u + b * m;
+
+        int status = p.status[b];
+        int rho_updates = p.rho_updates[b];
+        double rho_est = p.rho_estimate[b], res_prim = p.res_prim[b], res_dual = p.res_dual[b];
+        double rho = p.rho[b];
+        int iter_out = p.iter[b];
+        const bool reset = (p.mode & MODE_RESET) != 0;
+
+        // ---- per-row state in the owner lanes' registers ----------------------------------------
+        double zr[RO], yr[RO], lo[RO], up[RO], rhor[RO], rinv[RO], axr[RO];
+        int typ[RO];
+#pragma unroll
+        for (int t = 0; t < RO; ++t) {
+            const int i = own0 + t;
+            const bool real = i < m;
+            lo[t] = real ? gl[i] : -INF;
+            up[t] = real ? gu[i] : INF;
+            zr[t] = (real && !reset) ? p.z[b * m + i] : 0.0;
+            yr[t] = (real && !reset) ? p.y[b * m + i] : 0.0;
+            axr[t] = 0.0;
+            if (p.mode & MODE_FACTOR) {
+                typ[t] = classify(lo[t], up[t]);
+                if (real && row_primary) p.ctype[b * m + i] = (signed char)typ[t];
+            } else {
+                typ[t] = real ? p.ctype[b * m + i] : SQPB200_LOOSE_BOUNDS;
+            }
+        }
+        if (p.mode & MODE_FACTOR) {
+            rho = st.rho;
+            rho_updates += 1;  // rho_vec_update, qp.cpp:313
+        }
+#pragma unroll
+        for (int t = 0; t < RO; ++t) {
+            rhor[t] = rho_of(typ[t], rho);
+            rinv[t] = 1.0 / rhor[t];
+        }
+        if (tid < NP) {
+            sq[tid] = tid < n ? gq[tid] : 0.0;
+            sx[tid] = (tid < n && !reset) ? p.x[b * n + tid] : 0.0;
+        }
+
+        // ---- stage A (zero padded) and pull this lane's tile into registers -----------------------
+        double a[R][C];
+        auto stage_A = [&]() {
+            for (int e = tid; e < NP * MP; e += T) {
+                const int i = e % MP, j = e / MP;
+                sA[i + LS * j] = (i < m && j < n) ? gA[i + (size_t)m * j] : 0.0;
+            }
+        };
+        auto load_P = [&]() {
+            for (int e = tid; e < NP * NP; e += T) {
+                const int i = e % NP, j = e / NP;
+                sP[i + HS * j] = (i < n && j < n) ? gP[i + (size_t)n * j] : 0.0;
+            }
+        };
+        // H^-1 from the staged A: SYRK into registers, symmetric elimination, write -S to sH.
+        // Requires sA staged and srho written; ends with sH and sP valid and the CTA synchronised.
+        auto factorize = [&]() -> bool {
+            double S0[HC], S1[HC];
+            const int i0 = 2 * rp, i1 = 2 * rp + 1;
+#pragma unroll
+            for (int s = 0; s < HC; ++s) {
+                const int j = cg + CG * s;
+                // lower triangle of P mirrored (LDLT<Lower> reads nothing else), + sigma on the diagonal;
+                // padded variables get a unit diagonal block
+                auto h0 = [&](int i) -> double {
+                    if (i >= n || j >= n) return i == j ? 1.0 : 0.0;
+                    const double v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
+                    return i == j ? v + sigma : v;
+                };
+                S0[s] = h0(i0);
+                S1[s] = h0(i1);
+            }
+            const int mloop = (m + 1) / 2;
+            for (int kp = 0; kp < mloop; ++kp) {
+                const double2 rr = *reinterpret_cast<const double2 *>(srho + 2 * kp);
+                double2 a0 = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * i0);
+                double2 a1 = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * i1);
+                a0.x *= rr.x; a0.y *= rr.y; a1.x *= rr.x; a1.y *= rr.y;
+#pragma unroll
+                for (int s = 0; s < HC; ++s) {
+                    const double2 cj = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (cg + CG * s));
+                    S0[s] = fma(a0.x, cj.x, S0[s]);
+                    S0[s] = fma(a0.y, cj.y, S0[s]);
+                    S1[s] = fma(a1.x, cj.x, S1[s]);
+                    S1[s] = fma(a1.y, cj.y, S1[s]);
+                }
+            }
+            if (tid == 0) s_fail = 0;
+            cta_sync<NW>();  // everyone is done with sA; sH/sP may be overwritten from here on
+            // symmetric elimination, pivot by pivot; after step k rows/cols <= k hold -(H_kk block)^-1 parts
+            bool ok = true;
+#pragma unroll
+            for (int s = 0; s < HC; ++s) {
+#pragma unroll 1
+                for (int cgk = 0; cgk < CG; ++cgk) {
+                    const int k = cgk + CG * s;
+                    double *pv = piv + (k & 1) * NP;
+                    if (cg == cgk) {
+                        pv[i0] = S0[s];
+                        pv[i1] = S1[s];
+                    }
+                    cta_sync<NW>();
+                    const double d = pv[k];
+                    if (!(fabs(d) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
+                        ok = false;
+                        break;
+                    }
+                    const double inv_d = 1.0 / d;
+                    const double2 ci = *reinterpret_cast<const double2 *>(pv + i0);
+                    const double t0 = ci.x * inv_d, t1 = ci.y * inv_d;
+#pragma unroll
+                    for (int s2 = 0; s2 < HC; ++s2) {
+                        const double cj = pv[cg + CG * s2];
+                        double v0 = fma(-t0, cj, S0[s2]);
+                        double v1 = fma(-t1, cj, S1[s2]);
+                        if (i0 == k) v0 = cj * inv_d;
+                        if (i1 == k) v1 = cj * inv_d;
+                        S0[s2] = v0;
+                        S1[s2] = v1;
+                    }
+                    if (cg == cgk) {
+                        S0[s] = (i0 == k) ? -inv_d : t0;
+                        S1[s] = (i1 == k) ? -inv_d : t1;
+                    }
+                }
+                if (!ok) break;
+            }
+            cta_sync<NW>();
+            if (ok) {
+#pragma unroll
+                for (int s = 0; s < HC; ++s)
+                    *reinterpret_cast<double2 *>(sH + i0 + HS * (cg + CG * s)) = make_double2(-S0[s], -S1[s]);
+            }
+            load_P();
+            cta_sync<NW>();
+            return ok;
+        };
+
+        cta_sync<NW>();
+        stage_A();
+        if (row_primary) {
+#pragma unroll
+            for (int t = 0; t < RO; ++t) srho[own0 + t] = rhor[t];
+        }
+        cta_sync<NW>();
+#pragma unroll
+        for (int kk = 0; kk < C; ++kk) {
+            const double *colp = sA + row0 + LS * TL::colA(lc, kk);
+            if constexpr (R >= 2) {
+#pragma unroll
+                for (int kr = 0; kr < R; kr += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2 *>(colp + kr);
+                    a[kr][kk] = t2.x;
+                    a[kr + 1][kk] = t2.y;
+                }
+            } else {
+                a[0][kk] = colp[0];
+            }
+        }
+        bool do_factor = (p.mode & MODE_FACTOR) != 0, staged = true, in_solve = false;
+        if (!do_factor) {
+            cta_sync<NW>();  // tiles are in registers; the staging area may be overwritten
+            const double *gF = p.fact + b * n * n;
+            for (int e = tid; e < NP * NP; e += T) {
+                const int i = e % NP, j = e / NP;
+                sH[i + HS * j] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? 1.0 : 0.0);
+            }
+            load_P();
+            cta_sync<NW>();
+            staged = false;  // the staging copy of A has just been overwritten
+        }
+
+        long long executed = 0;
+        int iter = 0;
+        // Outer loop: one (re)factorisation, then ADMM iterations until convergence, max_iter, or the
+        // next adaptive-rho refactorisation.  A single factorisation call site keeps the code compact.
+        for (;;) {
+            if (do_factor) {
+                if (!staged) {
+                    cta_sync<NW>();  // all reads of sH/sP done before the staging overwrites them
+                    stage_A();
+                    if (row_primary) {
+#pragma unroll
+                        for (int t = 0; t < RO; ++t) srho[own0 + t] = rhor[t];
+                    }
+                    cta_sync<NW>();
+                }
+                const bool ok = factorize();
+                staged = false;
+                do_factor = false;
+                if (!in_solve) {
+                    status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+                } else if (!ok) {
+                    status = SQPB200_NUMERICAL_ISSUES;  // qp.cpp:139-142 (break before the loop increment)
+                    iter -= 1;
+                    break;
+                }
+            }
+            if (!in_solve) {
+                if (!((p.mode & MODE_SOLVE) && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES)) break;
+                in_solve = true;
+                iter = 1;
+                if (!reset) {  // A x for the warm-start iterate (ax is then carried by recurrence)
+                    double t0[RO];
+                    TL::mv_A(a, sx, lc, lane, t0);
+#pragma unroll
+                    for (int t = 0; t < RO; ++t) axr[t] = t0[t];
+                }
+            }
+            bool refactor = false;
+            for (; iter <= st.max_iter; ++iter) {
+                // P1: w = rho .* z - y (owner lanes) -> sw; partial A^T w over this warp's rows -> part[warp]
+                if (row_primary) {
+#pragma unroll
+                    for (int t = 0; t < RO; ++t) sw[own0 + t] = rhor[t] * zr[t] - yr[t];
+                }
+                __syncwarp();
+                TL::mv_At(a, sw, part + warp * NP, row0, lc, lane);
+                cta_sync<NW>();
+                // P2: b = sigma x - q + A^T w   (rhs of qp.cpp:272-276 pushed through the (2,2) block)
+                if (tid < NP) {
+                    double g = part[tid];
+#pragma unroll
+                    for (int w2 = 1; w2 < NW; ++w2) g += part[w2 * NP + tid];
+                    sb[tid] = sigma * sx[tid] - sq[tid] + g;
+                }
+                cta_sync<NW>();
+                // P3: x~ = H^-1 b ; x = alpha x~ + (1 - alpha) x   (qp.cpp:90-96)
+                {
+                    int row;
+                    bool prim;
+                    const double xt = TL::mv_sym(sH, sb, rp, cg, lane, row, prim);
+                    if (prim) {
+                        sxt[row] = xt;
+                        sx[row] = alpha * xt + (1.0 - alpha) * sx[row];
+                    }
+                }
+                cta_sync<NW>();
+                // P4: z~ = A x~ ; z, y updates in the owner lanes (qp.cpp:93-103)
+                {
+                    double zt[RO];
+                    TL::mv_A(a, sxt, lc, lane, zt);
+#pragma unroll
+                    for (int t = 0; t < RO; ++t) {
+                        const double zh = alpha * zt[t] + (1.0 - alpha) * zr[t];
+                        const double zn = box_project(zh + rinv[t] * yr[t], lo[t], up[t]);
+                        yr[t] = yr[t] + rhor[t] * (zh - zn);
+                        zr[t] = zn;
+                        axr[t] = alpha * zt[t] + (1.0 - alpha) * axr[t];  // A x by linearity of the x update
+                    }
+                }
+                const bool chk = st.check_termination != 0 && iter % st.check_termination == 0;
+                const bool adapt = st.adaptive_rho && st.adaptive_rho_interval > 0 && iter % st.adaptive_rho_interval == 0;
+                if (chk || adapt) {
+                    // update_state, qp.cpp:316-331
+                    double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
+#pragma unroll
+                    for (int t = 0; t < RO; ++t) {
+                        mx[0] = absmax(mx[0], axr[t]);
+                        mx[1] = absmax(mx[1], zr[t]);
+                        mx[5] = absmax(mx[5], axr[t] - zr[t]);
+                    }
+                    if (row_primary) {
+#pragma unroll
+                        for (int t = 0; t < RO; ++t) sw[own0 + t] = yr[t];
+                    }
+                    __syncwarp();
+                    TL::mv_At(a, sw, part + warp * NP, row0, lc, lane);
+                    {
+                        int row;
+                        bool prim;
+                        const double px = TL::mv_sym(sP, sx, rp, cg, lane, row, prim);
+                        if (prim) spx[row] = px;
+                    }
+                    cta_sync<NW>();
+                    if (tid < NP) {
+                        double aty = part[tid];
+#pragma unroll
+                        for (int w2 = 1; w2 < NW; ++w2) aty += part[w2 * NP + tid];
+                        const double px = spx[tid], qv = sq[tid];
+                        mx[2] = absmax(mx[2], px);
+                        mx[3] = absmax(mx[3], aty);
+                        mx[4] = absmax(mx[4], qv);
+                        mx[6] = absmax(mx[6], px + qv + aty);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const double v = warp_max(mx[k]);
+                        if (lane == 0) red[k * NW + warp] = v;
+                    }
+                    cta_sync<NW>();
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        double v = red[k * NW];
+#pragma unroll
+                        for (int w2 = 1; w2 < NW; ++w2) v = red[k * NW + w2] > v ? red[k * NW + w2] : v;
+                        mx[k] = v;
+                    }
+                    const double sc_p = fmax(mx[0], mx[1]);
+                    const double sc_d = fmax(mx[2], fmax(mx[3], mx[4]));
+                    res_prim = mx[5];
+                    res_dual = mx[6];
+                    if (chk) {  // termination_criteria, qp.cpp:363-371
+                        if (res_prim <= st.eps_abs + st.eps_rel * sc_p && res_dual <= st.eps_abs + st.eps_rel * sc_d) {
+                            status = SQPB200_SOLVED;
+                            break;
+                        }
+                    }
+                    if (adapt) {  // qp.cpp:125-144
+                        const double new_rho = rho_estimate_clamped(rho, res_prim, res_dual, sc_p, sc_d);
+                        rho_est = new_rho;
+                        if (new_rho < rho / st.adaptive_rho_tolerance || new_rho > rho * st.adaptive_rho_tolerance) {
+                            rho = new_rho;
+                            rho_updates += 1;
+#pragma unroll
+                            for (int t = 0; t < RO; ++t) {
+                                rhor[t] = rho_of(typ[t], rho);
+                                rinv[t] = 1.0 / rhor[t];
+                            }
+                            refactor = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            if (!refactor) break;
+            ++iter;  // the reference finishes the iteration (loop increment) after refactoring
+            do_factor = true;
+        }
+        if (in_solve) {
+            executed = iter <= st.max_iter ? iter : st.max_iter;
+            if (iter > st.max_iter) status = SQPB200_MAX_ITER_EXCEEDED;  // qp.cpp:147-149
+            iter_out = iter;                                            // qp.cpp:150
+        }
+
+        // ---- write back -----------------------------------------------------------------------------
+        cta_sync<NW>();
+        if (tid < n) p.x[b * n + tid] = sx[tid];
+        if (row_primary) {
+#pragma unroll
+            for (int t = 0; t < RO; ++t) {
+                const int i = own0 + t;
+                if (i < m) {
+                    p.z[b * m + i] = zr[t];
+                    p.y[b * m + i] = yr[t];
+                }
+            }
+        }
+        if ((p.mode & MODE_STORE_FACTOR) && status != SQPB200_NUMERICAL_ISSUES && status != SQPB200_UNINITIALIZED) {
+            double *gF = p.fact + b * n * n;
+            for (int e = tid; e < n * n; e += T) {
+                const int i = e % n, j = e / n;
+                gF[e] = sH[i + HS * j];
+            }
+        }
+        if (tid == 0) {
+            p.status[b] = status;
+            p.iter[b] = iter_out;
+            p.rho_updates[b] = rho_updates;
+            p.rho_estimate[b] = rho_est;
+            p.res_prim[b] = res_prim;
+            p.res_dual[b] = res_dual;
+            p.rho[b] = rho;
+            if (executed) atomicAdd(p.total_iters, (unsigned long long)executed);
+        }
+    }
+}
+
+// ---- dispatch ------------------------------------------------------------------------------------
+using Cfg64x128 = TileCfg<64, 128, 8, 8, 2>;
+using Cfg32x64 = TileCfg<32, 64, 2, 4, 8>;
+using Cfg16x32 = TileCfg<16, 32, 1, 4, 16>;
+using Cfg8x16 = TileCfg<8, 16, 1, 4, 16>;
+
+bool tile_supported(int n, int m) { return n >= 1 && m >= 0 && n <= 64 && m <= 128; }
+
+template <class Cfg>
+static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
+    cudaError_t e = cudaFuncSetAttribute(qp_tile_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qp_tile_kernel<Cfg>, Cfg::T, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
+    long long grid = (long long)sm_count * occ;  // persistent: a multiple of the SM count
+    if (grid > p.count) grid = p.count;
+    if (name) snprintf(name, name_len, "tile<%d,%d,%d>x%d", Cfg::NP, Cfg::MP, Cfg::NW, occ);
+    qp_tile_kernel<Cfg><<<(int)grid, Cfg::T, Cfg::SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
+    if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    if (p.n <= 16 && p.m <= 32) return launch_cfg<Cfg16x32>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    if (p.n <= 32 && p.m <= 64) return launch_cfg<Cfg32x64>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    return launch_cfg<Cfg64x128>(p, sm_count, ctas_per_sm, stream, name, name_len);
+}
+
 }  // namespace sqpb200
