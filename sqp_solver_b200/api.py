@@ -21,7 +21,7 @@ SOLVED, MAX_ITER_EXCEEDED, UNSOLVED, NUMERICAL_ISSUES, UNINITIALIZED = range(5) 
 INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = range(3)  # qp.hpp:134
 STATUS_NAMES = ["SOLVED", "MAX_ITER_EXCEEDED", "UNSOLVED", "NUMERICAL_ISSUES", "UNINITIALIZED"]
 HOST_PTRS, DEVICE_PTRS = 0, 1
-OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM = 1, 2, 3
+OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS = 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE = 0, 1, 2
 
 # every symbol include/sqp_b200_qp.h declares (checked by tests/test_abi_symbols.py)

@@ -24,7 +24,7 @@ struct sqpb200_ctx {
     long long launches = 0;
     double *scratch = nullptr;
     size_t scratch_bytes = 0;
-    int opt_kernel = 0, opt_chunks = 8, opt_ctas_per_sm = 0;
+    int opt_kernel = 0, opt_chunks = 8, opt_ctas_per_sm = 0, opt_tile_warps = 0;
     std::string err;
     char last_kernel[64] = "none";
     cudaEvent_t chunk_events[64]{};
@@ -147,6 +147,10 @@ int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
         case SQPB200_OPT_CTAS_PER_SM:
             if (value < 0 || value > 32) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_CTAS_PER_SM: 0..32");
             c->opt_ctas_per_sm = value;
+            return SQPB200_OK;
+        case SQPB200_OPT_TILE_WARPS:
+            if (value != 0 && value != 4 && value != 8) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_TILE_WARPS: 0, 4 or 8");
+            c->opt_tile_warps = value;
             return SQPB200_OK;
     }
     return fail(c, SQPB200_ERR_INVALID, "sqpb200_ctx_set_option: unknown option");
@@ -317,7 +321,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     p.fact = b->fact;
     cudaError_t e;
     if (want_tile) {
-        e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, stream, c->last_kernel, sizeof c->last_kernel);
+        e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, c->opt_tile_warps, stream, c->last_kernel, sizeof c->last_kernel);
     } else {
         if (!generic_supported(b->n, b->m, c->prop.sharedMemPerBlockOptin))
             return fail(c, SQPB200_ERR_UNSUPPORTED, "(n, m) too large for the generic kernel");

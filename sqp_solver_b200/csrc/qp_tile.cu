@@ -6,8 +6,10 @@
 //     g = A^T w (reduce over rows) and z~ = A x~ (reduce over columns), run from registers;
 //     partial sums are combined with warp-shuffle reduce-scatter trees, so after A x~ each row's
 //     z, y, l, u, rho live in the registers of the lane that owns the row.
-//   * H^-1 = (P_sym + sigma I + A^T diag(rho) A)^-1 lives in shared memory (padded columns,
-//     conflict-free LDS.128); x~ = H^-1 b is one dense symmetric mat-vec with a 3-step shuffle tree.
+//   * H^-1 = (P_sym + sigma I + A^T diag(rho) A)^-1 lives in REGISTERS too (HR x HC entries per
+//     lane); x~ = H^-1 b is one dense symmetric mat-vec with a short shuffle tree.  (The first
+//     version kept H^-1 in shared memory; ncu showed the LSU/shared pipe, not fp64, was the bound --
+//     profiles/r01a_*.json -- so every per-iteration matrix now sits in the register file.)
 //     H is formed by a register-blocked SYRK from a shared-memory staging copy of A and is
 //     factored in registers by symmetric pivot-by-pivot elimination (the pivots are exactly the D of
 //     the LDL^T of H; a zero/NaN pivot reports NUMERICAL_ISSUES) that is carried through to the
@@ -22,9 +24,9 @@ namespace sqpb200 {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-template <int NP_, int MP_, int NW_, int LC_, int MINB_>
+template <int NP_, int MP_, int NW_, int LC_, int HR_, int MINB_>
 struct TileCfg {
-    static constexpr int NP = NP_, MP = MP_, NW = NW_, LC = LC_, MINB = MINB_;
+    static constexpr int NP = NP_, MP = MP_, NW = NW_, LC = LC_, HR = HR_, MINB = MINB_;
     static constexpr int T = 32 * NW;
     static constexpr int LR = 32 / LC;   // lanes along the row direction inside a warp
     static constexpr int RW = MP / NW;   // rows per warp
@@ -32,20 +34,21 @@ struct TileCfg {
     static constexpr int C = NP / LC;    // columns per lane
     static constexpr int RO = (R >= LC) ? R / LC : 1;  // rows a lane owns after the A x~ reduce-scatter
     static constexpr int CO = (C >= LR) ? C / LR : 1;  // columns a lane holds after the A^T w reduce-scatter
-    static constexpr int CG = T / (NP / 2);             // lanes sharing a row pair in the symmetric mat-vec
-    static constexpr int HC = NP / CG;                  // columns per lane there
-    static constexpr int HS = NP + 16 / CG;             // padded column stride of H^-1 / P in smem
+    // symmetric n x n tiles (H^-1 in registers, P in smem): a lane holds HR consecutive rows x HC strided columns
+    static constexpr int CG = T * HR / NP;              // lanes sharing a row group
+    static constexpr int HC = NP / CG;                  // columns per lane
+    static constexpr int HS = NP + 16 / CG;             // padded column stride of P in smem
     static constexpr int LS = MP + 2;                   // padded column stride of the A staging copy
     static_assert(MP % NW == 0 && RW % LR == 0 && R >= 1, "row tiling");
     static_assert(NP % LC == 0 && C >= 2 && C % 2 == 0, "column tiling");
-    static_assert(CG >= 2 && CG <= 16 && (CG & (CG - 1)) == 0 && NP % CG == 0, "symmetric mat-vec tiling");
+    static_assert(CG >= 2 && CG <= 16 && (CG & (CG - 1)) == 0 && NP % CG == 0, "symmetric tile: column groups");
+    static_assert(HR >= 2 && HR % 2 == 0 && HR <= CG && NP % HR == 0 && (NP / HR) * CG == T, "symmetric tile: rows");
     static_assert(R == 1 || R % 2 == 0, "row tile must be vectorisable");
-    static_assert(NP * LS <= 2 * NP * HS, "A staging must fit in the H^-1 + P regions");
+    static_assert(NP * HS <= NP * LS, "P must fit in the A staging region it aliases");
     static_assert(T >= NP, "b stage needs one thread per variable");
     // shared memory carve-up (doubles)
-    static constexpr int OFF_H = 0;
-    static constexpr int OFF_P = OFF_H + NP * HS;
-    static constexpr int OFF_PART = OFF_P + NP * HS;
+    static constexpr int OFF_STAGE = 0;  // A staging copy during (re)factorisation; P afterwards
+    static constexpr int OFF_PART = OFF_STAGE + NP * LS;
     static constexpr int OFF_X = OFF_PART + NW * NP;
     static constexpr int OFF_XT = OFF_X + NP;
     static constexpr int OFF_B = OFF_XT + NP;
@@ -108,7 +111,7 @@ __device__ __forceinline__ int halve_base(int lane, bool &primary) {
 template <class Cfg>
 struct Tile {
     static constexpr int NP = Cfg::NP, MP = Cfg::MP, NW = Cfg::NW, LC = Cfg::LC, LR = Cfg::LR, T = Cfg::T;
-    static constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CO = Cfg::CO, CG = Cfg::CG, HC = Cfg::HC;
+    static constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CO = Cfg::CO, CG = Cfg::CG, HC = Cfg::HC, HR = Cfg::HR;
     static constexpr int HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
 
     // column (0..NP) of the kk-th entry of this lane's A tile: interleaved pairs so that the x~ loads
@@ -171,21 +174,42 @@ struct Tile {
         }
     }
 
-    // ---- y = M v for a padded column-major NP x NP matrix in smem; each row ends on CG/2 lanes ---
-    static __device__ __forceinline__ double mv_sym(const double *sM, const double *sv, int rp, int cg, int lane, int &row,
-                                                    bool &primary) {
-        double acc[2] = {0.0, 0.0};
+    // ---- y = M v for the symmetric-tile layout; each row ends fully reduced on CG/HR lanes --------
+    // M in registers (H^-1)
+    static __device__ __forceinline__ double mv_sym_reg(const double (&hv)[HR][HC], const double *sv, int rg, int cg, int lane,
+                                                        int &row, bool &primary) {
+        double acc[HR];
+#pragma unroll
+        for (int r = 0; r < HR; ++r) acc[r] = 0.0;
+#pragma unroll
+        for (int s = 0; s < HC; ++s) {
+            const double bv = sv[cg + CG * s];
+#pragma unroll
+            for (int r = 0; r < HR; ++r) acc[r] = fma(hv[r][s], bv, acc[r]);
+        }
+        Halve<HR, CG / 2, 1>::run(acc, lane);
+        row = HR * rg + halve_base<HR, CG / 2, 1>(lane, primary);
+        return acc[0];
+    }
+    // M in shared memory (P at the residual checks): padded column-major, column stride HS
+    static __device__ __forceinline__ double mv_sym_smem(const double *sM, const double *sv, int rg, int cg, int lane, int &row,
+                                                         bool &primary) {
+        double acc[HR];
+#pragma unroll
+        for (int r = 0; r < HR; ++r) acc[r] = 0.0;
 #pragma unroll
         for (int s = 0; s < HC; ++s) {
             const int k = cg + CG * s;
-            const double2 mv = *reinterpret_cast<const double2 *>(sM + 2 * rp + HS * k);
             const double bv = sv[k];
-            acc[0] = fma(mv.x, bv, acc[0]);
-            acc[1] = fma(mv.y, bv, acc[1]);
+#pragma unroll
+            for (int r = 0; r < HR; r += 2) {
+                const double2 mv = *reinterpret_cast<const double2 *>(sM + HR * rg + r + HS * k);
+                acc[r] = fma(mv.x, bv, acc[r]);
+                acc[r + 1] = fma(mv.y, bv, acc[r + 1]);
+            }
         }
-        Halve<2, CG / 2, 1>::run(acc, lane);
-        const int kb = halve_base<2, CG / 2, 1>(lane, primary);
-        row = 2 * rp + kb;
+        Halve<HR, CG / 2, 1>::run(acc, lane);
+        row = HR * rg + halve_base<HR, CG / 2, 1>(lane, primary);
         return acc[0];
     }
 };
@@ -194,10 +218,10 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams p) {
     using TL = Tile<Cfg>;
     constexpr int NP = Cfg::NP, MP = Cfg::MP, NW = Cfg::NW, LC = Cfg::LC, T = Cfg::T;
-    constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CG = Cfg::CG, HC = Cfg::HC, HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
+    constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CG = Cfg::CG, HC = Cfg::HC, HR = Cfg::HR, HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_qp, s_fail;
-    double *sH = smem + Cfg::OFF_H, *sP = smem + Cfg::OFF_P, *sA = smem + Cfg::OFF_H;  // sA aliases sH+sP
+    double *sA = smem + Cfg::OFF_STAGE, *sP = smem + Cfg::OFF_STAGE;  // P replaces the staging copy of A once H is formed
     double *part = smem + Cfg::OFF_PART, *sx = smem + Cfg::OFF_X, *sxt = smem + Cfg::OFF_XT, *sb = smem + Cfg::OFF_B;
     double *sq = smem + Cfg::OFF_Q, *spx = smem + Cfg::OFF_PX, *sw = smem + Cfg::OFF_W, *srho = smem + Cfg::OFF_RHO;
     double *piv = smem + Cfg::OFF_PIV, *red = smem + Cfg::OFF_RED;
@@ -208,7 +232,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     const int row0 = warp * RW + lr * R;  // first row of this lane's A tile
     bool row_primary;
     const int own0 = row0 + halve_base<R, LC / 2, 1>(lane, row_primary);  // first owned row after A x~
-    const int rp = tid / CG, cg = tid % CG;                                // symmetric mat-vec coordinates
+    const int rg = tid / CG, cg = tid % CG;                                // symmetric-tile coordinates
+    const int i0 = HR * rg;
     const sqpb200_qp_settings st = p.s;
     const double sigma = st.sigma, alpha = st.alpha;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -280,42 +305,50 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 sP[i + HS * j] = (i < n && j < n) ? gP[i + (size_t)n * j] : 0.0;
             }
         };
-        // H^-1 from the staged A: SYRK into registers, symmetric elimination, write -S to sH.
-        // Requires sA staged and srho written; ends with sH and sP valid and the CTA synchronised.
+        // H^-1 from the staged A, kept in registers hv[HR][HC]: SYRK, then symmetric elimination.
+        // Requires sA staged and srho written; ends with sP valid and the CTA synchronised.
+        double hv[HR][HC];
         auto factorize = [&]() -> bool {
-            double S0[HC], S1[HC];
-            const int i0 = 2 * rp, i1 = 2 * rp + 1;
 #pragma unroll
             for (int s = 0; s < HC; ++s) {
                 const int j = cg + CG * s;
-                // lower triangle of P mirrored (LDLT<Lower> reads nothing else), + sigma on the diagonal;
-                // padded variables get a unit diagonal block
-                auto h0 = [&](int i) -> double {
-                    if (i >= n || j >= n) return i == j ? 1.0 : 0.0;
-                    const double v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
-                    return i == j ? v + sigma : v;
-                };
-                S0[s] = h0(i0);
-                S1[s] = h0(i1);
+#pragma unroll
+                for (int r = 0; r < HR; ++r) {
+                    // lower triangle of P mirrored (LDLT<Lower> reads nothing else), + sigma on the diagonal;
+                    // padded variables get a unit diagonal block
+                    const int i = i0 + r;
+                    double v;
+                    if (i >= n || j >= n) v = (i == j) ? 1.0 : 0.0;
+                    else {
+                        v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
+                        if (i == j) v += sigma;
+                    }
+                    hv[r][s] = v;
+                }
             }
             const int mloop = (m + 1) / 2;
             for (int kp = 0; kp < mloop; ++kp) {
                 const double2 rr = *reinterpret_cast<const double2 *>(srho + 2 * kp);
-                double2 a0 = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * i0);
-                double2 a1 = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * i1);
-                a0.x *= rr.x; a0.y *= rr.y; a1.x *= rr.x; a1.y *= rr.y;
+                double2 ar[HR];
+#pragma unroll
+                for (int r = 0; r < HR; ++r) {
+                    ar[r] = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (i0 + r));
+                    ar[r].x *= rr.x;
+                    ar[r].y *= rr.y;
+                }
 #pragma unroll
                 for (int s = 0; s < HC; ++s) {
                     const double2 cj = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (cg + CG * s));
-                    S0[s] = fma(a0.x, cj.x, S0[s]);
-                    S0[s] = fma(a0.y, cj.y, S0[s]);
-                    S1[s] = fma(a1.x, cj.x, S1[s]);
-                    S1[s] = fma(a1.y, cj.y, S1[s]);
+#pragma unroll
+                    for (int r = 0; r < HR; ++r) {
+                        hv[r][s] = fma(ar[r].x, cj.x, hv[r][s]);
+                        hv[r][s] = fma(ar[r].y, cj.y, hv[r][s]);
+                    }
                 }
             }
             if (tid == 0) s_fail = 0;
-            cta_sync<NW>();  // everyone is done with sA; sH/sP may be overwritten from here on
-            // symmetric elimination, pivot by pivot; after step k rows/cols <= k hold -(H_kk block)^-1 parts
+            cta_sync<NW>();  // everyone is done with sA; the staging region may be overwritten from here on
+            // symmetric elimination, pivot by pivot: after all NP steps hv holds -(H^-1)
             bool ok = true;
 #pragma unroll
             for (int s = 0; s < HC; ++s) {
@@ -324,8 +357,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     const int k = cgk + CG * s;
                     double *pv = piv + (k & 1) * NP;
                     if (cg == cgk) {
-                        pv[i0] = S0[s];
-                        pv[i1] = S1[s];
+#pragma unroll
+                        for (int r = 0; r < HR; r += 2) *reinterpret_cast<double2 *>(pv + i0 + r) = make_double2(hv[r][s], hv[r + 1][s]);
                     }
                     cta_sync<NW>();
                     const double d = pv[k];
@@ -334,31 +367,36 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         break;
                     }
                     const double inv_d = 1.0 / d;
-                    const double2 ci = *reinterpret_cast<const double2 *>(pv + i0);
-                    const double t0 = ci.x * inv_d, t1 = ci.y * inv_d;
+                    const int krow = k - i0;  // row of this lane's tile that is the pivot row (if 0 <= krow < HR)
+                    double t[HR];
+#pragma unroll
+                    for (int r = 0; r < HR; r += 2) {
+                        const double2 ci = *reinterpret_cast<const double2 *>(pv + i0 + r);
+                        t[r] = ci.x * inv_d;
+                        t[r + 1] = ci.y * inv_d;
+                    }
 #pragma unroll
                     for (int s2 = 0; s2 < HC; ++s2) {
                         const double cj = pv[cg + CG * s2];
-                        double v0 = fma(-t0, cj, S0[s2]);
-                        double v1 = fma(-t1, cj, S1[s2]);
-                        if (i0 == k) v0 = cj * inv_d;
-                        if (i1 == k) v1 = cj * inv_d;
-                        S0[s2] = v0;
-                        S1[s2] = v1;
+                        const double rowv = cj * inv_d;
+#pragma unroll
+                        for (int r = 0; r < HR; ++r) {
+                            const double v = fma(-t[r], cj, hv[r][s2]);
+                            hv[r][s2] = (r == krow) ? rowv : v;
+                        }
                     }
                     if (cg == cgk) {
-                        S0[s] = (i0 == k) ? -inv_d : t0;
-                        S1[s] = (i1 == k) ? -inv_d : t1;
+#pragma unroll
+                        for (int r = 0; r < HR; ++r) hv[r][s] = (r == krow) ? -inv_d : t[r];
                     }
                 }
                 if (!ok) break;
             }
-            cta_sync<NW>();
-            if (ok) {
 #pragma unroll
-                for (int s = 0; s < HC; ++s)
-                    *reinterpret_cast<double2 *>(sH + i0 + HS * (cg + CG * s)) = make_double2(-S0[s], -S1[s]);
-            }
+            for (int s = 0; s < HC; ++s)
+#pragma unroll
+                for (int r = 0; r < HR; ++r) hv[r][s] = -hv[r][s];
+            cta_sync<NW>();
             load_P();
             cta_sync<NW>();
             return ok;
@@ -389,9 +427,14 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         if (!do_factor) {
             cta_sync<NW>();  // tiles are in registers; the staging area may be overwritten
             const double *gF = p.fact + b * n * n;
-            for (int e = tid; e < NP * NP; e += T) {
-                const int i = e % NP, j = e / NP;
-                sH[i + HS * j] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? 1.0 : 0.0);
+#pragma unroll
+            for (int s = 0; s < HC; ++s) {
+                const int j = cg + CG * s;
+#pragma unroll
+                for (int r = 0; r < HR; ++r) {
+                    const int i = i0 + r;
+                    hv[r][s] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? 1.0 : 0.0);
+                }
             }
             load_P();
             cta_sync<NW>();
@@ -405,7 +448,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         for (;;) {
             if (do_factor) {
                 if (!staged) {
-                    cta_sync<NW>();  // all reads of sH/sP done before the staging overwrites them
+                    cta_sync<NW>();  // all reads of sP done before the staging overwrites it
                     stage_A();
                     if (row_primary) {
 #pragma unroll
@@ -457,7 +500,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 {
                     int row;
                     bool prim;
-                    const double xt = TL::mv_sym(sH, sb, rp, cg, lane, row, prim);
+                    const double xt = TL::mv_sym_reg(hv, sb, rg, cg, lane, row, prim);
                     if (prim) {
                         sxt[row] = xt;
                         sx[row] = alpha * xt + (1.0 - alpha) * sx[row];
@@ -497,7 +540,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     {
                         int row;
                         bool prim;
-                        const double px = TL::mv_sym(sP, sx, rp, cg, lane, row, prim);
+                        const double px = TL::mv_sym_smem(sP, sx, rg, cg, lane, row, prim);
                         if (prim) spx[row] = px;
                     }
                     cta_sync<NW>();
@@ -576,9 +619,14 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         }
         if ((p.mode & MODE_STORE_FACTOR) && status != SQPB200_NUMERICAL_ISSUES && status != SQPB200_UNINITIALIZED) {
             double *gF = p.fact + b * n * n;
-            for (int e = tid; e < n * n; e += T) {
-                const int i = e % n, j = e / n;
-                gF[e] = sH[i + HS * j];
+#pragma unroll
+            for (int s = 0; s < HC; ++s) {
+                const int j = cg + CG * s;
+#pragma unroll
+                for (int r = 0; r < HR; ++r) {
+                    const int i = i0 + r;
+                    if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
+                }
             }
         }
         if (tid == 0) {
@@ -595,10 +643,11 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 }
 
 // ---- dispatch ------------------------------------------------------------------------------------
-using Cfg64x128 = TileCfg<64, 128, 8, 8, 2>;
-using Cfg32x64 = TileCfg<32, 64, 2, 4, 8>;
-using Cfg16x32 = TileCfg<16, 32, 1, 4, 16>;
-using Cfg8x16 = TileCfg<8, 16, 1, 4, 16>;
+using Cfg64x128w4 = TileCfg<64, 128, 4, 8, 4, 2>;  // 128 threads: 8x8 A tile + 4x8 H^-1 tile per lane
+using Cfg64x128w8 = TileCfg<64, 128, 8, 8, 2, 2>;  // 256 threads: 4x8 A tile + 2x8 H^-1 tile per lane
+using Cfg32x64 = TileCfg<32, 64, 2, 4, 2, 8>;
+using Cfg16x32 = TileCfg<16, 32, 1, 4, 2, 16>;
+using Cfg8x16 = TileCfg<8, 16, 1, 4, 2, 16>;
 
 bool tile_supported(int n, int m) { return n >= 1 && m >= 0 && n <= 64 && m <= 128; }
 
@@ -618,11 +667,13 @@ static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
+cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, int tile_warps, cudaStream_t stream, char *name,
+                        size_t name_len) {
     if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16>(p, sm_count, ctas_per_sm, stream, name, name_len);
     if (p.n <= 16 && p.m <= 32) return launch_cfg<Cfg16x32>(p, sm_count, ctas_per_sm, stream, name, name_len);
     if (p.n <= 32 && p.m <= 64) return launch_cfg<Cfg32x64>(p, sm_count, ctas_per_sm, stream, name, name_len);
-    return launch_cfg<Cfg64x128>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    if (tile_warps == 8) return launch_cfg<Cfg64x128w8>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    return launch_cfg<Cfg64x128w4>(p, sm_count, ctas_per_sm, stream, name, name_len);
 }
 
 }  // namespace sqpb200

@@ -4,5 +4,7 @@
 
 namespace sqpb200 {
 bool tile_supported(int n, int m);
-cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len);
+// tile_warps: 0 = default, 4 or 8 selects the warps-per-QP variant of the 64x128 configuration
+cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, int tile_warps, cudaStream_t stream, char *name,
+                        size_t name_len);
 }  // namespace sqpb200

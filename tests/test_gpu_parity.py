@@ -24,17 +24,22 @@ def ctx(api):
     c.close()
 
 
-KERNELS = ["generic", "tile"]
+KERNELS = ["generic", "tile", "tile8"]  # tile8 = the 8-warps-per-QP variant of the 64x128 configuration
 
 
 def select_kernel(api, ctx, kernel, n, m):
-    ctx.set_option(api.OPT_KERNEL, {"generic": api.KERNEL_GENERIC, "tile": api.KERNEL_TILE, "auto": api.KERNEL_AUTO}[kernel])
+    if kernel == "tile8" and not (n > 32 or m > 64):
+        pytest.skip("the 8-warp variant only exists for the 64x128 configuration")
+    ctx.set_option(api.OPT_KERNEL, {"generic": api.KERNEL_GENERIC, "tile": api.KERNEL_TILE, "tile8": api.KERNEL_TILE,
+                                    "auto": api.KERNEL_AUTO}[kernel])
+    ctx.set_option(api.OPT_TILE_WARPS, 8 if kernel == "tile8" else 0)
 
 
 @pytest.fixture(autouse=True)
 def _reset_kernel_option(api, ctx):
     yield
     ctx.set_option(api.OPT_KERNEL, api.KERNEL_AUTO)
+    ctx.set_option(api.OPT_TILE_WARPS, 0)
 
 
 def run_fused(api, ctx, d, settings, kernel):
@@ -44,7 +49,7 @@ def run_fused(api, ctx, d, settings, kernel):
     try:
         b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"])
     except api.SolverError as e:
-        if kernel == "tile" and "outside its range" in str(e):
+        if kernel.startswith("tile") and "outside its range" in str(e):
             pytest.skip("shape not covered by the register-tiled kernel")
         raise
     out = b.get()
@@ -149,8 +154,8 @@ def test_object_api_setup_solve_solve_update(api, ctx, oracle, golden, kernel):
     mirroring tests/qp_solver_test.cpp:102-125 and the dead update_qp case of qp_solver_sparse_test.cpp."""
     from sqp_solver_b200.synth import make_batch
 
-    select_kernel(api, ctx, kernel, 12, 20)
-    B, n, m = 6, 12, 20
+    B, n, m = (6, 12, 20) if kernel != "tile8" else (4, 40, 70)
+    select_kernel(api, ctx, kernel, n, m)
     d = make_batch(B, n, m, seed0=4000)
     d2 = make_batch(B, n, m, seed0=5000)
     b = api.QPBatch(ctx, B, n, m)
@@ -171,7 +176,7 @@ def test_object_api_setup_solve_solve_update(api, ctx, oracle, golden, kernel):
     try:
         b.solve(*args)
     except api.SolverError as e:
-        if kernel == "tile" and "outside its range" in str(e):
+        if kernel.startswith("tile") and "outside its range" in str(e):
             pytest.skip("shape not covered by the register-tiled kernel")
         raise
     info = b.info()
