@@ -42,6 +42,7 @@ def parse():
                     help="S1 = reference defaults (headline); S2 = alpha 1.6 + adaptive rho (SURVEY.md 8d)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tile"])
     ap.add_argument("--tile-warps", type=int, default=0, choices=[0, 4, 8])
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -193,6 +194,7 @@ def main():
     ctx = api.Context(local_rank)
     ctx.set_option(api.OPT_KERNEL, {"auto": 0, "generic": 1, "tile": 2}[args.kernel])
     ctx.set_option(api.OPT_TILE_WARPS, args.tile_warps)
+    ctx.set_option(api.OPT_CTAS_PER_SM, args.ctas_per_sm)
     B, n, m = args.batch, args.n, args.m
     d = make_batch(B, n, m, seed0=rank * B)  # every rank owns a disjoint shard of the seed sequence
     settings = api.default_settings(**settings_kwargs(args.settings))

@@ -178,14 +178,21 @@ struct Tile {
     // M in registers (H^-1)
     static __device__ __forceinline__ double mv_sym_reg(const double (&hv)[HR][HC], const double *sv, int rg, int cg, int lane,
                                                         int &row, bool &primary) {
-        double acc[HR];
+        double acc[HR], acc2[HR];  // two chains per row: the mat-vec is latency bound, not issue bound
 #pragma unroll
-        for (int r = 0; r < HR; ++r) acc[r] = 0.0;
+        for (int r = 0; r < HR; ++r) acc[r] = acc2[r] = 0.0;
 #pragma unroll
         for (int s = 0; s < HC; ++s) {
             const double bv = sv[cg + CG * s];
 #pragma unroll
-            for (int r = 0; r < HR; ++r) acc[r] = fma(hv[r][s], bv, acc[r]);
+            for (int r = 0; r < HR; ++r) {
+                if (s & 1) acc2[r] = fma(hv[r][s], bv, acc2[r]);
+                else acc[r] = fma(hv[r][s], bv, acc[r]);
+            }
+        }
+        if constexpr (HC > 1) {
+#pragma unroll
+            for (int r = 0; r < HR; ++r) acc[r] += acc2[r];
         }
         Halve<HR, CG / 2, 1>::run(acc, lane);
         row = HR * rg + halve_base<HR, CG / 2, 1>(lane, primary);
@@ -479,6 +486,10 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 }
             }
             bool refactor = false;
+            // iterations until the next termination check / adaptive-rho step (replaces iter % N, qp.cpp:105,125)
+            int to_chk = st.check_termination > 0 ? st.check_termination - (iter - 1) % st.check_termination : 0x7fffffff;
+            int to_adapt = (st.adaptive_rho && st.adaptive_rho_interval > 0)
+                               ? st.adaptive_rho_interval - (iter - 1) % st.adaptive_rho_interval : 0x7fffffff;
             for (; iter <= st.max_iter; ++iter) {
                 // P1: w = rho .* z - y (owner lanes) -> sw; partial A^T w over this warp's rows -> part[warp]
                 if (row_primary) {
@@ -490,10 +501,14 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 cta_sync<NW>();
                 // P2: b = sigma x - q + A^T w   (rhs of qp.cpp:272-276 pushed through the (2,2) block)
                 if (tid < NP) {
-                    double g = part[tid];
+                    double pw[NW];
 #pragma unroll
-                    for (int w2 = 1; w2 < NW; ++w2) g += part[w2 * NP + tid];
-                    sb[tid] = sigma * sx[tid] - sq[tid] + g;
+                    for (int w2 = 0; w2 < NW; ++w2) pw[w2] = part[w2 * NP + tid];
+#pragma unroll
+                    for (int h = NW / 2; h >= 1; h /= 2)
+#pragma unroll
+                        for (int w2 = 0; w2 < h; ++w2) pw[w2] += pw[w2 + h];
+                    sb[tid] = fma(sigma, sx[tid], pw[0] - sq[tid]);
                 }
                 cta_sync<NW>();
                 // P3: x~ = H^-1 b ; x = alpha x~ + (1 - alpha) x   (qp.cpp:90-96)
@@ -520,8 +535,10 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         axr[t] = alpha * zt[t] + (1.0 - alpha) * axr[t];  // A x by linearity of the x update
                     }
                 }
-                const bool chk = st.check_termination != 0 && iter % st.check_termination == 0;
-                const bool adapt = st.adaptive_rho && st.adaptive_rho_interval > 0 && iter % st.adaptive_rho_interval == 0;
+                const bool chk = --to_chk == 0;
+                const bool adapt = --to_adapt == 0;
+                if (chk) to_chk = st.check_termination;
+                if (adapt) to_adapt = st.adaptive_rho_interval;
                 if (chk || adapt) {
                     // update_state, qp.cpp:316-331
                     double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
