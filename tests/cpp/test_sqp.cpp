@@ -1,0 +1,116 @@
+// GPU: mirrors the reference's tests/sqp_test.cpp and the NLPs of tests/sqp_test_autodiff.cpp (with
+// hand-written derivatives; Eigen's AutoDiff module is not available) against sqp::SQP<double> running its
+// QP subproblems on the B200, and checks sqp::BatchSQP (lock-step batch) against a loop of single solves.
+#include "mini_test.hpp"
+
+#include "sqp_problems.hpp"
+
+TEST(SQPTestCase, TestSimpleNLP) {  // tests/sqp_test.cpp:46-67
+    SimpleNLP problem;
+    SQP<double> solver;
+    solver.settings().max_iter = 100;
+    solver.settings().second_order_correction = true;
+    solver.solve(problem, v2(1.2, 0.1), zeros(3));
+    solver.info().print();
+    EXPECT_TRUE(solver.primal_solution().isApprox(v2(1, 1), 1e-2));
+    EXPECT_LT(solver.info().iter, solver.settings().max_iter);
+    EXPECT_EQ(solver.info().iter, 4);             // oracle regression values
+    EXPECT_EQ(solver.info().qp_solver_iter, 300);
+}
+
+TEST(SQPTestCase, SimpleNLP_InfeasibleStart) {  // tests/sqp_test.cpp:69-90
+    SimpleNLP problem;
+    SQP<double> solver;
+    Vec y0(3);
+    y0.setConstant(1);
+    solver.settings().max_iter = 100;
+    solver.settings().second_order_correction = true;
+    solver.solve(problem, v2(2, -1), y0);
+    EXPECT_TRUE(solver.primal_solution().isApprox(v2(1, 1), 1e-2));
+    EXPECT_LT(solver.info().iter, solver.settings().max_iter);
+}
+
+TEST(SQPTestCase, TestSimpleQP) {  // tests/sqp_test.cpp:126-141
+    SimpleQPasNLP problem;
+    SQP<double> solver;
+    solver.settings().second_order_correction = true;
+    solver.solve(problem, v2(0, 0), zeros(3));
+    EXPECT_TRUE(solver.primal_solution().isApprox(v2(0.3, 0.7), 1e-2));
+    EXPECT_LT(solver.info().iter, solver.settings().max_iter);
+}
+
+TEST(SQPAutoDiff, TestConstrainedRosenbrock2D) {  // tests/sqp_test_autodiff.cpp:101-120
+    ConstrainedRosenbrock2D problem;
+    SQP<double> solver;
+    solver.settings().max_iter = 100;
+    solver.solve(problem, v2(0, 0), zeros(2));
+    EXPECT_TRUE(solver.primal_solution().isApprox(v2(0.707106781, 0.707106781), 1e-2));
+    EXPECT_LT(solver.info().iter, solver.settings().max_iter);
+    EXPECT_EQ(solver.info().iter, 15);
+    EXPECT_EQ(solver.info().qp_solver_iter, 731);
+}
+
+TEST(SQPAutoDiff, TestSimpleNLP_noSOC) {  // tests/sqp_test_autodiff.cpp:194-217
+    SimpleNLP problem;
+    SQP<double> solver;
+    solver.settings().max_iter = 100;
+    solver.settings().second_order_correction = false;
+    solver.solve(problem, v2(1.2, 0.1), zeros(3));
+    EXPECT_TRUE(solver.primal_solution().isApprox(v2(1, 1), 1e-2));
+    EXPECT_LT(solver.info().iter, solver.settings().max_iter);
+}
+
+TEST(SQPAutoDiff, TestSimpleNLP2) {  // tests/sqp_test_autodiff.cpp:267-282
+    SimpleNLP2 problem;
+    SQP<double> solver;
+    solver.solve(problem, v2(1.2, 0.1), zeros(1));
+    EXPECT_TRUE(solver.primal_solution().isApprox(v2(-1, -1), 1e-2));
+    EXPECT_LT(solver.info().iter, solver.settings().max_iter);
+}
+
+TEST(SQPCallback, IterationCallbackFires) {  // sqp.hpp:23, sqp.cpp:68-70, 89-91
+    SimpleNLP2 problem;
+    SQP<double> solver;
+    int calls = 0;
+    solver.settings().iteration_callback = [&](SQP<double> &) { ++calls; };
+    solver.solve(problem, v2(1.2, 0.1), zeros(1));
+    EXPECT_EQ(calls, solver.info().iter + 1);
+}
+
+// BASELINE.json config 4 in miniature: a batch of constrained-Rosenbrock instances from different starts,
+// BFGS Hessian + host outer loop + ONE batched GPU QP solve per outer iteration.
+TEST(BatchSQPTest, LockStepMatchesSingleSolves) {
+    const int B = 96;
+    std::vector<ConstrainedRosenbrock2D> probs(B);
+    std::vector<NonLinearProblem<double> *> ptrs;
+    std::vector<Vec> x0, l0;
+    for (int i = 0; i < B; ++i) {
+        ptrs.push_back(&probs[i]);
+        // deterministic infeasible starts around the origin (|x|^2 != 1), cf. SURVEY.md Appendix B.3
+        x0.push_back(v2(-0.4 + 0.011 * i, 0.3 - 0.007 * i));
+        l0.push_back(zeros(2));
+    }
+    BatchSQP batch(ptrs);
+    batch.settings().max_iter = 100;
+    batch.solve(x0, l0);
+    int solved = 0, max_outer = 0;
+    for (int i = 0; i < B; ++i) {
+        SQP<double> single;
+        single.settings().max_iter = 100;
+        single.solve(probs[i], x0[i], l0[i]);
+        EXPECT_EQ(batch.info(i).iter, single.info().iter);
+        EXPECT_EQ(batch.info(i).qp_solver_iter, single.info().qp_solver_iter);
+        EXPECT_EQ(batch.info(i).status, single.info().status);
+        EXPECT_TRUE(batch.primal_solution(i).isApprox(single.primal_solution(), 1e-9));
+        if (batch.info(i).status == SOLVED) {
+            ++solved;
+            EXPECT_TRUE(batch.primal_solution(i).isApprox(v2(0.707106781, 0.707106781), 1e-2));
+        }
+        max_outer = std::max(max_outer, batch.info(i).iter);
+    }
+    printf("  batch of %d: %d solved, %d batched QP launches for up to %d outer iterations\n", B, solved, batch.qp_launches(), max_outer);
+    EXPECT_GE(solved, B * 9 / 10);
+    EXPECT_LE(batch.qp_launches(), max_outer);
+}
+
+MINI_TEST_MAIN()

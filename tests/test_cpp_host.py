@@ -1,0 +1,146 @@
+"""Builds and runs the C++ tests of the host-side mirror of the reference interface
+(sqp_solver_b200/host/solvers/*.hpp). They read like the reference's own GoogleTest files."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "tests", "cpp")
+OUT = os.path.join(CPP, "build")
+
+
+def compile_cpp(name):
+    from sqp_solver_b200 import build
+
+    build.build()
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, name)
+    libdir = os.path.join(ROOT, "sqp_solver_b200")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(libdir, "host"), os.path.join(CPP, name + ".cpp"),
+           "-o", exe, "-L" + libdir, "-lsqp_b200", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64",
+           "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def run(exe):
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    print(r.stderr)
+    return r
+
+
+def test_bfgs_and_host_logic_cpu():
+    """tests/bfgs_test.cpp mirror + dense shim + settings: needs no GPU."""
+    r = run(compile_cpp("test_bfgs"))
+    assert r.returncode == 0, r.stdout
+
+
+def test_all_cpp_tests_compile():
+    for name in ("test_qp_solver", "test_sqp", "sqp_cli"):
+        compile_cpp(name)
+
+
+def test_bfgs_oracle_keeps_posdef(oracle):
+    """Oracle restatement of bfgs.hpp:15-41 keeps B positive definite under arbitrary curvature pairs."""
+    from oracle import sqp_oracle
+
+    rng = np.random.default_rng(5)
+    B = np.eye(4)
+    for k in range(12):
+        s = rng.standard_normal(4)
+        y = rng.standard_normal(4) * (1 if k % 3 else -1)
+        B = sqp_oracle.bfgs_update(B, s, y)
+        assert sqp_oracle.is_posdef(B)
+
+
+def test_sqp_oracle_reference_kats(oracle, golden):
+    """The SQP oracle against the reference's own assertions (tests/sqp_test.cpp, tests/sqp_test_autodiff.cpp):
+    solution within isApprox 1e-2 and iter < max_iter; plus the regression counts of SURVEY.md Appendix B.2."""
+    from oracle import sqp_oracle as S
+
+    ids = {"ConstrainedRosenbrock2D": S.CONSTRAINED_ROSENBROCK_2D, "SimpleNLP_feasible": S.SIMPLE_NLP,
+           "SimpleNLP_infeasible": S.SIMPLE_NLP, "SimpleQP_as_NLP": S.SIMPLE_QP}
+    appendix_b2 = {"ConstrainedRosenbrock2D": (15, 731), "SimpleNLP_feasible": (4, 300), "SimpleNLP_infeasible": (8, 622),
+                   "SimpleQP_as_NLP": (7, 820)}
+    for name, g in golden["sqp_problems"].items():
+        if name.startswith("_"):
+            continue
+        o = S.solve(ids[name], g["x0"], g["lambda0"], S.default_settings(max_iter=g["max_iter"], second_order_correction=int(g["soc"])))
+        sol = np.array(g["solution"], dtype=float)
+        assert np.sum((o["x"] - sol) ** 2) <= 1e-4 * min(np.sum(o["x"] ** 2), np.sum(sol ** 2)), name
+        assert o["iter"] < g["max_iter"], name
+        assert (o["iter"], o["qp_solver_iter"]) == appendix_b2[name], name
+    o = S.solve(S.SIMPLE_NLP2, [1.2, 0.1], [0], S.default_settings())  # tests/sqp_test_autodiff.cpp:267-282
+    assert np.allclose(o["x"], [-1, -1], atol=1e-2) and (o["iter"], o["qp_solver_iter"]) == (16, 520)
+
+
+@pytest.mark.gpu
+def test_qp_solver_cpp_gpu():
+    """tests/qp_solver_test.cpp mirror through qp_solver::QPSolver<Scalar> on the B200."""
+    r = run(compile_cpp("test_qp_solver"))
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_sqp_cpp_gpu():
+    """tests/sqp_test.cpp + sqp_test_autodiff.cpp mirror; BatchSQP lock-step == loop of single solves."""
+    r = run(compile_cpp("test_sqp"))
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_sqp_trajectory_matches_oracle(oracle, golden):
+    """Caller-level parity: the host SQP loop with GPU QP solves reproduces the CPU
+    oracle's outer/inner iteration counts and final iterate on the reference's NLP test problems."""
+    from oracle import sqp_oracle as S
+
+    r = run(compile_cpp("sqp_cli"))
+    assert r.returncode == 0
+    got = {d["name"]: d for d in map(json.loads, [ln for ln in r.stdout.splitlines() if ln.startswith("{")])}
+    cases = {
+        "ConstrainedRosenbrock2D": (S.CONSTRAINED_ROSENBROCK_2D, [0, 0], [0, 0], 0, [0.707106781, 0.707106781]),
+        "SimpleNLP_feasible_SOC": (S.SIMPLE_NLP, [1.2, 0.1], [0, 0, 0], 1, [1, 1]),
+        "SimpleNLP_infeasible_SOC": (S.SIMPLE_NLP, [2, -1], [1, 1, 1], 1, [1, 1]),
+        "SimpleQP_as_NLP_SOC": (S.SIMPLE_QP, [0, 0], [0, 0, 0], 1, [0.3, 0.7]),
+        "SimpleNLP2": (S.SIMPLE_NLP2, [1.2, 0.1], [0], 0, [-1, -1]),
+    }
+    for name, (pid, x0, l0, soc, sol) in cases.items():
+        ref = S.solve(pid, x0, l0, S.default_settings(second_order_correction=soc))
+        g = got[name]
+        x = np.array(g["x"])
+        # the reference's own pin: isApprox(solution, 1e-2) and iter < max_iter
+        assert np.sum((x - sol) ** 2) <= 1e-4 * min(np.sum(x * x), np.sum(np.square(sol))), name
+        assert g["iter"] < 100, name
+        # oracle parity
+        assert (g["iter"], g["qp_solver_iter"], g["status"]) == (ref["iter"], ref["qp_solver_iter"], ref["status"]), (name, g, ref)
+        assert np.linalg.norm(x - ref["x"]) <= 1e-6 * np.linalg.norm(ref["x"]), name
+        assert np.abs(np.array(g["lambda"]) - ref["lam"]).max() <= 1e-5 * max(1.0, np.abs(ref["lam"]).max()), name
+
+
+@pytest.mark.gpu
+def test_sqp_generated_subproblems_match_oracle(oracle):
+    """Per-QP-subproblem parity on QPs an SQP run actually generates (n=2, m=2..3, infinite bounds, BFGS
+    Hessians, the SQP constructor's QP settings): every QP the oracle's SQP solved is re-solved on the GPU."""
+    from helpers import assert_parity
+    from oracle import sqp_oracle as S
+    from sqp_solver_b200 import api
+
+    ctx = api.Context(0)
+    for pid, x0, l0, soc in ((S.CONSTRAINED_ROSENBROCK_2D, [0, 0], [0, 0], 0), (S.SIMPLE_NLP, [2, -1], [1, 1, 1], 1),
+                             (S.SIMPLE_NLP, [1.2, 0.1], [0, 0, 0], 0), (S.SIMPLE_QP, [0, 0], [0, 0, 0], 1)):
+        tr = S.solve(pid, x0, l0, S.default_settings(second_order_correction=soc), trace_cap=512)["qps"]
+        k = tr["count"]
+        nx, nc = tr["q"].shape[1], tr["l"].shape[1]
+        b = api.QPBatch(ctx, k, nx, nc)
+        b.settings = api.sqp_ctor_settings()
+        b.setup_solve(tr["P"], tr["q"], tr["A"], tr["l"], tr["u"])
+        out = b.get()
+        ref = dict(x=tr["x"], y=tr["y"], status=tr["status"], iter=tr["iter"])
+        out.pop("rho_updates")
+        assert_parity(out, ref, what="SQP-generated QPs of problem %d" % pid)
+        b.close()
+    ctx.close()
