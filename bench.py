@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tile"])
     ap.add_argument("--tile-warps", type=int, default=0, choices=[0, 4, 8])
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): every rank solves its own batch. strong: ONE batch on rank 0 "
+                         "is split over the ranks with NCCL send/recv, solved, and gathered back (north star's split/gather)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -173,6 +176,45 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_strong(args, rank, world, ctx, api, d, settings):
+    """Strong scaling: rank 0 owns the whole batch; NCCL send/recv splits it, each rank solves its slice,
+    NCCL gathers x, y, z and the info arrays back to rank 0. The split and gather are inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    from sqp_solver_b200 import sharding
+
+    B, n, m = args.batch, args.n, args.m
+    lo, hi = sharding.shard_range(B, rank, world)
+    qb = api.QPBatch(ctx, max(hi - lo, 1), n, m)
+    qb.settings = settings
+    prob = {k: torch.from_numpy(d[k]).cuda() for k in sharding.PROBLEM_KEYS} if rank == 0 else None
+    solve_local = sharding.gpu_solve_local(qb)
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        out = sharding.solve_sharded(prob, n, m, B, solve_local, root=0)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        out = sharding.solve_sharded(prob, n, m, B, solve_local, root=0)
+    ev1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t.item())
+        its = int(torch.clamp(out["iter"], max=settings.max_iter).sum().item())
+        print(json.dumps({"metric": METRIC, "value": B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "configs[2]: ONE batch=%d n=%d m=%d on rank 0, NCCL split -> solve -> NCCL gather "
+                                                 "(both inside the timed region)" % (B, n, m), "kernel": ctx.last_kernel},
+                          "admm_iters_per_s": its / (ms / 1e3 / args.steps)}))
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -196,8 +238,14 @@ def main():
     ctx.set_option(api.OPT_TILE_WARPS, args.tile_warps)
     ctx.set_option(api.OPT_CTAS_PER_SM, args.ctas_per_sm)
     B, n, m = args.batch, args.n, args.m
-    d = make_batch(B, n, m, seed0=rank * B)  # every rank owns a disjoint shard of the seed sequence
+    strong = args.scaling == "strong" and world > 1
+    # weak: every rank owns a disjoint shard of the seed sequence; strong: only rank 0 builds the (single) batch
+    d = make_batch(B if (not strong or rank == 0) else 1, n, m, seed0=0 if strong else rank * B)
     settings = api.default_settings(**settings_kwargs(args.settings))
+    if strong:
+        run_strong(args, rank, world, ctx, api, d, settings)
+        dist.destroy_process_group()
+        return
     dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")}
     qb = api.QPBatch(ctx, B, n, m)
     qb.settings = settings
