@@ -16,6 +16,7 @@
 //     inverse, so the ADMM loop has no serial substitution chain.
 //   * P lives in shared memory for the residual checks (P*x uses all of P, qp.cpp:323).
 // Reference functions covered: identical list to qp_generic.cu (all of src/qp.cpp:11-371).
+#include <cstdint>
 #include <cstdio>
 
 #include "qp_tile.cuh"
@@ -61,6 +62,35 @@ struct TileCfg {
     static constexpr int SMEM_DOUBLES = OFF_RED + 8 * NW;
     static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
 };
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ---------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 template <int NW>
 __device__ __forceinline__ void cta_sync() {
@@ -228,6 +258,9 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CG = Cfg::CG, HC = Cfg::HC, HR = Cfg::HR, HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_qp, s_fail;
+    __shared__ __align__(8) unsigned long long s_mbar;  // completion barrier of the TMA bulk copies
+    __shared__ double s_info[3];
+    unsigned mbar_parity = 0;
     double *sA = smem + Cfg::OFF_STAGE, *sP = smem + Cfg::OFF_STAGE;  // P replaces the staging copy of A once H is formed
     double *part = smem + Cfg::OFF_PART, *sx = smem + Cfg::OFF_X, *sxt = smem + Cfg::OFF_XT, *sb = smem + Cfg::OFF_B;
     double *sq = smem + Cfg::OFF_Q, *spx = smem + Cfg::OFF_PX, *sw = smem + Cfg::OFF_W, *srho = smem + Cfg::OFF_RHO;
@@ -244,6 +277,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     const sqpb200_qp_settings st = p.s;
     const double sigma = st.sigma, alpha = st.alpha;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    if (tid == 0) mbar_init(&s_mbar, 1);
 
     for (;;) {
         cta_sync<NW>();
@@ -251,22 +285,30 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         cta_sync<NW>();
         const int local = s_qp;
         if (local >= p.count) break;
-        const size_t b = (size_t)p.first + local;
-        const double *__restrict__ gP = p.P + b * n * n;
-        const double *__restrict__ gA = p.A + b * m * n;
-        const double *__restrict__ gq = p.q + b * n;
-        const double *__restrict__ gl = p.l + b * m;
-        const double *__restrict__ gu = p.u + b * m;
+        // Only the batch index stays live across the solve; problem pointers are re-derived from the kernel
+        // parameters (constant bank) where needed -- the hot loop is register-limited.
+        const int bi = p.first + local;
+        const size_t b = (size_t)bi;
+#define gP (p.P + (size_t)bi * n * n)
+#define gA (p.A + (size_t)bi * m * n)
+#define gq (p.q + (size_t)bi * n)
+#define gl (p.l + (size_t)bi * m)
+#define gu (p.u + (size_t)bi * m)
 
         int status = p.status[b];
         int rho_updates = p.rho_updates[b];
-        double rho_est = p.rho_estimate[b], res_prim = p.res_prim[b], res_dual = p.res_dual[b];
+        // rho_estimate / res_prim / res_dual (QPSolverInfo, qp.hpp:76-78) only change at checks: kept in shared memory
+        if (tid == 0) {
+            s_info[0] = p.rho_estimate[b];
+            s_info[1] = p.res_prim[b];
+            s_info[2] = p.res_dual[b];
+        }
         double rho = p.rho[b];
         int iter_out = p.iter[b];
         const bool reset = (p.mode & MODE_RESET) != 0;
 
         // ---- per-row state in the owner lanes' registers ----------------------------------------
-        double zr[RO], yr[RO], lo[RO], up[RO], rhor[RO], rinv[RO], axr[RO];
+        double zr[RO], yr[RO], lo[RO], up[RO], rhor[RO], rinv[RO];
         int typ[RO];
 #pragma unroll
         for (int t = 0; t < RO; ++t) {
@@ -276,7 +318,6 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             up[t] = real ? gu[i] : INF;
             zr[t] = (real && !reset) ? p.z[b * m + i] : 0.0;
             yr[t] = (real && !reset) ? p.y[b * m + i] : 0.0;
-            axr[t] = 0.0;
             if (p.mode & MODE_FACTOR) {
                 typ[t] = classify(lo[t], up[t]);
                 if (real && row_primary) p.ctype[b * m + i] = (signed char)typ[t];
@@ -300,13 +341,40 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 
         // ---- stage A (zero padded) and pull this lane's tile into registers -----------------------
         double a[R][C];
+        // Full-size, 16-byte aligned problems are staged by TMA bulk copies (one per matrix column, into the
+        // padded shared-memory columns) issued by warp 0 and awaited on an mbarrier; ragged or unaligned ones
+        // fall back to guarded, coalesced loads with zero padding. Callers synchronise the CTA before (no reader
+        // of the region is left) and after.
+        const bool bulk = n == NP && m == MP && ((reinterpret_cast<uintptr_t>(gA) | reinterpret_cast<uintptr_t>(gP)) & 15) == 0;
         auto stage_A = [&]() {
+            if (bulk) {
+                if (warp == 0) {
+                    fence_proxy_async();
+                    if (lane == 0) mbar_expect_tx(&s_mbar, (unsigned)(NP * MP * sizeof(double)));
+                    __syncwarp();
+                    for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sA + LS * j, gA + (size_t)MP * j, (unsigned)(MP * sizeof(double)), &s_mbar);
+                }
+                mbar_wait(&s_mbar, mbar_parity);
+                mbar_parity ^= 1;
+                return;
+            }
             for (int e = tid; e < NP * MP; e += T) {
                 const int i = e % MP, j = e / MP;
                 sA[i + LS * j] = (i < m && j < n) ? gA[i + (size_t)m * j] : 0.0;
             }
         };
         auto load_P = [&]() {
+            if (bulk) {
+                if (warp == 0) {
+                    fence_proxy_async();
+                    if (lane == 0) mbar_expect_tx(&s_mbar, (unsigned)(NP * NP * sizeof(double)));
+                    __syncwarp();
+                    for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sP + HS * j, gP + (size_t)NP * j, (unsigned)(NP * sizeof(double)), &s_mbar);
+                }
+                mbar_wait(&s_mbar, mbar_parity);
+                mbar_parity ^= 1;
+                return;
+            }
             for (int e = tid; e < NP * NP; e += T) {
                 const int i = e % NP, j = e / NP;
                 sP[i + HS * j] = (i < n && j < n) ? gP[i + (size_t)n * j] : 0.0;
@@ -478,12 +546,6 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 if (!((p.mode & MODE_SOLVE) && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES)) break;
                 in_solve = true;
                 iter = 1;
-                if (!reset) {  // A x for the warm-start iterate (ax is then carried by recurrence)
-                    double t0[RO];
-                    TL::mv_A(a, sx, lc, lane, t0);
-#pragma unroll
-                    for (int t = 0; t < RO; ++t) axr[t] = t0[t];
-                }
             }
             bool refactor = false;
             // iterations until the next termination check / adaptive-rho step (replaces iter % N, qp.cpp:105,125)
@@ -532,7 +594,6 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         const double zn = box_project(zh + rinv[t] * yr[t], lo[t], up[t]);
                         yr[t] = yr[t] + rhor[t] * (zh - zn);
                         zr[t] = zn;
-                        axr[t] = alpha * zt[t] + (1.0 - alpha) * axr[t];  // A x by linearity of the x update
                     }
                 }
                 const bool chk = --to_chk == 0;
@@ -542,11 +603,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 if (chk || adapt) {
                     // update_state, qp.cpp:316-331
                     double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
+                    {
+                        double ax[RO];  // A x (x, not x~: they differ when alpha != 1), qp.cpp:319
+                        TL::mv_A(a, sx, lc, lane, ax);
 #pragma unroll
-                    for (int t = 0; t < RO; ++t) {
-                        mx[0] = absmax(mx[0], axr[t]);
-                        mx[1] = absmax(mx[1], zr[t]);
-                        mx[5] = absmax(mx[5], axr[t] - zr[t]);
+                        for (int t = 0; t < RO; ++t) {
+                            mx[0] = absmax(mx[0], ax[t]);
+                            mx[1] = absmax(mx[1], zr[t]);
+                            mx[5] = absmax(mx[5], ax[t] - zr[t]);
+                        }
                     }
                     if (row_primary) {
 #pragma unroll
@@ -586,8 +651,11 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     }
                     const double sc_p = fmax(mx[0], mx[1]);
                     const double sc_d = fmax(mx[2], fmax(mx[3], mx[4]));
-                    res_prim = mx[5];
-                    res_dual = mx[6];
+                    const double res_prim = mx[5], res_dual = mx[6];
+                    if (tid == 0) {
+                        s_info[1] = res_prim;
+                        s_info[2] = res_dual;
+                    }
                     if (chk) {  // termination_criteria, qp.cpp:363-371
                         if (res_prim <= st.eps_abs + st.eps_rel * sc_p && res_dual <= st.eps_abs + st.eps_rel * sc_d) {
                             status = SQPB200_SOLVED;
@@ -596,7 +664,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     }
                     if (adapt) {  // qp.cpp:125-144
                         const double new_rho = rho_estimate_clamped(rho, res_prim, res_dual, sc_p, sc_d);
-                        rho_est = new_rho;
+                        if (tid == 0) s_info[0] = new_rho;
                         if (new_rho < rho / st.adaptive_rho_tolerance || new_rho > rho * st.adaptive_rho_tolerance) {
                             rho = new_rho;
                             rho_updates += 1;
@@ -650,14 +718,20 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             p.status[b] = status;
             p.iter[b] = iter_out;
             p.rho_updates[b] = rho_updates;
-            p.rho_estimate[b] = rho_est;
-            p.res_prim[b] = res_prim;
-            p.res_dual[b] = res_dual;
+            p.rho_estimate[b] = s_info[0];
+            p.res_prim[b] = s_info[1];
+            p.res_dual[b] = s_info[2];
             p.rho[b] = rho;
             if (executed) atomicAdd(p.total_iters, (unsigned long long)executed);
         }
     }
 }
+
+#undef gP
+#undef gA
+#undef gq
+#undef gl
+#undef gu
 
 // ---- dispatch ------------------------------------------------------------------------------------
 using Cfg64x128w4 = TileCfg<64, 128, 4, 8, 4, 2>;  // 128 threads: 8x8 A tile + 4x8 H^-1 tile per lane
