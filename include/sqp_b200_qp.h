@@ -84,7 +84,7 @@ typedef enum sqpb200_error {
 
 /* context options for sqpb200_ctx_set_option */
 #define SQPB200_OPT_KERNEL 1       /* 0 = auto (default), 1 = force the generic kernel, 2 = force the register-tiled kernel */
-#define SQPB200_OPT_H2D_CHUNKS 2   /* number of pipeline chunks for HOST_PTRS calls (default 8) */
+#define SQPB200_OPT_H2D_CHUNKS 2   /* number of staging chunks for HOST_PTRS calls (default 16) */
 #define SQPB200_OPT_CTAS_PER_SM 3  /* 0 = auto */
 #define SQPB200_OPT_TILE_WARPS 4   /* warps per QP of the 64x128 register-tiled kernel: 0 = default, 4, 8 (tuning/tests) */
 

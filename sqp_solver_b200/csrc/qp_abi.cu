@@ -20,11 +20,13 @@ struct sqpb200_ctx {
     cudaStream_t stream = nullptr;       // internal housekeeping stream (state initialisation)
     cudaStream_t copy_stream = nullptr;  // H2D staging for HOST_PTRS calls
     int *counters = nullptr;             // ring of work-queue counters, one per launch
+    int *ready_dev = nullptr;            // device flag: QPs staged so far (host-pointer calls)
+    int *ready_host = nullptr;           // pinned: chunk boundaries, source of the flag copies
     static constexpr int kCounters = 1024;
     long long launches = 0;
     double *scratch = nullptr;
     size_t scratch_bytes = 0;
-    int opt_kernel = 0, opt_chunks = 8, opt_ctas_per_sm = 0, opt_tile_warps = 0;
+    int opt_kernel = 0, opt_chunks = 16, opt_ctas_per_sm = 0, opt_tile_warps = 0;
     std::string err;
     char last_kernel[64] = "none";
     cudaEvent_t chunk_events[64]{};
@@ -105,7 +107,8 @@ int sqpb200_ctx_create(int device, sqpb200_ctx **out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&c->counters, sizeof(int) * sqpb200_ctx::kCounters)) != cudaSuccess) {
+        (e = cudaMalloc(&c->counters, sizeof(int) * sqpb200_ctx::kCounters)) != cudaSuccess ||
+        (e = cudaMalloc(&c->ready_dev, sizeof(int))) != cudaSuccess || (e = cudaMallocHost(&c->ready_host, sizeof(int) * 64)) != cudaSuccess) {
         int rc = fail(nullptr, SQPB200_ERR_CUDA, "sqpb200_ctx_create", e);
         delete c;
         return rc;
@@ -127,6 +130,8 @@ int sqpb200_ctx_destroy(sqpb200_ctx *c) {
         if (ev) cudaEventDestroy(ev);
     if (c->scratch) cudaFree(c->scratch);
     if (c->counters) cudaFree(c->counters);
+    if (c->ready_dev) cudaFree(c->ready_dev);
+    if (c->ready_host) cudaFreeHost(c->ready_host);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -292,7 +297,7 @@ static int ensure_staging(sqpb200_qp_batch *b) {
 // One kernel launch over QPs [first, first+count) of the batch arrays.
 static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode, int first, int count,
                         const double *P, const double *q, const double *A, const double *l, const double *u,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const int *ready = nullptr) {
     sqpb200_ctx *c = b->ctx;
     KernelParams p{};
     p.first = first;
@@ -306,6 +311,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     p.ctype = b->ctype;
     p.total_iters = b->total_iters;
     p.mode = mode;
+    p.ready = ready;
     p.s = *st;
     int slot = (int)(c->launches % sqpb200_ctx::kCounters);
     p.work_counter = c->counters + slot;
@@ -351,15 +357,19 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
     const size_t n = b->n, m = b->m;
     if (flags & SQPB200_DEVICE_PTRS) return launch_range(b, st, mode, 0, count, P, q, A, l, u, stream);
 
-    // HOST_PTRS: stage in chunks on the copy stream, overlap each chunk's H2D with the previous chunk's solve
+    // HOST_PTRS: ONE persistent launch over the whole batch; the inputs are staged chunk by chunk on the copy
+    // stream while it runs. After each chunk a 4-byte copy publishes how many QPs have landed; a CTA that
+    // draws a QP beyond that count waits (draw_qp). H2D and compute overlap with no per-chunk launch tails.
     int rc = ensure_staging(b);
     if (rc) return rc;
     int chunks = c->opt_chunks;
     if (chunks > count) chunks = count;
-    // the compute stream may still be reading the staging buffers from an earlier call
+    CK(c, cudaMemsetAsync(c->ready_dev, 0, sizeof(int), stream));
+    // the compute stream may still be reading the staging buffers from an earlier call; the flag reset must precede the copies
     CK(c, cudaEventRecord(c->chunk_events[63], stream));
     CK(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_events[63], 0));
     for (int k = 0; k < chunks; ++k) {
+        // early chunks are small so the first CTAs start after ~1 % of the transfer
         size_t lo = (size_t)count * k / chunks, hi = (size_t)count * (k + 1) / chunks, cnt = hi - lo;
         CK(c, cudaMemcpyAsync(b->dP + lo * n * n, P + lo * n * n, cnt * n * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
         CK(c, cudaMemcpyAsync(b->dA + lo * m * n, A + lo * m * n, cnt * m * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
@@ -368,10 +378,13 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
             CK(c, cudaMemcpyAsync(b->dl + lo * m, l + lo * m, cnt * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
             CK(c, cudaMemcpyAsync(b->du + lo * m, u + lo * m, cnt * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
         }
-        CK(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
-        CK(c, cudaStreamWaitEvent(stream, c->chunk_events[k], 0));
-        rc = launch_range(b, st, mode, (int)lo, (int)cnt, b->dP, b->dq, b->dA, b->dl, b->du, stream);
-        if (rc) return rc;
+        c->ready_host[k] = (int)hi;
+        CK(c, cudaMemcpyAsync(c->ready_dev, c->ready_host + k, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    rc = launch_range(b, st, mode, 0, count, b->dP, b->dq, b->dA, b->dl, b->du, stream, c->ready_dev);
+    if (rc) {
+        cudaStreamSynchronize(c->copy_stream);
+        return rc;
     }
     CK(c, cudaStreamSynchronize(stream));
     return SQPB200_OK;

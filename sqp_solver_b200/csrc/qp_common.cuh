@@ -49,6 +49,8 @@ struct KernelParams {
     double *fact;        // [B][n*n] H^-1 (column-major, full symmetric); may be null when fused
     double *scratch;     // generic kernel: per-CTA n*n workspace
     int *work_counter;   // persistent-CTA work queue
+    const int *ready;    // optional: number of leading QPs whose inputs have landed in device memory (host-staged calls);
+                         // a CTA that draws QP i waits until *ready > i. nullptr: everything is resident
     unsigned long long *total_iters;
     unsigned mode;
     sqpb200_qp_settings s;
@@ -73,6 +75,17 @@ __device__ __forceinline__ double box_project(double z, double l, double u) {
 __device__ __forceinline__ double absmax(double r, double v) {
     v = fabs(v);
     return v > r ? v : r;
+}
+// Draw the next QP of this launch from the work queue (one thread per CTA calls this). For host-staged
+// calls the inputs arrive chunk by chunk on a copy stream while the kernel is already running: wait
+// until the chunk holding this QP has landed (flag written by a stream-ordered 4-byte copy after the data).
+__device__ __forceinline__ int draw_qp(const KernelParams &p) {
+    const int v = atomicAdd(p.work_counter, 1);
+    if (p.ready != nullptr && v < p.count) {
+        while (*reinterpret_cast<const volatile int *>(p.ready) <= v) __nanosleep(500);
+        __threadfence();
+    }
+    return v;
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(GT) qp_generic_kernel(KernelParams p) {
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_qp = atomicAdd(p.work_counter, 1);
+        if (tid == 0) s_qp = draw_qp(p);
         __syncthreads();
         const int local = s_qp;
         if (local >= p.count) break;

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 
     for (;;) {
         cta_sync<NW>();
-        if (tid == 0) s_qp = atomicAdd(p.work_counter, 1);
+        if (tid == 0) s_qp = draw_qp(p);
         cta_sync<NW>();
         const int local = s_qp;
         if (local >= p.count) break;
