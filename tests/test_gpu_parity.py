@@ -330,3 +330,86 @@ def test_full_size_properties_config3(api, ctx, oracle):
     ref = oracle.solve_batch(d["P"][idx], d["q"][idx], d["A"][idx], d["l"][idx], d["u"][idx], oracle_settings_from(oracle, s))
     sub = {k: v[idx] for k, v in out.items() if isinstance(v, np.ndarray)}
     assert_parity(sub, ref, what="config 3 sample")
+
+
+def test_generic_kernel_beyond_tile_range(api, ctx, oracle):
+    """Shapes outside the register-tiled kernel (n > 64 or m > 128) dispatch to the generic kernel automatically."""
+    from sqp_solver_b200.synth import make_batch
+
+    for n, m, batch in ((80, 150, 6), (100, 40, 4), (20, 300, 4)):
+        d = make_batch(batch, n, m, seed0=9000)
+        s = api.default_settings(max_iter=300)
+        out = run_fused(api, ctx, d, s, "auto")
+        assert out["kernel"] == "generic"
+        ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+        assert_parity(out, ref, what="generic n=%d m=%d" % (n, m))
+
+
+def test_api_argument_errors(api, ctx):
+    """API-level failures come back as error codes with text (SURVEY.md 8b 'Errors'), never as a crash."""
+    from sqp_solver_b200.synth import make_batch
+
+    with pytest.raises(api.SolverError, match="batch >= 1"):
+        api.QPBatch(ctx, 0, 4, 4)
+    with pytest.raises(api.SolverError, match="too large"):
+        api.QPBatch(ctx, 1, 20000, 20000)
+    d = make_batch(3, 4, 5, seed0=2)
+    b = api.QPBatch(ctx, 3, 4, 5)
+    with pytest.raises(api.SolverError, match="count outside"):
+        b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"], count=4)
+    b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"], count=0)  # no-op
+    assert (b.info()["status"] == api.UNINITIALIZED).all()
+    with pytest.raises(api.SolverError, match="host arrays or all"):
+        import torch
+
+        b.setup_solve(torch.from_numpy(d["P"]).cuda(), d["q"], d["A"], d["l"], d["u"])
+    with pytest.raises(api.SolverError):
+        ctx.set_option(api.OPT_KERNEL, 7)
+    b.close()
+
+
+def test_two_batches_and_streams_are_independent(api, ctx, oracle):
+    """Two batch objects driven on two CUDA streams do not disturb each other's state."""
+    import torch
+    from sqp_solver_b200.synth import make_batch
+
+    d1, d2 = make_batch(24, 32, 64, seed0=11000), make_batch(16, 16, 24, seed0=12000)
+    dev1 = {k: torch.from_numpy(d1[k]).cuda() for k in ("P", "q", "A", "l", "u")}
+    dev2 = {k: torch.from_numpy(d2[k]).cuda() for k in ("P", "q", "A", "l", "u")}
+    torch.cuda.synchronize()
+    b1, b2 = api.QPBatch(ctx, 24, 32, 64), api.QPBatch(ctx, 16, 16, 24)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        b1.setup_solve(dev1["P"], dev1["q"], dev1["A"], dev1["l"], dev1["u"], stream=s1.cuda_stream)
+        b2.setup_solve(dev2["P"], dev2["q"], dev2["A"], dev2["l"], dev2["u"], stream=s2.cuda_stream)
+    torch.cuda.synchronize()
+    s = api.default_settings()
+    for b, d in ((b1, d1), (b2, d2)):
+        ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+        got = b.get()
+        assert (got.pop("rho_updates") == 3).all()  # cumulative over the three setups, like the reference (qp.cpp:313)
+        assert_parity(got, ref, what="concurrent batches")
+    b1.close()
+    b2.close()
+
+
+def test_linearity_property_full_size_config2(api, ctx):
+    """Size-independent property at BASELINE config 2 (batch 1024, n=32, m=64): scaling the objective (P, q) and
+    rho by c > 0 leaves the primal ADMM trajectory unchanged and scales the duals by c."""
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(1024, 32, 64, seed0=5)
+    # loose rows keep rho = RHO_MIN whatever rho is, which breaks the scaling symmetry: make them wide finite boxes
+    d["l"] = np.maximum(d["l"], -50.0)
+    d["u"] = np.minimum(d["u"], 50.0)
+    c = 4.0  # a power of two: the scaled run is the same floating-point computation up to exact scaling
+    s = api.default_settings(eps_abs=0.0, eps_rel=1e-3, sigma=1e-6)
+    out1 = run_fused(api, ctx, d, s, "auto")
+    d2 = dict(d, P=d["P"] * c, q=d["q"] * c)
+    s2 = api.default_settings(eps_abs=0.0, eps_rel=1e-3, sigma=1e-6 * c, rho=0.1 * c)
+    out2 = run_fused(api, ctx, d2, s2, "auto")
+    np.testing.assert_array_equal(out1["iter"], out2["iter"])
+    np.testing.assert_array_equal(out1["status"], out2["status"])
+    np.testing.assert_allclose(out2["x"], out1["x"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out2["y"], c * out1["y"], rtol=1e-9, atol=1e-11)
+    assert (out1["status"] == api.SOLVED).sum() > 512
