@@ -45,10 +45,14 @@ struct TileCfg {
     static_assert(CG >= 2 && CG <= 16 && (CG & (CG - 1)) == 0 && NP % CG == 0, "symmetric tile: column groups");
     static_assert(HR >= 2 && HR % 2 == 0 && HR <= CG && NP % HR == 0 && (NP / HR) * CG == T, "symmetric tile: rows");
     static_assert(R == 1 || R % 2 == 0, "row tile must be vectorisable");
-    static_assert(NP * HS <= NP * LS, "P must fit in the A staging region it aliases");
     static_assert(T >= NP, "b stage needs one thread per variable");
     // shared memory carve-up (doubles)
-    static constexpr int OFF_STAGE = 0;  // A staging copy during (re)factorisation; P afterwards
+    // The padded staging copy of A (needed only while H is formed) and the padded copy of P (needed afterwards, for
+    // P*x at the checks) share one region: a second 34 KB region would shrink the L1 that backs the few register
+    // spills of the hot loop and measurably slows it (26.7 ms vs 24.9 ms on config 3).
+    static_assert(NP * HS <= NP * LS, "P must fit in the A staging region it aliases");
+    static constexpr int OFF_STAGE = 0;
+    static constexpr int OFF_P = OFF_STAGE;
     static constexpr int OFF_PART = OFF_STAGE + NP * LS;
     static constexpr int OFF_X = OFF_PART + NW * NP;
     static constexpr int OFF_XT = OFF_X + NP;
@@ -58,7 +62,8 @@ struct TileCfg {
     static constexpr int OFF_W = OFF_PX + NP;
     static constexpr int OFF_RHO = OFF_W + MP;
     static constexpr int OFF_PIV = OFF_RHO + MP;
-    static constexpr int OFF_RED = OFF_PIV + 2 * NP;
+    static constexpr int PIVS = NP + 2;  // pivot column + 1/d + d
+    static constexpr int OFF_RED = OFF_PIV + 2 * PIVS;
     static constexpr int SMEM_DOUBLES = OFF_RED + 8 * NW;
     static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
 };
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     __shared__ __align__(8) unsigned long long s_mbar;  // completion barrier of the TMA bulk copies
     __shared__ double s_info[3];
     unsigned mbar_parity = 0;
-    double *sA = smem + Cfg::OFF_STAGE, *sP = smem + Cfg::OFF_STAGE;  // P replaces the staging copy of A once H is formed
+    double *sA = smem + Cfg::OFF_STAGE, *sP = smem + Cfg::OFF_P;
     double *part = smem + Cfg::OFF_PART, *sx = smem + Cfg::OFF_X, *sxt = smem + Cfg::OFF_XT, *sb = smem + Cfg::OFF_B;
     double *sq = smem + Cfg::OFF_Q, *spx = smem + Cfg::OFF_PX, *sw = smem + Cfg::OFF_W, *srho = smem + Cfg::OFF_RHO;
     double *piv = smem + Cfg::OFF_PIV, *red = smem + Cfg::OFF_RED;
@@ -346,42 +351,36 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         // fall back to guarded, coalesced loads with zero padding. Callers synchronise the CTA before (no reader
         // of the region is left) and after.
         const bool bulk = n == NP && m == MP && ((reinterpret_cast<uintptr_t>(gA) | reinterpret_cast<uintptr_t>(gP)) & 15) == 0;
-        auto stage_A = [&]() {
+        // stage(A?, P?): both land on the same mbarrier phase, so the first staging of a QP overlaps the two loads
+        auto stage = [&](bool want_A, bool want_P) {
             if (bulk) {
                 if (warp == 0) {
                     fence_proxy_async();
-                    if (lane == 0) mbar_expect_tx(&s_mbar, (unsigned)(NP * MP * sizeof(double)));
+                    if (lane == 0)
+                        mbar_expect_tx(&s_mbar, (unsigned)(((want_A ? NP * MP : 0) + (want_P ? NP * NP : 0)) * sizeof(double)));
                     __syncwarp();
-                    for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sA + LS * j, gA + (size_t)MP * j, (unsigned)(MP * sizeof(double)), &s_mbar);
+                    if (want_A)
+                        for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sA + LS * j, gA + (size_t)MP * j, (unsigned)(MP * sizeof(double)), &s_mbar);
+                    if (want_P)
+                        for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sP + HS * j, gP + (size_t)NP * j, (unsigned)(NP * sizeof(double)), &s_mbar);
                 }
                 mbar_wait(&s_mbar, mbar_parity);
                 mbar_parity ^= 1;
                 return;
             }
-            for (int e = tid; e < NP * MP; e += T) {
-                const int i = e % MP, j = e / MP;
-                sA[i + LS * j] = (i < m && j < n) ? gA[i + (size_t)m * j] : 0.0;
-            }
-        };
-        auto load_P = [&]() {
-            if (bulk) {
-                if (warp == 0) {
-                    fence_proxy_async();
-                    if (lane == 0) mbar_expect_tx(&s_mbar, (unsigned)(NP * NP * sizeof(double)));
-                    __syncwarp();
-                    for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sP + HS * j, gP + (size_t)NP * j, (unsigned)(NP * sizeof(double)), &s_mbar);
+            if (want_A)
+                for (int e = tid; e < NP * MP; e += T) {
+                    const int i = e % MP, j = e / MP;
+                    sA[i + LS * j] = (i < m && j < n) ? gA[i + (size_t)m * j] : 0.0;
                 }
-                mbar_wait(&s_mbar, mbar_parity);
-                mbar_parity ^= 1;
-                return;
-            }
-            for (int e = tid; e < NP * NP; e += T) {
-                const int i = e % NP, j = e / NP;
-                sP[i + HS * j] = (i < n && j < n) ? gP[i + (size_t)n * j] : 0.0;
-            }
+            if (want_P)
+                for (int e = tid; e < NP * NP; e += T) {
+                    const int i = e % NP, j = e / NP;
+                    sP[i + HS * j] = (i < n && j < n) ? gP[i + (size_t)n * j] : 0.0;
+                }
         };
         // H^-1 from the staged A, kept in registers hv[HR][HC]: SYRK, then symmetric elimination.
-        // Requires sA staged and srho written; ends with sP valid and the CTA synchronised.
+        // Requires sA staged; ends with sP valid (it replaces the staging copy) and the CTA synchronised.
         double hv[HR][HC];
         auto factorize = [&]() -> bool {
 #pragma unroll
@@ -430,19 +429,26 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #pragma unroll 1
                 for (int cgk = 0; cgk < CG; ++cgk) {
                     const int k = cgk + CG * s;
-                    double *pv = piv + (k & 1) * NP;
+                    double *pv = piv + (k & 1) * Cfg::PIVS;
+                    const int krow = k - i0;  // row of this lane's tile that is the pivot row (if 0 <= krow < HR)
                     if (cg == cgk) {
 #pragma unroll
                         for (int r = 0; r < HR; r += 2) *reinterpret_cast<double2 *>(pv + i0 + r) = make_double2(hv[r][s], hv[r + 1][s]);
+                        if ((unsigned)krow < (unsigned)HR) {  // the one lane that owns the pivot publishes d and 1/d
+                            double d = hv[0][s];
+#pragma unroll
+                            for (int r = 1; r < HR; ++r) d = (r == krow) ? hv[r][s] : d;
+                            pv[NP] = 1.0 / d;
+                            pv[NP + 1] = d;
+                        }
                     }
                     cta_sync<NW>();
-                    const double d = pv[k];
-                    if (!(fabs(d) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
+                    const double2 dd = *reinterpret_cast<const double2 *>(pv + NP);
+                    const double inv_d = dd.x;
+                    if (!(fabs(dd.y) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
                         ok = false;
                         break;
                     }
-                    const double inv_d = 1.0 / d;
-                    const int krow = k - i0;  // row of this lane's tile that is the pivot row (if 0 <= krow < HR)
                     double t[HR];
 #pragma unroll
                     for (int r = 0; r < HR; r += 2) {
@@ -453,11 +459,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #pragma unroll
                     for (int s2 = 0; s2 < HC; ++s2) {
                         const double cj = pv[cg + CG * s2];
-                        const double rowv = cj * inv_d;
 #pragma unroll
-                        for (int r = 0; r < HR; ++r) {
-                            const double v = fma(-t[r], cj, hv[r][s2]);
-                            hv[r][s2] = (r == krow) ? rowv : v;
+                        for (int r = 0; r < HR; ++r) hv[r][s2] = fma(-t[r], cj, hv[r][s2]);
+                    }
+                    if ((unsigned)krow < (unsigned)HR) {  // the row group holding pivot row k: that row becomes c_j / d
+#pragma unroll
+                        for (int s2 = 0; s2 < HC; ++s2) {
+                            const double rowv = pv[cg + CG * s2] * inv_d;
+#pragma unroll
+                            for (int r = 0; r < HR; ++r) hv[r][s2] = (r == krow) ? rowv : hv[r][s2];
                         }
                     }
                     if (cg == cgk) {
@@ -472,17 +482,13 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #pragma unroll
                 for (int r = 0; r < HR; ++r) hv[r][s] = -hv[r][s];
             cta_sync<NW>();
-            load_P();
+            stage(false, true);  // P replaces the staging copy of A
             cta_sync<NW>();
             return ok;
         };
 
         cta_sync<NW>();
-        stage_A();
-        if (row_primary) {
-#pragma unroll
-            for (int t = 0; t < RO; ++t) srho[own0 + t] = rhor[t];
-        }
+        stage(true, false);
         cta_sync<NW>();
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) {
@@ -498,9 +504,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 a[0][kk] = colp[0];
             }
         }
-        bool do_factor = (p.mode & MODE_FACTOR) != 0, staged = true, in_solve = false;
+        bool do_factor = (p.mode & MODE_FACTOR) != 0, first_factor = true, in_solve = false;
         if (!do_factor) {
-            cta_sync<NW>();  // tiles are in registers; the staging area may be overwritten
             const double *gF = p.fact + b * n * n;
 #pragma unroll
             for (int s = 0; s < HC; ++s) {
@@ -511,9 +516,10 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     hv[r][s] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? 1.0 : 0.0);
                 }
             }
-            load_P();
+            cta_sync<NW>();  // tiles are in registers; the staging area may be overwritten
+            stage(false, true);
             cta_sync<NW>();
-            staged = false;  // the staging copy of A has just been overwritten
+            first_factor = false;  // the staging copy of A is gone
         }
 
         long long executed = 0;
@@ -522,17 +528,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         // next adaptive-rho refactorisation.  A single factorisation call site keeps the code compact.
         for (;;) {
             if (do_factor) {
-                if (!staged) {
-                    cta_sync<NW>();  // all reads of sP done before the staging overwrites it
-                    stage_A();
-                    if (row_primary) {
+                cta_sync<NW>();
+                if (!first_factor) stage(true, false);  // adaptive-rho refactorisation: bring A back (P is reloaded after)
+                if (row_primary) {
 #pragma unroll
-                        for (int t = 0; t < RO; ++t) srho[own0 + t] = rhor[t];
-                    }
-                    cta_sync<NW>();
+                    for (int t = 0; t < RO; ++t) srho[own0 + t] = rhor[t];
                 }
+                cta_sync<NW>();
                 const bool ok = factorize();
-                staged = false;
+                first_factor = false;
                 do_factor = false;
                 if (!in_solve) {
                     status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
