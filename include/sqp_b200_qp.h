@@ -137,6 +137,18 @@ int sqpb200_qp_batch_setup_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings 
                                  const double *q, const double *A, const double *l, const double *u, unsigned flags,
                                  void *stream);
 
+/* setup_solve with factor bookkeeping for callers that re-solve the SAME P and A with new q, l, u -- the
+ * second-order-correction QP of SQP<T>::second_order_correction (sqp.cpp:244-276, "TODO: only l and u change").
+ *   SQPB200_KEEP_FACTOR   remember each instance's setup factor (one n*n store per QP)
+ *   SQPB200_REUSE_FACTOR  the caller guarantees P and A are those of the call that kept the factor; every instance whose
+ *                         constraint classes (from the new l, u) and settings->rho are unchanged skips the factorisation,
+ *                         the others factor as usual. Results are bit-identical to a plain setup_solve. */
+#define SQPB200_KEEP_FACTOR 1u
+#define SQPB200_REUSE_FACTOR 2u
+int sqpb200_qp_batch_setup_solve_opts(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                                      const double *q, const double *A, const double *l, const double *u, unsigned flags,
+                                      void *stream, unsigned opts);
+
 /* Read back solutions and info (any pointer may be NULL). primal_solution()/dual_solution()/info(),
  * qp.hpp:159-169; z is exposed in addition so a caller can checkpoint a warm start. */
 int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,

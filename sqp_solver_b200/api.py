@@ -23,13 +23,15 @@ STATUS_NAMES = ["SOLVED", "MAX_ITER_EXCEEDED", "UNSOLVED", "NUMERICAL_ISSUES", "
 HOST_PTRS, DEVICE_PTRS = 0, 1
 OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS = 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE = 0, 1, 2
+KEEP_FACTOR, REUSE_FACTOR = 1, 2
 
 # every symbol include/sqp_b200_qp.h declares (checked by tests/test_abi_symbols.py)
 ABI_SYMBOLS = [
     "sqpb200_abi_version", "sqpb200_ctx_create", "sqpb200_ctx_destroy", "sqpb200_ctx_set_option", "sqpb200_last_error",
     "sqpb200_device_query", "sqpb200_launch_count", "sqpb200_last_kernel", "sqpb200_qp_default_settings",
     "sqpb200_constr_type_init", "sqpb200_qp_batch_create", "sqpb200_qp_batch_destroy", "sqpb200_qp_batch_setup",
-    "sqpb200_qp_batch_update_qp", "sqpb200_qp_batch_solve", "sqpb200_qp_batch_setup_solve", "sqpb200_qp_batch_get",
+    "sqpb200_qp_batch_update_qp", "sqpb200_qp_batch_solve", "sqpb200_qp_batch_setup_solve",
+    "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
     "sqpb200_qp_solve_batch",
 ]
@@ -84,6 +86,7 @@ def load_library(path=None):
     L.sqpb200_qp_batch_destroy.argtypes = [vp]
     for name in ("setup", "update_qp", "solve", "setup_solve"):
         getattr(L, "sqpb200_qp_batch_" + name).argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp]
+    L.sqpb200_qp_batch_setup_solve_opts.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp, C.c_uint]
     L.sqpb200_qp_batch_get.argtypes = [vp, C.c_int, dp, dp, dp, ip, ip, ip, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_set_iterates.argtypes = [vp, C.c_int, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_device_view.argtypes = [vp, C.POINTER(DeviceView)]
@@ -209,7 +212,7 @@ class QPBatch:
         except Exception:
             pass
 
-    def _call(self, name, P, q, A, l, u, count, stream):
+    def _call(self, name, P, q, A, l, u, count, stream, opts=None):
         count = self.batch if count is None else int(count)
         ptrs, spaces = [], set()
         for nm, a in (("P", P), ("q", q), ("A", A), ("l", l), ("u", u)):
@@ -225,7 +228,8 @@ class QPBatch:
 
             stream = torch.cuda.current_stream().cuda_stream
         fn = getattr(self._L, "sqpb200_qp_batch_" + name)
-        self.ctx._check(fn(self._h, C.byref(self.settings), count, *ptrs, flags, C.c_void_p(stream or 0)), name)
+        extra = () if opts is None else (int(opts),)
+        self.ctx._check(fn(self._h, C.byref(self.settings), count, *ptrs, flags, C.c_void_p(stream or 0), *extra), name)
 
     def setup(self, P, q, A, l, u, count=None, stream=None):  # QPSolver::setup, qp.cpp:11-44
         self._call("setup", P, q, A, l, u, count, stream)
@@ -236,8 +240,12 @@ class QPBatch:
     def solve(self, P, q, A, l, u, count=None, stream=None):  # QPSolver::solve, qp.cpp:64-157
         self._call("solve", P, q, A, l, u, count, stream)
 
-    def setup_solve(self, P, q, A, l, u, count=None, stream=None):  # sqp.cpp:221-222 fused
-        self._call("setup_solve", P, q, A, l, u, count, stream)
+    def setup_solve(self, P, q, A, l, u, count=None, stream=None, opts=0):  # sqp.cpp:221-222 fused
+        """opts: KEEP_FACTOR / REUSE_FACTOR for re-solves with the same P and A (sqp.cpp:244-276)."""
+        if opts:
+            self._call("setup_solve_opts", P, q, A, l, u, count, stream, opts=opts)
+        else:
+            self._call("setup_solve", P, q, A, l, u, count, stream)
 
     def get(self, count=None, fields=("x", "y", "z", "status", "iter", "rho_updates", "rho_estimate", "res_prim", "res_dual")):
         """Copy results to fresh host arrays (synchronises)."""

@@ -40,6 +40,7 @@ struct sqpb200_qp_batch {
     double *rho_estimate = nullptr, *res_prim = nullptr, *res_dual = nullptr, *rho = nullptr;
     signed char *ctype = nullptr;
     double *fact = nullptr;  // lazily allocated
+    double *fact_rho = nullptr;
     bool fused_used = false;
     bool fact_valid = false;  // a setup()/update_qp()/solve() launch has stored H^-1, rho and classes
     unsigned long long *total_iters = nullptr;
@@ -182,7 +183,7 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
-                    b->rho, b->ctype, b->fact, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du};
+                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -219,6 +220,7 @@ int sqpb200_qp_batch_create(sqpb200_ctx *c, int batch, int n, int m, sqpb200_qp_
     alloc((void **)&b->res_dual, B * sizeof(double));
     alloc((void **)&b->rho, B * sizeof(double));
     alloc((void **)&b->ctype, B * mm);
+    alloc((void **)&b->fact_rho, B * sizeof(double));
     alloc((void **)&b->total_iters, sizeof(unsigned long long));
     if (e != cudaSuccess) {
         int rc = fail(c, e == cudaErrorMemoryAllocation ? SQPB200_ERR_NOMEM : SQPB200_ERR_CUDA, "sqpb200_qp_batch_create: cudaMalloc", e);
@@ -237,6 +239,7 @@ int sqpb200_qp_batch_create(sqpb200_ctx *c, int batch, int n, int m, sqpb200_qp_
     cudaMemsetAsync(b->res_dual, 0, B * sizeof(double), s);
     cudaMemsetAsync(b->rho, 0, B * sizeof(double), s);
     cudaMemsetAsync(b->ctype, 0, B * mm, s);
+    cudaMemsetAsync(b->fact_rho, 0xff, B * sizeof(double), s);  // all-ones bit pattern is a NaN: no factor stored
     cudaMemsetAsync(b->total_iters, 0, sizeof(unsigned long long), s);
     // status = UNINITIALIZED (4): byte pattern 0x04040404 is not 4, so fill through a tiny kernel-free path
     {
@@ -309,6 +312,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     p.status = b->status; p.iter = b->iter; p.rho_updates = b->rho_updates;
     p.rho_estimate = b->rho_estimate; p.res_prim = b->res_prim; p.res_dual = b->res_dual; p.rho = b->rho;
     p.ctype = b->ctype;
+    p.fact_rho = b->fact_rho;
     p.total_iters = b->total_iters;
     p.mode = mode;
     p.ready = ready;
@@ -319,7 +323,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
 
     const bool want_tile = c->opt_kernel != 1 && tile_supported(b->n, b->m);
     if (c->opt_kernel == 2 && !want_tile) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
-    const bool needs_fact = !want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR));
+    const bool needs_fact = !want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE));
     if (needs_fact) {
         int rc = ensure_fact(b);
         if (rc) return rc;
@@ -424,6 +428,19 @@ int sqpb200_qp_batch_setup_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings 
         b->fused_used = true;
     }
     return run(b, s, MODE_RESET | MODE_FACTOR | MODE_SOLVE, count, P, q, A, l, u, flags, stream);
+}
+
+int sqpb200_qp_batch_setup_solve_opts(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P,
+                                      const double *q, const double *A, const double *l, const double *u, unsigned flags,
+                                      void *stream, unsigned opts) {
+    if (!b) return SQPB200_ERR_INVALID;
+    if (opts & ~(SQPB200_KEEP_FACTOR | SQPB200_REUSE_FACTOR)) return fail(b->ctx, SQPB200_ERR_INVALID, "unknown opts bit");
+    unsigned mode = MODE_RESET | MODE_FACTOR | MODE_SOLVE;
+    if (opts & SQPB200_KEEP_FACTOR) mode |= MODE_KEEP_INITIAL;
+    if (opts & SQPB200_REUSE_FACTOR) mode |= MODE_REUSE;
+    b->fact_valid = false;
+    b->fused_used = true;
+    return run(b, s, mode, count, P, q, A, l, u, flags, stream);
 }
 
 int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,

@@ -35,6 +35,9 @@ enum : unsigned {
     MODE_SOLVE = 4u,         // ADMM loop                                        (qp.cpp:64-157)
     MODE_STORE_FACTOR = 8u,  // keep H^-1, rho, constraint classes for a later solve() launch
     MODE_LOAD_FACTOR = 16u,  // solve() after a separate setup()/update_qp()
+    MODE_KEEP_INITIAL = 32u, // with FACTOR: remember the setup factor (for settings.rho) in the slab, tagged with its rho
+    MODE_REUSE = 64u,        // with FACTOR: same P, A as the launch that kept the factor; skip the factorisation of every
+                             // instance whose constraint classes and rho are unchanged (the TODO at reference sqp.cpp:273)
 };
 
 struct KernelParams {
@@ -47,6 +50,7 @@ struct KernelParams {
     double *rho_estimate, *res_prim, *res_dual, *rho;
     signed char *ctype;  // [B][m] constraint classes of the last setup/update_qp
     double *fact;        // [B][n*n] H^-1 (column-major, full symmetric); may be null when fused
+    double *fact_rho;    // [B] scalar rho the stored H^-1 belongs to (NaN: none stored)
     double *scratch;     // generic kernel: per-CTA n*n workspace
     int *work_counter;   // persistent-CTA work queue
     const int *ready;    // optional: number of leading QPs whose inputs have landed in device memory (host-staged calls);

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(GT) qp_generic_kernel(KernelParams p) {
         double rho_est = p.rho_estimate[b], res_prim = p.res_prim[b], res_dual = p.res_dual[b];
         double rho = p.rho[b];
         int iter_out = p.iter[b];
+        bool same_classes = true;
 
         for (int i = tid; i < n; i += GT) {
             s.q[i] = q[i];
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(GT) qp_generic_kernel(KernelParams p) {
             for (int i = tid; i < m; i += GT) {
                 int t = classify(l[i], u[i]);
                 s.type[i] = t;
+                if ((p.mode & MODE_REUSE) && p.ctype[b * m + i] != (signed char)t) same_classes = false;
                 p.ctype[b * m + i] = (signed char)t;
             }
         } else {
@@ -161,8 +163,15 @@ __global__ void __launch_bounds__(GT) qp_generic_kernel(KernelParams p) {
         }
         __syncthreads();
         if (p.mode & MODE_FACTOR) {
-            bool ok = factor_generic(P, A, s, n, m, st.sigma, H, W, &s_fail);
-            status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+            // MODE_REUSE: same P, A as the launch whose factor sits in the slab; skip when classes and rho are unchanged
+            const bool reuse = (p.mode & MODE_REUSE) && __syncthreads_and(same_classes && p.fact_rho[b] == st.rho);
+            if (reuse) {
+                status = SQPB200_UNSOLVED;
+            } else {
+                bool ok = factor_generic(P, A, s, n, m, st.sigma, H, W, &s_fail);
+                status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+                if (tid == 0) p.fact_rho[b] = ok ? rho : nan("");
+            }
         }
 
         long long executed = 0;
@@ -264,7 +273,9 @@ __global__ void __launch_bounds__(GT) qp_generic_kernel(KernelParams p) {
                                 s.rhoinv[i] = 1.0 / r;
                             }
                             __syncthreads();
-                            if (!factor_generic(P, A, s, n, m, sigma, H, W, &s_fail)) {
+                            const bool ok2 = factor_generic(P, A, s, n, m, sigma, H, W, &s_fail);
+                            if (tid == 0) p.fact_rho[b] = ok2 ? rho : nan("");  // the slab now holds the factor for the new rho
+                            if (!ok2) {
                                 status = SQPB200_NUMERICAL_ISSUES;
                                 break;
                             }

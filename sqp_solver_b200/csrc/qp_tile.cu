@@ -63,7 +63,8 @@ struct TileCfg {
     static constexpr int OFF_RHO = OFF_W + MP;
     static constexpr int OFF_PIV = OFF_RHO + MP;
     static constexpr int PIVS = NP + 2;  // pivot column + 1/d + d
-    static constexpr int OFF_RED = OFF_PIV + 2 * PIVS;
+    static constexpr int OFF_BND = OFF_PIV + 2 * PIVS;  // (l, u) pairs per row: read once per iteration by the row owner
+    static constexpr int OFF_RED = OFF_BND + 2 * MP;
     static constexpr int SMEM_DOUBLES = OFF_RED + 8 * NW;
     static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
 };
@@ -97,6 +98,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
                  : "memory");
 }
 
+template <int NW>
+__device__ __forceinline__ bool cta_all(bool pred) {
+    if constexpr (NW == 1) return __all_sync(0xffffffffu, pred);
+    else return __syncthreads_and(pred) != 0;
+}
 template <int NW>
 __device__ __forceinline__ void cta_sync() {
     if constexpr (NW == 1) __syncwarp();
@@ -264,12 +270,13 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_qp, s_fail;
     __shared__ __align__(8) unsigned long long s_mbar;  // completion barrier of the TMA bulk copies
-    __shared__ double s_info[3];
+    __shared__ double s_info[4];  // rho_estimate, res_prim, res_dual, rho (CTA-uniform scalars that only change at checks)
+    __shared__ int s_cnt[1];      // rho_updates
     unsigned mbar_parity = 0;
     double *sA = smem + Cfg::OFF_STAGE, *sP = smem + Cfg::OFF_P;
     double *part = smem + Cfg::OFF_PART, *sx = smem + Cfg::OFF_X, *sxt = smem + Cfg::OFF_XT, *sb = smem + Cfg::OFF_B;
     double *sq = smem + Cfg::OFF_Q, *spx = smem + Cfg::OFF_PX, *sw = smem + Cfg::OFF_W, *srho = smem + Cfg::OFF_RHO;
-    double *piv = smem + Cfg::OFF_PIV, *red = smem + Cfg::OFF_RED;
+    double *piv = smem + Cfg::OFF_PIV, *red = smem + Cfg::OFF_RED, *sbnd = smem + Cfg::OFF_BND;
 
     const int n = p.n, m = p.m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -301,42 +308,39 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #define gu (p.u + (size_t)bi * m)
 
         int status = p.status[b];
-        int rho_updates = p.rho_updates[b];
         // rho_estimate / res_prim / res_dual (QPSolverInfo, qp.hpp:76-78) only change at checks: kept in shared memory
         if (tid == 0) {
             s_info[0] = p.rho_estimate[b];
             s_info[1] = p.res_prim[b];
             s_info[2] = p.res_dual[b];
+            s_info[3] = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
+            s_cnt[0] = p.rho_updates[b] + ((p.mode & MODE_FACTOR) ? 1 : 0);  // rho_vec_update, qp.cpp:313
         }
-        double rho = p.rho[b];
-        int iter_out = p.iter[b];
+        const double rho0 = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
         const bool reset = (p.mode & MODE_RESET) != 0;
 
         // ---- per-row state in the owner lanes' registers ----------------------------------------
-        double zr[RO], yr[RO], lo[RO], up[RO], rhor[RO], rinv[RO];
-        int typ[RO];
+        double zr[RO], yr[RO], rhor[RO], rinv[RO];
+        bool same_classes = true;
 #pragma unroll
         for (int t = 0; t < RO; ++t) {
             const int i = own0 + t;
             const bool real = i < m;
-            lo[t] = real ? gl[i] : -INF;
-            up[t] = real ? gu[i] : INF;
+            const double lo = real ? gl[i] : -INF, up = real ? gu[i] : INF;
+            if (row_primary) *reinterpret_cast<double2 *>(sbnd + 2 * i) = make_double2(lo, up);
             zr[t] = (real && !reset) ? p.z[b * m + i] : 0.0;
             yr[t] = (real && !reset) ? p.y[b * m + i] : 0.0;
+            int typ;
             if (p.mode & MODE_FACTOR) {
-                typ[t] = classify(lo[t], up[t]);
-                if (real && row_primary) p.ctype[b * m + i] = (signed char)typ[t];
+                typ = classify(lo, up);
+                if (real) {
+                    if ((p.mode & MODE_REUSE) && p.ctype[b * m + i] != (signed char)typ) same_classes = false;
+                    if (row_primary) p.ctype[b * m + i] = (signed char)typ;
+                }
             } else {
-                typ[t] = real ? p.ctype[b * m + i] : SQPB200_LOOSE_BOUNDS;
+                typ = real ? p.ctype[b * m + i] : SQPB200_LOOSE_BOUNDS;
             }
-        }
-        if (p.mode & MODE_FACTOR) {
-            rho = st.rho;
-            rho_updates += 1;  // rho_vec_update, qp.cpp:313
-        }
-#pragma unroll
-        for (int t = 0; t < RO; ++t) {
-            rhor[t] = rho_of(typ[t], rho);
+            rhor[t] = rho_of(typ, rho0);
             rinv[t] = 1.0 / rhor[t];
         }
         if (tid < NP) {
@@ -505,6 +509,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             }
         }
         bool do_factor = (p.mode & MODE_FACTOR) != 0, first_factor = true, in_solve = false;
+        if (do_factor && (p.mode & MODE_REUSE)) {
+            // same P and A as the launch that kept the factor: reuse it where classes and rho are unchanged
+            // (duplicate owner lanes read the old classes before the primary wrote the same row: benign, values equal or both differ)
+            const bool reuse = cta_all<NW>(same_classes && p.fact_rho[b] == st.rho);
+            if (reuse) {
+                do_factor = false;
+                status = SQPB200_UNSOLVED;
+            }
+        }
         if (!do_factor) {
             const double *gF = p.fact + b * n * n;
 #pragma unroll
@@ -540,6 +553,19 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 do_factor = false;
                 if (!in_solve) {
                     status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+                    if (ok && (p.mode & MODE_KEEP_INITIAL)) {
+                        double *gF = p.fact + b * n * n;
+#pragma unroll
+                        for (int s = 0; s < HC; ++s) {
+                            const int j = cg + CG * s;
+#pragma unroll
+                            for (int r = 0; r < HR; ++r) {
+                                const int i = i0 + r;
+                                if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
+                            }
+                        }
+                        if (tid == 0) p.fact_rho[b] = s_info[3];
+                    }
                 } else if (!ok) {
                     status = SQPB200_NUMERICAL_ISSUES;  // qp.cpp:139-142 (break before the loop increment)
                     iter -= 1;
@@ -595,7 +621,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #pragma unroll
                     for (int t = 0; t < RO; ++t) {
                         const double zh = alpha * zt[t] + (1.0 - alpha) * zr[t];
-                        const double zn = box_project(zh + rinv[t] * yr[t], lo[t], up[t]);
+                        const double2 bd = *reinterpret_cast<const double2 *>(sbnd + 2 * (own0 + t));
+                        const double zn = box_project(zh + rinv[t] * yr[t], bd.x, bd.y);
                         yr[t] = yr[t] + rhor[t] * (zh - zn);
                         zr[t] = zn;
                     }
@@ -645,6 +672,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         const double v = warp_max(mx[k]);
                         if (lane == 0) red[k * NW + warp] = v;
                     }
+                    const double rho = s_info[3];  // read before the barrier: thread 0 rewrites it after the decision below
                     cta_sync<NW>();
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
@@ -670,11 +698,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         const double new_rho = rho_estimate_clamped(rho, res_prim, res_dual, sc_p, sc_d);
                         if (tid == 0) s_info[0] = new_rho;
                         if (new_rho < rho / st.adaptive_rho_tolerance || new_rho > rho * st.adaptive_rho_tolerance) {
-                            rho = new_rho;
-                            rho_updates += 1;
+                            if (tid == 0) {
+                                s_info[3] = new_rho;
+                                s_cnt[0] += 1;
+                            }
 #pragma unroll
                             for (int t = 0; t < RO; ++t) {
-                                rhor[t] = rho_of(typ[t], rho);
+                                const int i = own0 + t;  // constraint classes were fixed by setup (qp.cpp:31): read them back
+                                const int typ = i < m ? p.ctype[b * m + i] : SQPB200_LOOSE_BOUNDS;
+                                rhor[t] = rho_of(typ, new_rho);
                                 rinv[t] = 1.0 / rhor[t];
                             }
                             refactor = true;
@@ -690,7 +722,6 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         if (in_solve) {
             executed = iter <= st.max_iter ? iter : st.max_iter;
             if (iter > st.max_iter) status = SQPB200_MAX_ITER_EXCEEDED;  // qp.cpp:147-149
-            iter_out = iter;                                            // qp.cpp:150
         }
 
         // ---- write back -----------------------------------------------------------------------------
@@ -717,15 +748,16 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
                 }
             }
+            if (tid == 0) p.fact_rho[b] = s_info[3];
         }
         if (tid == 0) {
             p.status[b] = status;
-            p.iter[b] = iter_out;
-            p.rho_updates[b] = rho_updates;
+            if (in_solve) p.iter[b] = iter;  // qp.cpp:150
+            p.rho_updates[b] = s_cnt[0];
             p.rho_estimate[b] = s_info[0];
             p.res_prim[b] = s_info[1];
             p.res_dual[b] = s_info[2];
-            p.rho[b] = rho;
+            p.rho[b] = s_info[3];
             if (executed) atomicAdd(p.total_iters, (unsigned long long)executed);
         }
     }

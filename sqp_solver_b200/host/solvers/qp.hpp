@@ -159,8 +159,14 @@ class BatchQPSolver {
         call(sqpb200_qp_batch_solve, "solve", P, q, A, l, u, count);
     }
     // setup immediately followed by solve in one launch: the pattern of SQP<T>::run_solve_qp (sqp.cpp:221-222)
-    void setup_solve(const double *P, const double *q, const double *A, const double *l, const double *u, int count = -1) {
-        call(sqpb200_qp_batch_setup_solve, "setup_solve", P, q, A, l, u, count);
+    // opts: SQPB200_KEEP_FACTOR / SQPB200_REUSE_FACTOR for re-solves of the same P, A with new q, l, u
+    void setup_solve(const double *P, const double *q, const double *A, const double *l, const double *u, int count = -1,
+                     unsigned opts = 0) {
+        auto fn = [opts](sqpb200_qp_batch *h, const sqpb200_qp_settings *s, int c, const double *P_, const double *q_, const double *A_,
+                         const double *l_, const double *u_, unsigned flags, void *stream) {
+            return sqpb200_qp_batch_setup_solve_opts(h, s, c, P_, q_, A_, l_, u_, flags, stream, opts);
+        };
+        call(fn, "setup_solve", P, q, A, l, u, count);
     }
 
     const double *primal_solution(int i = 0) const { return x_.data() + (size_t)i * n_; }

@@ -409,14 +409,14 @@ class BatchSQP {
                 slot_[na++] = (int)i;
             }
             if (na == 0) break;
-            solve_packed(na);
+            solve_packed(na, settings_.second_order_correction ? SQPB200_KEEP_FACTOR : 0u);
             if (settings_.second_order_correction) {
                 for (int k = 0; k < na; ++k) {
                     auto &I = inst_[slot_[k]];
                     I.form_soc_bounds(*probs_[slot_[k]]);
                     pack(k, I, false);  // only l and u change (the TODO at src/sqp.cpp:273)
                 }
-                solve_packed(na);
+                solve_packed(na, SQPB200_REUSE_FACTOR);  // same P, A: instances with unchanged constraint classes skip the factorisation
             }
             for (int k = 0; k < na; ++k) {
                 auto &I = inst_[slot_[k]];
@@ -449,8 +449,8 @@ class BatchSQP {
             u_[(size_t)k * nc_ + i] = I.qu(i);
         }
     }
-    void solve_packed(int na) {  // run_solve_qp for every active instance (src/sqp.cpp:210-242)
-        qp_.setup_solve(P_.data(), q_.data(), A_.data(), l_.data(), u_.data(), na);
+    void solve_packed(int na, unsigned opts) {  // run_solve_qp for every active instance (src/sqp.cpp:210-242)
+        qp_.setup_solve(P_.data(), q_.data(), A_.data(), l_.data(), u_.data(), na, opts);
         ++launches_;
         for (int k = 0; k < na; ++k) {
             auto &I = inst_[slot_[k]];

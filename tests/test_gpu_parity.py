@@ -413,3 +413,43 @@ def test_linearity_property_full_size_config2(api, ctx):
     np.testing.assert_allclose(out2["x"], out1["x"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(out2["y"], c * out1["y"], rtol=1e-9, atol=1e-11)
     assert (out1["status"] == api.SOLVED).sum() > 512
+
+
+@pytest.mark.parametrize("kernel", ["generic", "tile"])
+@pytest.mark.parametrize("n,m", [(64, 128), (12, 20)])
+def test_keep_and_reuse_factor_is_bit_identical(api, ctx, oracle, kernel, n, m):
+    """Re-solving the same P, A with new q, l, u (the second-order-correction QP, sqp.cpp:244-276) with
+    KEEP_FACTOR / REUSE_FACTOR gives exactly the plain setup_solve results, whether or not an instance's
+    constraint classes changed (those refactor), and with adaptive rho moving rho in the first solve."""
+    from sqp_solver_b200.synth import make_batch
+
+    B = 24
+    d = make_batch(B, n, m, seed0=13000)
+    s = api.default_settings(alpha=1.6, adaptive_rho=1)
+    select_kernel(api, ctx, kernel, n, m)
+    b = api.QPBatch(ctx, B, n, m)
+    b.settings = s
+    b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"], opts=api.KEEP_FACTOR)
+    first = b.get()
+    plain = run_fused(api, ctx, d, s, kernel)
+    for k in ("x", "y", "iter", "status"):
+        np.testing.assert_array_equal(first[k], plain[k])
+    # second problem: same P, A; shifted bounds and new q; instances 0..5 also change a constraint class
+    rng = np.random.default_rng(1)
+    d2 = dict(d, q=d["q"] + 0.1 * rng.standard_normal(d["q"].shape), l=d["l"].copy(), u=d["u"].copy())
+    shift = 0.05 * rng.standard_normal(d["l"].shape)
+    finite = np.abs(d["l"]) < 1e19
+    d2["l"][finite] += shift[finite]
+    d2["u"][finite] += shift[finite]
+    for i in range(6):
+        row = int(np.argmax((d2["u"][i] - d2["l"][i] > 1e-3) & finite[i]))
+        d2["u"][i, row] = d2["l"][i, row]  # inequality -> equality
+    b.setup_solve(d2["P"], d2["q"], d2["A"], d2["l"], d2["u"], opts=api.REUSE_FACTOR)
+    reused = b.get()
+    plain2 = run_fused(api, ctx, d2, s, kernel)
+    for k in ("x", "y", "z", "iter", "status", "res_prim", "res_dual"):
+        np.testing.assert_array_equal(reused[k], plain2[k], err_msg=k)
+    ref = oracle.solve_batch(d2["P"], d2["q"], d2["A"], d2["l"], d2["u"], oracle_settings_from(oracle, s))
+    reused.pop("rho_updates")
+    assert_parity(reused, ref, what="reuse-factor re-solve")
+    b.close()
