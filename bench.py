@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--settings", default="S1", choices=["S1", "S2"],
                     help="S1 = reference defaults (headline); S2 = alpha 1.6 + adaptive rho (SURVEY.md 8d)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tile"])
-    ap.add_argument("--tile-warps", type=int, default=0, choices=[0, 4, 8])
+    ap.add_argument("--tile-warps", type=int, default=0, choices=[0, 1, 2, 4, 8])
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the driver's contract): every rank solves its own batch. strong: ONE batch on rank 0 "

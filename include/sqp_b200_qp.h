@@ -86,7 +86,7 @@ typedef enum sqpb200_error {
 #define SQPB200_OPT_KERNEL 1       /* 0 = auto (default), 1 = force the generic kernel, 2 = force the register-tiled kernel */
 #define SQPB200_OPT_H2D_CHUNKS 2   /* number of staging chunks for HOST_PTRS calls (default 16) */
 #define SQPB200_OPT_CTAS_PER_SM 3  /* 0 = auto */
-#define SQPB200_OPT_TILE_WARPS 4   /* warps per QP of the 64x128 register-tiled kernel: 0 = default, 4, 8 (tuning/tests) */
+#define SQPB200_OPT_TILE_WARPS 4   /* warps per QP of the register-tiled kernel: 0 = default; 4 (default) or 8 for the 64x128 class, 1 (default) or 2 for the 32x64 class (tuning/tests) */
 
 typedef struct sqpb200_ctx sqpb200_ctx;           /* one per (host thread, GPU) */
 typedef struct sqpb200_qp_batch sqpb200_qp_batch; /* B solver instances: state x,z,y, info, factor */

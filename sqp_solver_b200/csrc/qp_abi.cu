@@ -155,7 +155,8 @@ int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
             c->opt_ctas_per_sm = value;
             return SQPB200_OK;
         case SQPB200_OPT_TILE_WARPS:
-            if (value != 0 && value != 4 && value != 8) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_TILE_WARPS: 0, 4 or 8");
+            if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
+                return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_TILE_WARPS: 0, 1, 2, 4 or 8");
             c->opt_tile_warps = value;
             return SQPB200_OK;
     }

@@ -24,15 +24,15 @@ def ctx(api):
     c.close()
 
 
-KERNELS = ["generic", "tile", "tile8"]  # tile8 = the 8-warps-per-QP variant of the 64x128 configuration
+KERNELS = ["generic", "tile", "tile8"]  # tile8 = the non-default warps-per-QP variants (8 for the 64x128 class, 2 for 32x64)
 
 
 def select_kernel(api, ctx, kernel, n, m):
-    if kernel == "tile8" and not (n > 32 or m > 64):
-        pytest.skip("the 8-warp variant only exists for the 64x128 configuration")
+    if kernel == "tile8" and not (n > 16 or m > 32):
+        pytest.skip("alternative warps-per-QP variants only exist for the 32x64 and 64x128 classes")
     ctx.set_option(api.OPT_KERNEL, {"generic": api.KERNEL_GENERIC, "tile": api.KERNEL_TILE, "tile8": api.KERNEL_TILE,
                                     "auto": api.KERNEL_AUTO}[kernel])
-    ctx.set_option(api.OPT_TILE_WARPS, 8 if kernel == "tile8" else 0)
+    ctx.set_option(api.OPT_TILE_WARPS, (8 if (n > 32 or m > 64) else 2) if kernel == "tile8" else 0)
 
 
 @pytest.fixture(autouse=True)
