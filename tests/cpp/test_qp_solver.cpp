@@ -5,100 +5,96 @@
 
 using namespace qp_solver;
 
+// The fixture of tests/qp_solver_test.cpp:6-41 (P = [[4,1],[1,2]], q = [1,1], A = [[1,1],[1,0],[0,1]],
+// l = [1,0,0], u = [1,0.7,0.7], solution [0.3,0.7]); the problem owns its storage and exposes the
+// reference's non-owning QuadraticProblem view.
 template <typename Scalar>
-class SimpleQP : public QuadraticProblem<Scalar> {  // tests/qp_solver_test.cpp:6-41
-   public:
-    using BASE = QuadraticProblem<Scalar>;
+struct SimpleQP : QuadraticProblem<Scalar> {
     using Matrix = sqpb200_dense::Matrix<Scalar>;
     using Vector = sqpb200_dense::Vector<Scalar>;
-    SimpleQP() : SOLUTION(2) {
-        Matrix *P = new Matrix(2, 2);
-        Vector *q = new Vector(2);
-        Matrix *A = new Matrix(3, 2);
-        Vector *l = new Vector(3);
-        Vector *u = new Vector(3);
-        (*P)(0, 0) = 4; (*P)(0, 1) = 1; (*P)(1, 0) = 1; (*P)(1, 1) = 2;
-        (*q)(0) = 1; (*q)(1) = 1;
-        (*A)(0, 0) = 1; (*A)(0, 1) = 1; (*A)(1, 0) = 1; (*A)(1, 1) = 0; (*A)(2, 0) = 0; (*A)(2, 1) = 1;
-        (*l)(0) = 1; (*l)(1) = 0; (*l)(2) = 0;
-        (*u)(0) = 1; (*u)(1) = 0.7; (*u)(2) = 0.7;
-        BASE::P = P; BASE::q = q; BASE::A = A; BASE::l = l; BASE::u = u;
-        SOLUTION(0) = 0.3; SOLUTION(1) = 0.7;
+    Matrix Pm{2, 2}, Am{3, 2};
+    Vector qv{Scalar(1), Scalar(1)}, lv{Scalar(1), Scalar(0), Scalar(0)}, uv{Scalar(1), Scalar(0.7), Scalar(0.7)};
+    Vector SOLUTION{Scalar(0.3), Scalar(0.7)};
+    SimpleQP() {
+        const Scalar Pvals[2][2] = {{4, 1}, {1, 2}}, Avals[3][2] = {{1, 1}, {1, 0}, {0, 1}};
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) Pm(i, j) = Pvals[i][j];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 2; ++j) Am(i, j) = Avals[i][j];
+        this->P = &Pm;
+        this->q = &qv;
+        this->A = &Am;
+        this->l = &lv;
+        this->u = &uv;
     }
-    ~SimpleQP() { delete BASE::P; delete BASE::q; delete BASE::A; delete BASE::l; delete BASE::u; }
-    Vector SOLUTION;
+    SimpleQP(const SimpleQP &) = delete;
 };
 
-TEST(QPSolverTest, testSimpleQP) {
-    SimpleQP<double> qp;
-    QPSolver<double> solver;
-    solver.settings().max_iter = 1000;
+// setup + solve of the fixture with caller-chosen settings; returns the solver for inspection
+template <typename Scalar, typename Configure>
+static QPSolver<Scalar> solved(const SimpleQP<Scalar> &qp, Configure configure) {
+    QPSolver<Scalar> solver;
+    configure(solver.settings());
     solver.setup(qp);
     solver.solve(qp);
-    auto sol = solver.primal_solution();
-    EXPECT_TRUE(sol.isApprox(qp.SOLUTION, 1e-2));
+    return solver;
+}
+
+TEST(QPSolverTest, testSimpleQP) {  // tests/qp_solver_test.cpp:43-56
+    SimpleQP<double> qp;
+    auto solver = solved<double>(qp, [](QPSolverSettings<double> &s) { s.max_iter = 1000; });
+    EXPECT_TRUE(solver.primal_solution().isApprox(qp.SOLUTION, 1e-2));
     EXPECT_LT(solver.info().iter, solver.settings().max_iter);
     EXPECT_EQ(solver.info().status, SOLVED);
     EXPECT_EQ(solver.info().iter, 125);  // oracle regression value
 }
 
-TEST(QPSolverTest, testSinglePrecisionFloat) {
+TEST(QPSolverTest, testSinglePrecisionFloat) {  // tests/qp_solver_test.cpp:58-69
     SimpleQP<float> qp;
-    QPSolver<float> solver;
-    solver.setup(qp);
-    solver.solve(qp);
-    auto sol = solver.primal_solution();
-    EXPECT_TRUE(sol.isApprox(qp.SOLUTION, 1e-2f));
+    auto solver = solved<float>(qp, [](QPSolverSettings<float> &) {});
+    EXPECT_TRUE(solver.primal_solution().isApprox(qp.SOLUTION, 1e-2f));
     EXPECT_LT(solver.info().iter, solver.settings().max_iter);
     EXPECT_EQ(solver.info().status, SOLVED);
 }
 
-TEST(QPSolverTest, testConstraintViolation) {
+TEST(QPSolverTest, testConstraintViolation) {  // tests/qp_solver_test.cpp:71-87
     SimpleQP<double> qp;
-    QPSolver<double> solver;
-    solver.settings().eps_rel = 1e-4f;
-    solver.settings().eps_abs = 1e-4f;
-    solver.setup(qp);
-    solver.solve(qp);
-    auto sol = solver.primal_solution();
-    double lower = 1e300, upper = -1e300;
+    auto solver = solved<double>(qp, [](QPSolverSettings<double> &s) { s.eps_rel = s.eps_abs = 1e-4f; });
+    const auto &sol = solver.primal_solution();
+    // feasibility with the reference's epsilon margin: l - 1e-3 <= A x <= u + 1e-3
     for (int i = 0; i < 3; ++i) {
-        double Ax = (*qp.A)(i, 0) * sol(0) + (*qp.A)(i, 1) * sol(1);
-        lower = std::min(lower, Ax - (*qp.l)(i));
-        upper = std::max(upper, Ax - (*qp.u)(i));
+        const double Ax = qp.Am(i, 0) * sol(0) + qp.Am(i, 1) * sol(1);
+        EXPECT_GE(Ax - qp.lv(i), -1e-3);
+        EXPECT_LE(Ax - qp.uv(i), 1e-3);
     }
-    EXPECT_GE(lower, -1e-3);
-    EXPECT_LE(upper, 1e-3);
 }
 
-TEST(QPSolverTest, testAdaptiveRho) {
+TEST(QPSolverTest, testAdaptiveRho) {  // tests/qp_solver_test.cpp:89-100
     SimpleQP<double> qp;
-    QPSolver<double> solver;
-    solver.settings().adaptive_rho = true;
-    solver.settings().adaptive_rho_interval = 10;
-    solver.setup(qp);
-    solver.solve(qp);
+    auto solver = solved<double>(qp, [](QPSolverSettings<double> &s) {
+        s.adaptive_rho = true;
+        s.adaptive_rho_interval = 10;
+    });
     EXPECT_EQ(solver.info().status, SOLVED);
-    EXPECT_EQ(solver.info().rho_updates, 2);
+    EXPECT_EQ(solver.info().rho_updates, 2);  // oracle regression value
 }
 
-TEST(QPSolverTest, testAdaptiveRhoImprovesConvergence) {
+TEST(QPSolverTest, testAdaptiveRhoImprovesConvergence) {  // tests/qp_solver_test.cpp:102-125
     SimpleQP<double> qp;
-    QPSolver<double> solver;
-    solver.settings().warm_start = false;
-    solver.settings().max_iter = 1000;
-    solver.settings().rho = 0.1;
-    solver.settings().adaptive_rho = false;
-    solver.setup(qp);
-    solver.solve(qp);
-    int prev_iter = solver.info().iter;
+    auto solver = solved<double>(qp, [](QPSolverSettings<double> &s) {
+        s.warm_start = false;
+        s.max_iter = 1000;
+        s.rho = 0.1;
+        s.adaptive_rho = false;
+    });
+    const int iters_without = solver.info().iter;
+    // second solve on the same solver (a warm start in the reference) with adaptive rho
     solver.settings().adaptive_rho = true;
     solver.settings().adaptive_rho_interval = 10;
     solver.solve(qp);
-    auto info = solver.info();
-    EXPECT_LT(info.iter, solver.settings().max_iter);
-    EXPECT_LT(info.iter, prev_iter);
-    EXPECT_EQ(info.status, SOLVED);
+    EXPECT_LT(solver.info().iter, solver.settings().max_iter);
+    EXPECT_LT(solver.info().iter, iters_without);
+    EXPECT_EQ(solver.info().status, SOLVED);
 }
 
 TEST(QPSolverTest, TestConstraint) {
