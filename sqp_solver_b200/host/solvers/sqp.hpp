@@ -401,16 +401,25 @@ class BatchSQP {
         for (int iter = 1; iter <= settings_.max_iter; ++iter) {
             // compact the still-active instances into the leading slots of the packed QP arrays
             int na = 0;
-            for (size_t i = 0; i < B; ++i) {
-                if (!inst_[i].active) continue;
-                inst_[i].info_.iter = iter;
-                inst_[i].form_qp(*probs_[i]);
-                pack(na, inst_[i], true);
-                slot_[na++] = (int)i;
-            }
+            for (size_t i = 0; i < B; ++i)
+                if (inst_[i].active) slot_[na++] = (int)i;
             if (na == 0) break;
+            // host side of the outer iteration: independent per instance (user callbacks must be re-entrant across
+            // DIFFERENT problem objects when built with OpenMP)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+            for (int k = 0; k < na; ++k) {
+                auto &I = inst_[slot_[k]];
+                I.info_.iter = iter;
+                I.form_qp(*probs_[slot_[k]]);
+                pack(k, I, true);
+            }
             solve_packed(na, settings_.second_order_correction ? SQPB200_KEEP_FACTOR : 0u);
             if (settings_.second_order_correction) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
                 for (int k = 0; k < na; ++k) {
                     auto &I = inst_[slot_[k]];
                     I.form_soc_bounds(*probs_[slot_[k]]);
@@ -418,6 +427,9 @@ class BatchSQP {
                 }
                 solve_packed(na, SQPB200_REUSE_FACTOR);  // same P, A: instances with unchanged constraint classes skip the factorisation
             }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
             for (int k = 0; k < na; ++k) {
                 auto &I = inst_[slot_[k]];
                 if (I.finish_iteration(*probs_[slot_[k]], settings_)) {
