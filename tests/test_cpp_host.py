@@ -176,7 +176,9 @@ def test_batch_sqp_config4_full_size(oracle):
         ref = S.solve(S.CONSTRAINED_ROSENBROCK_2D, inst["x0"], [0, 0], S.default_settings())
         same = (inst["iter"], inst["qp_solver_iter"], inst["status"]) == (ref["iter"], ref["qp_solver_iter"], ref["status"])
         if same:
-            assert np.linalg.norm(np.array(inst["x"]) - ref["x"]) <= 1e-5 * max(np.linalg.norm(ref["x"]), 1e-3)
+            # the outer loop stops on step norms <= 1e-4 (sqp.hpp:17-18); late subproblems carry cond(P) up to 1e14, so
+            # two fp64 runs of the same trajectory agree to the SQP tolerance, not to QP-level 1e-6
+            assert np.linalg.norm(np.array(inst["x"]) - ref["x"]) <= 1e-4 * max(np.linalg.norm(ref["x"]), 1e-3)
         agree += same
     # the reference's l1-merit line search is decided by ~1e-6 noise from feasible-side iterates,
     # so a few trajectories may branch differently from the oracle's; the large majority must coincide
