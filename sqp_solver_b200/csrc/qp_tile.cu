@@ -46,6 +46,9 @@ struct TileCfg {
     static_assert(HR >= 2 && HR % 2 == 0 && HR <= CG && NP % HR == 0 && (NP / HR) * CG == T, "symmetric tile: rows");
     static_assert(R == 1 || R % 2 == 0, "row tile must be vectorisable");
     static_assert(T >= NP, "b stage needs one thread per variable");
+    // A^T diag(rho) A on the fp64 tensor cores (mma.sync m8n8k4): warp w owns IB 8-row blocks of H x all JB 8-column blocks
+    static constexpr bool DMMA = (NP % (8 * NW) == 0);
+    static constexpr int IB = DMMA ? NP / (8 * NW) : 1, JB = NP / 8;
     // shared memory carve-up (doubles)
     // The padded staging copy of A (needed only while H is formed) and the padded copy of P (needed afterwards, for
     // P*x at the checks) share one region: a second 34 KB region would shrink the L1 that backs the few register
@@ -387,40 +390,82 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         // Requires sA staged; ends with sP valid (it replaces the staging copy) and the CTA synchronised.
         double hv[HR][HC];
         auto factorize = [&]() -> bool {
+            // lower triangle of P mirrored (LDLT<Lower> reads nothing else), + sigma on the diagonal;
+            // padded variables get a unit diagonal block
+            auto h_init = [&](int i, int j) -> double {
+                if (i >= n || j >= n) return (i == j) ? 1.0 : 0.0;
+                const double v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
+                return (i == j) ? v + sigma : v;
+            };
+            if constexpr (Cfg::DMMA) {
+                // The one genuine dense contraction of the path, H += A^T diag(rho) A (n x n x m), runs on the fp64 tensor
+                // cores: D(8x8) += A(8x4) B(4x8) with A(i,k) = rho_k A[k][i] and B(k,j) = A[k][j]; both fragments are the same
+                // one-LDS.64-per-lane read of the staged A. Accumulators start at 0; P_lowsym + sigma I is added afterwards.
+                constexpr int IB = Cfg::IB, JB = Cfg::JB;
+                double c0[IB][JB], c1[IB][JB];
 #pragma unroll
-            for (int s = 0; s < HC; ++s) {
-                const int j = cg + CG * s;
+                for (int ib = 0; ib < IB; ++ib)
 #pragma unroll
-                for (int r = 0; r < HR; ++r) {
-                    // lower triangle of P mirrored (LDLT<Lower> reads nothing else), + sigma on the diagonal;
-                    // padded variables get a unit diagonal block
-                    const int i = i0 + r;
-                    double v;
-                    if (i >= n || j >= n) v = (i == j) ? 1.0 : 0.0;
-                    else {
-                        v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
-                        if (i == j) v += sigma;
+                    for (int jb = 0; jb < JB; ++jb) c0[ib][jb] = c1[ib][jb] = 0.0;
+                const int fr = lane >> 2, fk = lane & 3;
+                const int ksteps = (m + 3) / 4;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int k = 4 * ks + fk;
+                    const double rk = srho[k];
+                    double af[IB], bf[JB];
+#pragma unroll
+                    for (int ib = 0; ib < IB; ++ib) af[ib] = sA[k + LS * (8 * (IB * warp + ib) + fr)] * rk;
+#pragma unroll
+                    for (int jb = 0; jb < JB; ++jb) bf[jb] = sA[k + LS * (8 * jb + fr)];
+#pragma unroll
+                    for (int ib = 0; ib < IB; ++ib)
+#pragma unroll
+                        for (int jb = 0; jb < JB; ++jb)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                         : "+d"(c0[ib][jb]), "+d"(c1[ib][jb])
+                                         : "d"(af[ib]), "d"(bf[jb]));
+                }
+                cta_sync<NW>();  // every warp is done with the staged A: the region now carries the accumulators across lanes
+#pragma unroll
+                for (int ib = 0; ib < IB; ++ib)
+#pragma unroll
+                    for (int jb = 0; jb < JB; ++jb) {
+                        const int i = 8 * (IB * warp + ib) + fr, j = 8 * jb + 2 * fk;
+                        sA[i + HS * j] = c0[ib][jb];
+                        sA[i + HS * (j + 1)] = c1[ib][jb];
                     }
-                    hv[r][s] = v;
-                }
-            }
-            const int mloop = (m + 1) / 2;
-            for (int kp = 0; kp < mloop; ++kp) {
-                const double2 rr = *reinterpret_cast<const double2 *>(srho + 2 * kp);
-                double2 ar[HR];
+                cta_sync<NW>();
 #pragma unroll
-                for (int r = 0; r < HR; ++r) {
-                    ar[r] = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (i0 + r));
-                    ar[r].x *= rr.x;
-                    ar[r].y *= rr.y;
-                }
+                for (int s = 0; s < HC; ++s)
 #pragma unroll
-                for (int s = 0; s < HC; ++s) {
-                    const double2 cj = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (cg + CG * s));
+                    for (int r = 0; r < HR; r += 2) {
+                        const double2 h2 = *reinterpret_cast<const double2 *>(sA + i0 + r + HS * (cg + CG * s));
+                        hv[r][s] = h_init(i0 + r, cg + CG * s) + h2.x;
+                        hv[r + 1][s] = h_init(i0 + r + 1, cg + CG * s) + h2.y;
+                    }
+            } else {
 #pragma unroll
+                for (int s = 0; s < HC; ++s)
+#pragma unroll
+                    for (int r = 0; r < HR; ++r) hv[r][s] = h_init(i0 + r, cg + CG * s);
+                const int mloop = (m + 1) / 2;
+                for (int kp = 0; kp < mloop; ++kp) {
+                    const double2 rr = *reinterpret_cast<const double2 *>(srho + 2 * kp);
+                    double2 ar[HR];
+    #pragma unroll
                     for (int r = 0; r < HR; ++r) {
-                        hv[r][s] = fma(ar[r].x, cj.x, hv[r][s]);
-                        hv[r][s] = fma(ar[r].y, cj.y, hv[r][s]);
+                        ar[r] = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (i0 + r));
+                        ar[r].x *= rr.x;
+                        ar[r].y *= rr.y;
+                    }
+    #pragma unroll
+                    for (int s = 0; s < HC; ++s) {
+                        const double2 cj = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (cg + CG * s));
+    #pragma unroll
+                        for (int r = 0; r < HR; ++r) {
+                            hv[r][s] = fma(ar[r].x, cj.x, hv[r][s]);
+                            hv[r][s] = fma(ar[r].y, cj.y, hv[r][s]);
+                        }
                     }
                 }
             }
