@@ -143,6 +143,15 @@ class QPSolver:
     def dual_solution(self):
         return np.ctypeslib.as_array(self._f("oracle_qp_dual")(self._h), shape=(self.m,)).copy()
 
+    def set_iterates(self, x=None, y=None, z=None):
+        """Overwrite the solver's iterates in place. The reference exposes x and y through the non-const
+        `Vector &primal_solution()` / `dual_solution()` accessors (qp.hpp:160,163); z is written here only to
+        mirror sqpb200_qp_batch_set_iterates in the warm-start tests."""
+        for name, val, ln in (("primal", x, self.n), ("dual", y, self.m), ("z", z, self.m)):
+            if val is not None:
+                dst = np.ctypeslib.as_array(self._f("oracle_qp_" + name)(self._h), shape=(ln,))
+                dst[:] = np.asarray(val, dtype=self.dtype)
+
     def z(self):
         return np.ctypeslib.as_array(self._f("oracle_qp_z")(self._h), shape=(self.m,)).copy()
 

@@ -453,3 +453,39 @@ def test_keep_and_reuse_factor_is_bit_identical(api, ctx, oracle, kernel, n, m):
     reused.pop("rho_updates")
     assert_parity(reused, ref, what="reuse-factor re-solve")
     b.close()
+
+
+def test_set_iterates_warm_start_from_checkpoint(api, ctx, oracle):
+    """Checkpointed iterates restored with sqpb200_qp_batch_set_iterates continue exactly like the oracle whose
+    x, y (qp.hpp:160,163 expose them by reference) and z are overwritten with the same values."""
+    from sqp_solver_b200.synth import make_batch
+
+    B, n, m = 12, 24, 40
+    d = make_batch(B, n, m, seed0=14000)
+    args = (d["P"], d["q"], d["A"], d["l"], d["u"])
+    b = api.QPBatch(ctx, B, n, m)
+    b.settings.max_iter = 60
+    b.setup(*args)
+    b.solve(*args)
+    ck = b.get()  # checkpoint after 60 iterations
+    b2 = api.QPBatch(ctx, B, n, m)
+    b2.setup(*args)
+    b2.set_iterates(x=ck["x"], y=ck["y"], z=ck["z"])
+    b2.settings.max_iter = 1000
+    b2.solve(*args)
+    got = b2.get()
+    refs = []
+    for i in range(B):
+        qp = oracle.QuadraticProblem(d["P"][i].reshape(n, n, order="F"), d["q"][i], d["A"][i].reshape(m, n, order="F"), d["l"][i], d["u"][i])
+        s = oracle.QPSolver()
+        s.setup(qp)
+        s.set_iterates(x=ck["x"][i], y=ck["y"][i], z=ck["z"][i])
+        s.solve(qp)
+        refs.append(s)
+    ref = dict(x=np.array([s.primal_solution() for s in refs]), y=np.array([s.dual_solution() for s in refs]),
+               status=np.array([s.info().status for s in refs]), iter=np.array([s.info().iter for s in refs]),
+               rho_updates=np.array([s.info().rho_updates for s in refs]))
+    assert_parity(got, ref, what="warm start from checkpoint")
+    assert (got["iter"] < 1000).any()
+    b.close()
+    b2.close()
