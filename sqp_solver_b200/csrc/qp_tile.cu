@@ -65,7 +65,8 @@ struct TileCfg {
     static constexpr int OFF_W = OFF_PX + NP;
     static constexpr int OFF_RHO = OFF_W + MP;
     static constexpr int OFF_PIV = OFF_RHO + MP;
-    static constexpr int PIVS = NP + 2;  // pivot column + 1/d + d
+    static constexpr int PIVS = 2 * NP;  // two pivot columns per elimination step
+    static_assert(CG % 2 == 0, "the rank-2 elimination pairs adjacent pivot columns");
     static constexpr int OFF_BND = OFF_PIV + 2 * PIVS;  // (l, u) pairs per row: read once per iteration by the row owner
     static constexpr int OFF_RED = OFF_BND + 2 * MP;
     static constexpr int SMEM_DOUBLES = OFF_RED + 8 * NW;
@@ -185,24 +186,29 @@ struct Tile {
     // v for the lane's R rows is read from sw (written by the row owners just before)
     static __device__ __forceinline__ void mv_At(const double (&a)[R][C], const double *sw, double *part_w, int row0,
                                                  int lc, int lane) {
-        double wv[R];
-        if constexpr (R >= 2) {
-#pragma unroll
-            for (int kr = 0; kr < R; kr += 2) {
-                const double2 t2 = *reinterpret_cast<const double2 *>(sw + row0 + kr);
-                wv[kr] = t2.x;
-                wv[kr + 1] = t2.y;
-            }
-        } else {
-            wv[0] = sw[row0];
-        }
+        // w is consumed in chunks of at most 4 rows so that only 4 of its values are live next to the C accumulators
+        // and the R*C tile: the hot loop of the 64x128 configuration sits at the 255-register limit
         double acc[C];
 #pragma unroll
-        for (int kk = 0; kk < C; ++kk) {
-            double s = 0.0;
+        for (int kk = 0; kk < C; ++kk) acc[kk] = 0.0;
+        constexpr int WCH = (R >= 4) ? 4 : R;
 #pragma unroll
-            for (int kr = 0; kr < R; ++kr) s = fma(a[kr][kk], wv[kr], s);
-            acc[kk] = s;
+        for (int h = 0; h < R; h += WCH) {
+            double wv[WCH];
+            if constexpr (WCH >= 2) {
+#pragma unroll
+                for (int kr = 0; kr < WCH; kr += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2 *>(sw + row0 + h + kr);
+                    wv[kr] = t2.x;
+                    wv[kr + 1] = t2.y;
+                }
+            } else {
+                wv[0] = sw[row0 + h];
+            }
+#pragma unroll
+            for (int kk = 0; kk < C; ++kk)
+#pragma unroll
+                for (int kr = 0; kr < WCH; ++kr) acc[kk] = fma(a[h + kr][kk], wv[kr], acc[kk]);
         }
         Halve<C, 16, LC>::run(acc, lane);
         bool primary;
@@ -265,7 +271,10 @@ struct Tile {
     }
 };
 
-template <class Cfg>
+// SWEEP2 selects the elimination variant of the (re)factorisation: two pivots per barrier step (fewer, heavier steps: the
+// better choice when adaptive rho refactors often) or one pivot per step (leaves the compiler the leaner hot loop: the better
+// choice when the launch is iteration-dominated). Measured on config 3: S1 24.6 vs 25.1 ms, S2 5.58 vs 5.32 ms.
+template <class Cfg, bool SWEEP2>
 __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams p) {
     using TL = Tile<Cfg>;
     constexpr int NP = Cfg::NP, MP = Cfg::MP, NW = Cfg::NW, LC = Cfg::LC, T = Cfg::T;
@@ -471,60 +480,125 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             }
             if (tid == 0) s_fail = 0;
             cta_sync<NW>();  // everyone is done with sA; the staging region may be overwritten from here on
-            // symmetric elimination, pivot by pivot: after all NP steps hv holds -(H^-1)
             bool ok = true;
-#pragma unroll
-            for (int s = 0; s < HC; ++s) {
-#pragma unroll 1
-                for (int cgk = 0; cgk < CG; ++cgk) {
-                    const int k = cgk + CG * s;
-                    double *pv = piv + (k & 1) * Cfg::PIVS;
-                    const int krow = k - i0;  // row of this lane's tile that is the pivot row (if 0 <= krow < HR)
-                    if (cg == cgk) {
-#pragma unroll
-                        for (int r = 0; r < HR; r += 2) *reinterpret_cast<double2 *>(pv + i0 + r) = make_double2(hv[r][s], hv[r + 1][s]);
-                        if ((unsigned)krow < (unsigned)HR) {  // the one lane that owns the pivot publishes d and 1/d
-                            double d = hv[0][s];
-#pragma unroll
-                            for (int r = 1; r < HR; ++r) d = (r == krow) ? hv[r][s] : d;
-                            pv[NP] = 1.0 / d;
-                            pv[NP + 1] = d;
+            if constexpr (SWEEP2) {
+                // Symmetric elimination, TWO pivots per step (NP/2 steps, one barrier each): with K = {k, k+1},
+                // E = S[K][K], S <- S - S[:,K] E^-1 S[K,:],  S[:,K] <- S[:,K] E^-1,  S[K,:] <- E^-1 S[K,:],  S[K][K] <- -E^-1.
+                // After all steps hv holds -(H^-1). The pivots of the unpivoted LDL^T are d_k = E00 and d_k+1 = det(E)/E00: a zero
+                // or NaN in either reports NUMERICAL_ISSUES (Eigen::LDLT::info() != Success). Every lane inverts the 2x2 block
+                // itself after the barrier, so no lane waits on a pivot owner's reciprocal.
+    #pragma unroll
+                for (int s = 0; s < HC; ++s) {
+    #pragma unroll 1
+                    for (int cgk = 0; cgk < CG; cgk += 2) {
+                        const int k = cgk + CG * s;
+                        double *pvA = piv + ((k >> 1) & 1) * Cfg::PIVS, *pvB = pvA + NP;
+                        if (cg == cgk || cg == cgk + 1) {
+                            double *dst = (cg == cgk) ? pvA : pvB;
+    #pragma unroll
+                            for (int r = 0; r < HR; r += 2) *reinterpret_cast<double2 *>(dst + i0 + r) = make_double2(hv[r][s], hv[r + 1][s]);
                         }
-                    }
-                    cta_sync<NW>();
-                    const double2 dd = *reinterpret_cast<const double2 *>(pv + NP);
-                    const double inv_d = dd.x;
-                    if (!(fabs(dd.y) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
-                        ok = false;
-                        break;
-                    }
-                    double t[HR];
-#pragma unroll
-                    for (int r = 0; r < HR; r += 2) {
-                        const double2 ci = *reinterpret_cast<const double2 *>(pv + i0 + r);
-                        t[r] = ci.x * inv_d;
-                        t[r + 1] = ci.y * inv_d;
-                    }
-#pragma unroll
-                    for (int s2 = 0; s2 < HC; ++s2) {
-                        const double cj = pv[cg + CG * s2];
-#pragma unroll
-                        for (int r = 0; r < HR; ++r) hv[r][s2] = fma(-t[r], cj, hv[r][s2]);
-                    }
-                    if ((unsigned)krow < (unsigned)HR) {  // the row group holding pivot row k: that row becomes c_j / d
-#pragma unroll
+                        cta_sync<NW>();
+                        const double2 ab = *reinterpret_cast<const double2 *>(pvA + k);  // E00, E10
+                        const double e_c = pvB[k + 1];                                     // E11
+                        const double det = fma(ab.x, e_c, -ab.y * ab.y);
+                        if (!(fabs(ab.x) > 0.0) || !(fabs(det) > 0.0)) {
+                            ok = false;
+                            break;
+                        }
+                        const double inv_det = 1.0 / det;
+                        const double e00 = e_c * inv_det, e01 = -ab.y * inv_det, e11 = ab.x * inv_det;  // E^-1
+                        double wA[HR], wB[HR];  // rows of S[:,K] E^-1
+    #pragma unroll
+                        for (int r = 0; r < HR; r += 2) {
+                            const double2 ca = *reinterpret_cast<const double2 *>(pvA + i0 + r);
+                            const double2 cb = *reinterpret_cast<const double2 *>(pvB + i0 + r);
+                            wA[r] = fma(ca.x, e00, cb.x * e01);
+                            wB[r] = fma(ca.x, e01, cb.x * e11);
+                            wA[r + 1] = fma(ca.y, e00, cb.y * e01);
+                            wB[r + 1] = fma(ca.y, e01, cb.y * e11);
+                        }
+                        const int krow = k - i0;  // pivot rows k, k+1 are rows krow, krow+1 of this lane's tile if 0 <= krow < HR
+    #pragma unroll
                         for (int s2 = 0; s2 < HC; ++s2) {
-                            const double rowv = pv[cg + CG * s2] * inv_d;
-#pragma unroll
-                            for (int r = 0; r < HR; ++r) hv[r][s2] = (r == krow) ? rowv : hv[r][s2];
+                            const double cja = pvA[cg + CG * s2], cjb = pvB[cg + CG * s2];
+    #pragma unroll
+                            for (int r = 0; r < HR; ++r) hv[r][s2] = fma(-wB[r], cjb, fma(-wA[r], cja, hv[r][s2]));
+                        }
+                        if ((unsigned)krow < (unsigned)HR) {  // the row group that holds the two pivot rows
+    #pragma unroll
+                            for (int s2 = 0; s2 < HC; ++s2) {
+                                const double cja = pvA[cg + CG * s2], cjb = pvB[cg + CG * s2];
+                                const double ra = fma(e00, cja, e01 * cjb), rb = fma(e01, cja, e11 * cjb);
+    #pragma unroll
+                                for (int r = 0; r < HR; ++r) hv[r][s2] = (r == krow) ? ra : ((r == krow + 1) ? rb : hv[r][s2]);
+                            }
+                        }
+                        if (cg == cgk) {
+    #pragma unroll
+                            for (int r = 0; r < HR; ++r) hv[r][s] = (r == krow) ? -e00 : ((r == krow + 1) ? -e01 : wA[r]);
+                        } else if (cg == cgk + 1) {
+    #pragma unroll
+                            for (int r = 0; r < HR; ++r) hv[r][s] = (r == krow) ? -e01 : ((r == krow + 1) ? -e11 : wB[r]);
                         }
                     }
-                    if (cg == cgk) {
-#pragma unroll
-                        for (int r = 0; r < HR; ++r) hv[r][s] = (r == krow) ? -inv_d : t[r];
-                    }
+                    if (!ok) break;
                 }
-                if (!ok) break;
+            } else {
+                // symmetric elimination, pivot by pivot: after all NP steps hv holds -(H^-1)
+    #pragma unroll
+                for (int s = 0; s < HC; ++s) {
+    #pragma unroll 1
+                    for (int cgk = 0; cgk < CG; ++cgk) {
+                        const int k = cgk + CG * s;
+                        double *pv = piv + (k & 1) * (NP + 2);
+                        const int krow = k - i0;  // row of this lane's tile that is the pivot row (if 0 <= krow < HR)
+                        if (cg == cgk) {
+    #pragma unroll
+                            for (int r = 0; r < HR; r += 2) *reinterpret_cast<double2 *>(pv + i0 + r) = make_double2(hv[r][s], hv[r + 1][s]);
+                            if ((unsigned)krow < (unsigned)HR) {  // the one lane that owns the pivot publishes d and 1/d
+                                double d = hv[0][s];
+    #pragma unroll
+                                for (int r = 1; r < HR; ++r) d = (r == krow) ? hv[r][s] : d;
+                                pv[NP] = 1.0 / d;
+                                pv[NP + 1] = d;
+                            }
+                        }
+                        cta_sync<NW>();
+                        const double2 dd = *reinterpret_cast<const double2 *>(pv + NP);
+                        const double inv_d = dd.x;
+                        if (!(fabs(dd.y) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
+                            ok = false;
+                            break;
+                        }
+                        double t[HR];
+    #pragma unroll
+                        for (int r = 0; r < HR; r += 2) {
+                            const double2 ci = *reinterpret_cast<const double2 *>(pv + i0 + r);
+                            t[r] = ci.x * inv_d;
+                            t[r + 1] = ci.y * inv_d;
+                        }
+    #pragma unroll
+                        for (int s2 = 0; s2 < HC; ++s2) {
+                            const double cj = pv[cg + CG * s2];
+    #pragma unroll
+                            for (int r = 0; r < HR; ++r) hv[r][s2] = fma(-t[r], cj, hv[r][s2]);
+                        }
+                        if ((unsigned)krow < (unsigned)HR) {  // the row group holding pivot row k: that row becomes c_j / d
+    #pragma unroll
+                            for (int s2 = 0; s2 < HC; ++s2) {
+                                const double rowv = pv[cg + CG * s2] * inv_d;
+    #pragma unroll
+                                for (int r = 0; r < HR; ++r) hv[r][s2] = (r == krow) ? rowv : hv[r][s2];
+                            }
+                        }
+                        if (cg == cgk) {
+    #pragma unroll
+                            for (int r = 0; r < HR; ++r) hv[r][s] = (r == krow) ? -inv_d : t[r];
+                        }
+                    }
+                    if (!ok) break;
+                }
             }
 #pragma unroll
             for (int s = 0; s < HC; ++s)
@@ -826,17 +900,18 @@ bool tile_supported(int n, int m) { return n >= 1 && m >= 0 && n <= 64 && m <= 1
 
 template <class Cfg>
 static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
-    cudaError_t e = cudaFuncSetAttribute(qp_tile_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    auto kernel = p.s.adaptive_rho ? qp_tile_kernel<Cfg, true> : qp_tile_kernel<Cfg, false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qp_tile_kernel<Cfg>, Cfg::T, Cfg::SMEM_BYTES);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, Cfg::T, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
     long long grid = (long long)sm_count * occ;  // persistent: a multiple of the SM count
     if (grid > p.count) grid = p.count;
-    if (name) snprintf(name, name_len, "tile<%d,%d,%d>x%d", Cfg::NP, Cfg::MP, Cfg::NW, occ);
-    qp_tile_kernel<Cfg><<<(int)grid, Cfg::T, Cfg::SMEM_BYTES, stream>>>(p);
+    if (name) snprintf(name, name_len, "tile<%d,%d,%d>x%d", Cfg::NP, Cfg::MP, Cfg::NW, occ);  // (the sweep variant is not part of the name)
+    kernel<<<(int)grid, Cfg::T, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 
