@@ -149,6 +149,17 @@ int sqpb200_qp_batch_setup_solve_opts(sqpb200_qp_batch *b, const sqpb200_qp_sett
                                       const double *q, const double *A, const double *l, const double *u, unsigned flags,
                                       void *stream, unsigned opts);
 
+/* setup + solve with a SPARSE constraint matrix: one sparsity pattern shared by the batch, per-instance values
+ * A_values[B][nnz]. layout SQPB200_SPARSE_CSC is Eigen::SparseMatrix's compressed column storage (the reference's intended
+ * sparse variant, qp.hpp:22-25; A_outer has n+1 entries, A_inner holds row indices); SQPB200_SPARSE_CSR has m+1 outer
+ * entries and column indices. P stays dense. Round 1 densifies on the device and runs the dense kernels (results are
+ * identical to the dense entry points); a sparsity-exploiting kernel is next-round work. */
+#define SQPB200_SPARSE_CSC 0
+#define SQPB200_SPARSE_CSR 1
+int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                                        const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
+                                        int layout, const double *l, const double *u, unsigned flags, void *stream);
+
 /* Read back solutions and info (any pointer may be NULL). primal_solution()/dual_solution()/info(),
  * qp.hpp:159-169; z is exposed in addition so a caller can checkpoint a warm start. */
 int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,

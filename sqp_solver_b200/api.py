@@ -24,6 +24,7 @@ HOST_PTRS, DEVICE_PTRS = 0, 1
 OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS = 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE = 0, 1, 2
 KEEP_FACTOR, REUSE_FACTOR = 1, 2
+SPARSE_CSC, SPARSE_CSR = 0, 1
 
 # every symbol include/sqp_b200_qp.h declares (checked by tests/test_abi_symbols.py)
 ABI_SYMBOLS = [
@@ -31,7 +32,7 @@ ABI_SYMBOLS = [
     "sqpb200_device_query", "sqpb200_launch_count", "sqpb200_last_kernel", "sqpb200_qp_default_settings",
     "sqpb200_constr_type_init", "sqpb200_qp_batch_create", "sqpb200_qp_batch_destroy", "sqpb200_qp_batch_setup",
     "sqpb200_qp_batch_update_qp", "sqpb200_qp_batch_solve", "sqpb200_qp_batch_setup_solve",
-    "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_get",
+    "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
     "sqpb200_qp_solve_batch",
 ]
@@ -87,6 +88,8 @@ def load_library(path=None):
     for name in ("setup", "update_qp", "solve", "setup_solve"):
         getattr(L, "sqpb200_qp_batch_" + name).argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_setup_solve_opts.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp, C.c_uint]
+    L.sqpb200_qp_batch_setup_solve_sparse.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, ip, ip, C.c_int, C.c_int, dp, dp,
+                                                      C.c_uint, vp]
     L.sqpb200_qp_batch_get.argtypes = [vp, C.c_int, dp, dp, dp, ip, ip, ip, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_set_iterates.argtypes = [vp, C.c_int, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_device_view.argtypes = [vp, C.POINTER(DeviceView)]
@@ -246,6 +249,30 @@ class QPBatch:
             self._call("setup_solve_opts", P, q, A, l, u, count, stream, opts=opts)
         else:
             self._call("setup_solve", P, q, A, l, u, count, stream)
+
+    def setup_solve_sparse(self, P, q, A_values, A_outer, A_inner, l, u, layout=SPARSE_CSC, count=None, stream=None):
+        """setup + solve with A given as CSC (Eigen::SparseMatrix layout) or CSR: one pattern for the whole batch
+        (A_outer, A_inner: int32), per-instance values A_values[B, nnz]."""
+        count = self.batch if count is None else int(count)
+        ptrs, spaces = [], set()
+        for nm, a, dt in (("P", P, np.float64), ("q", q, np.float64), ("A_values", A_values, np.float64), ("A_outer", A_outer, np.int32),
+                          ("A_inner", A_inner, np.int32), ("l", l, np.float64), ("u", u, np.float64)):
+            p_, sp = _ptr_and_space(a, dt, nm)
+            ptrs.append(p_)
+            spaces.add(sp)
+        spaces.discard(None)
+        if len(spaces) != 1:
+            raise SolverError("all arrays must be host arrays or all CUDA tensors")
+        flags = spaces.pop()
+        nnz = int(A_inner.shape[0])
+        if flags == DEVICE_PTRS and stream is None:
+            import torch
+
+            stream = torch.cuda.current_stream().cuda_stream
+        P_, q_, Av, Ao, Ai, l_, u_ = ptrs
+        self.ctx._check(self._L.sqpb200_qp_batch_setup_solve_sparse(self._h, C.byref(self.settings), count, P_, q_, Av, Ao, Ai, nnz,
+                                                                    int(layout), l_, u_, flags, C.c_void_p(stream or 0)),
+                        "setup_solve_sparse")
 
     def get(self, count=None, fields=("x", "y", "z", "status", "iter", "rho_updates", "rho_estimate", "res_prim", "res_dual")):
         """Copy results to fresh host arrays (synchronises)."""

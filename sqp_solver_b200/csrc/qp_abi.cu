@@ -46,6 +46,10 @@ struct sqpb200_qp_batch {
     unsigned long long *total_iters = nullptr;
     // staging for HOST_PTRS calls (lazily allocated)
     double *dP = nullptr, *dq = nullptr, *dA = nullptr, *dl = nullptr, *du = nullptr;
+    // sparse-A entry point: device copies of the shared pattern and of the per-instance values
+    int *sp_outer = nullptr, *sp_inner = nullptr;
+    double *sp_vals = nullptr;
+    int sp_nnz_cap = 0;
 };
 
 static int fail(sqpb200_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -184,7 +188,7 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
-                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du};
+                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -442,6 +446,67 @@ int sqpb200_qp_batch_setup_solve_opts(sqpb200_qp_batch *b, const sqpb200_qp_sett
     b->fact_valid = false;
     b->fused_used = true;
     return run(b, s, mode, count, P, q, A, l, u, flags, stream);
+}
+
+int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P,
+                                        const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
+                                        int layout, const double *l, const double *u, unsigned flags, void *stream_) {
+    if (!b) return SQPB200_ERR_INVALID;
+    sqpb200_ctx *c = b->ctx;
+    if (!s) return fail(c, SQPB200_ERR_INVALID, "settings is NULL");
+    if (count < 0 || count > b->batch) return fail(c, SQPB200_ERR_INVALID, "count outside [0, batch]");
+    if (layout != SQPB200_SPARSE_CSC && layout != SQPB200_SPARSE_CSR) return fail(c, SQPB200_ERR_INVALID, "layout must be SQPB200_SPARSE_CSC or SQPB200_SPARSE_CSR");
+    if (nnz < 0 || (nnz > 0 && (!A_values || !A_inner)) || !A_outer || !P || !q || ((!l || !u) && b->m > 0))
+        return fail(c, SQPB200_ERR_INVALID, "NULL problem array");
+    if (count == 0) return SQPB200_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t n = b->n, m = b->m, B = count;
+    const int n_outer = layout == SQPB200_SPARSE_CSR ? b->m : b->n;
+    int rc = ensure_staging(b);
+    if (rc) return rc;
+    const bool dev = (flags & SQPB200_DEVICE_PTRS) != 0;
+    const int *d_outer = A_outer, *d_inner = A_inner;
+    const double *d_vals = A_values, *dP = P, *dq = q, *dl = l, *du = u;
+    if (!dev) {
+        if (nnz > b->sp_nnz_cap || !b->sp_outer) {
+            CK(c, cudaStreamSynchronize(stream));
+            if (b->sp_outer) cudaFree(b->sp_outer);
+            if (b->sp_inner) cudaFree(b->sp_inner);
+            if (b->sp_vals) cudaFree(b->sp_vals);
+            b->sp_outer = b->sp_inner = nullptr;
+            b->sp_vals = nullptr;
+            const size_t cap = nnz > 0 ? nnz : 1;
+            cudaError_t e = cudaMalloc(&b->sp_outer, sizeof(int) * ((b->m > b->n ? b->m : b->n) + 1));
+            if (e == cudaSuccess) e = cudaMalloc(&b->sp_inner, sizeof(int) * cap);
+            if (e == cudaSuccess) e = cudaMalloc(&b->sp_vals, sizeof(double) * cap * b->batch);
+            if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "sparse staging cudaMalloc", e);
+            b->sp_nnz_cap = (int)cap;
+        }
+        CK(c, cudaMemcpyAsync(b->sp_outer, A_outer, sizeof(int) * (n_outer + 1), cudaMemcpyHostToDevice, stream));
+        if (nnz > 0) {
+            CK(c, cudaMemcpyAsync(b->sp_inner, A_inner, sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
+            CK(c, cudaMemcpyAsync(b->sp_vals, A_values, sizeof(double) * B * nnz, cudaMemcpyHostToDevice, stream));
+        }
+        CK(c, cudaMemcpyAsync(b->dP, P, sizeof(double) * B * n * n, cudaMemcpyHostToDevice, stream));
+        CK(c, cudaMemcpyAsync(b->dq, q, sizeof(double) * B * n, cudaMemcpyHostToDevice, stream));
+        if (m > 0) {
+            CK(c, cudaMemcpyAsync(b->dl, l, sizeof(double) * B * m, cudaMemcpyHostToDevice, stream));
+            CK(c, cudaMemcpyAsync(b->du, u, sizeof(double) * B * m, cudaMemcpyHostToDevice, stream));
+        }
+        d_outer = b->sp_outer; d_inner = b->sp_inner; d_vals = b->sp_vals;
+        dP = b->dP; dq = b->dq; dl = b->dl; du = b->du;
+    }
+    cudaError_t e = launch_densify(d_vals, d_outer, d_inner, nnz, b->m, b->n, layout == SQPB200_SPARSE_CSR, count, b->dA, stream);
+    if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "densify launch", e);
+    c->launches += nnz > 0 ? 1 : 0;
+    CK(c, cudaMemsetAsync(b->total_iters, 0, sizeof(unsigned long long), stream));
+    b->fact_valid = false;
+    b->fused_used = true;
+    rc = launch_range(b, s, MODE_RESET | MODE_FACTOR | MODE_SOLVE, 0, count, dP, dq, b->dA, dl, du, stream);
+    if (rc) return rc;
+    if (!dev) CK(c, cudaStreamSynchronize(stream));
+    return SQPB200_OK;
 }
 
 int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,

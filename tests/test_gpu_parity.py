@@ -489,3 +489,77 @@ def test_set_iterates_warm_start_from_checkpoint(api, ctx, oracle):
     assert (got["iter"] < 1000).any()
     b.close()
     b2.close()
+
+
+def _sparse_batch(batch, n, m, density, seed0, layout):
+    """Synthetic QPs whose A shares one sparsity pattern (density of nonzeros); returns the dense dict and the
+    compressed arrays in the requested layout ('csc' like Eigen::SparseMatrix, or 'csr')."""
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(batch, n, m, seed0=seed0)
+    rng = np.random.default_rng(seed0 + 12345)
+    mask = rng.uniform(size=(m, n)) < density
+    mask[np.arange(m), rng.integers(0, n, m)] = True  # no empty rows
+    A3 = d["A"].reshape(batch, n, m).transpose(0, 2, 1) * mask  # [B, m, n]
+    # keep the problems feasible: rebuild the bounds around c = A x0 with the same widths
+    x0 = rng.standard_normal((batch, n))
+    c = np.einsum("bij,bj->bi", A3, x0)
+    width_l, width_u = rng.uniform(0, 1, (batch, m)), rng.uniform(0, 1, (batch, m))
+    l, u = c - width_l, c + width_u
+    eq = rng.uniform(size=(batch, m)) < 0.1
+    l[eq] = c[eq]
+    u[eq] = c[eq]
+    d["l"], d["u"] = np.ascontiguousarray(l), np.ascontiguousarray(u)
+    d["A"] = np.ascontiguousarray(A3.transpose(0, 2, 1).reshape(batch, n * m))  # column-major per instance
+    if layout == "csc":
+        cols, rows = np.nonzero(mask.T)  # column-major order of the stored entries
+        outer = np.concatenate([[0], np.cumsum(mask.sum(axis=0))]).astype(np.int32)
+        inner = rows.astype(np.int32)
+        vals = np.ascontiguousarray(A3[:, rows, cols])
+    else:
+        rows, cols = np.nonzero(mask)
+        outer = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int32)
+        inner = cols.astype(np.int32)
+        vals = np.ascontiguousarray(A3[:, rows, cols])
+    return d, vals, outer, np.ascontiguousarray(inner)
+
+
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+@pytest.mark.parametrize("n,m,batch,density", [(40, 60, 12, 0.15), (256, 512, 3, 0.03)])
+def test_sparse_A_entry_point(api, ctx, oracle, layout, n, m, batch, density):
+    """SURVEY.md 8f row 3 / BASELINE config 5 shape: A in compressed column (Eigen) or compressed row storage with a
+    shared pattern. Parity against the oracle on the densified problem, and bit-identity with the dense entry point."""
+    d, vals, outer, inner = _sparse_batch(batch, n, m, density, 15000, layout)
+    s = api.default_settings(alpha=1.6, adaptive_rho=1, max_iter=400)
+    b = api.QPBatch(ctx, batch, n, m)
+    b.settings = s
+    b.setup_solve_sparse(d["P"], d["q"], vals, outer, inner, d["l"], d["u"],
+                         layout=api.SPARSE_CSC if layout == "csc" else api.SPARSE_CSR)
+    got = b.get()
+    dense = run_fused(api, ctx, d, s, "auto")
+    for k in ("x", "y", "iter", "status"):
+        np.testing.assert_array_equal(got[k], dense[k], err_msg=k)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    assert_parity(got, ref, what="sparse %s n=%d m=%d" % (layout, n, m))
+    b.close()
+
+
+def test_sparse_simple_qp_reference_fixture(api, ctx, golden):
+    """The reference's (dead) tests/qp_solver_sparse_test.cpp:36-49 and :85-98: SimpleQP with sparse A, adaptive rho ->
+    [0.3, 0.7]; then P = I, q = 0 -> [0.5, 0.5]. A = [[1,1],[1,0],[0,1]] in CSC has 4 stored entries."""
+    g = golden["simple_qp"]
+    A = np.array(g["A"], dtype=float)
+    cols, rows = np.nonzero(A.T)
+    outer = np.concatenate([[0], np.cumsum((A != 0).sum(axis=0))]).astype(np.int32)
+    vals = np.ascontiguousarray(A[rows, cols][None, :])
+    P = np.array(g["P"], dtype=float).reshape(1, 4)
+    q, l, u = (np.array(g[k], dtype=float).reshape(1, -1) for k in ("q", "l", "u"))
+    b = api.QPBatch(ctx, 1, 2, 3)
+    b.settings = api.default_settings(max_iter=1000, adaptive_rho=1)
+    b.setup_solve_sparse(P, q, vals, outer, rows.astype(np.int32), l, u)
+    out = b.get()
+    assert out["status"][0] == api.SOLVED and is_approx(out["x"][0], g["solution"], 1e-2)
+    b.setup_solve_sparse(np.eye(2).reshape(1, 4), np.zeros((1, 2)), vals, outer, rows.astype(np.int32), l, u)
+    out = b.get()
+    assert out["status"][0] == api.SOLVED and is_approx(out["x"][0], [0.5, 0.5], 1e-2)
+    b.close()
