@@ -120,27 +120,43 @@ class ClockSampler:
 
 
 def cpu_baseline(d, settings_name, sample, steps=1):
-    """The reference algorithm (oracle restatement -- Eigen is absent, so kind='port') on this box's
-    host cores, OpenMP dynamic schedule over a bounded sample of the same workload."""
+    """The reference algorithm (oracle restatement -- Eigen is absent, so kind='port') on this box's host cores:
+    headline = gcc -O2, OpenMP dynamic schedule over a bounded sample of the same workload on all cores; BASELINE.md
+    section 4's other rows (one core; -O3 -march=native built on this box) ride along in `extra`."""
     from oracle import qp_oracle as O
 
     O.build()
     cores = O.num_procs()
     if sample <= 0:
         sample = min(d["batch"], 64 * cores)
-    sl = slice(0, sample)
     st = O.default_settings(**settings_kwargs(settings_name))
-    best, its = None, 0
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        out = O.solve_batch(d["P"][sl], d["q"][sl], d["A"][sl], d["l"][sl], d["u"][sl], st, nthreads=cores)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+
+    def timed(count, nthreads, native=False):
+        sl = slice(0, count)
+        best, out = None, None
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            out = O.solve_batch(d["P"][sl], d["q"][sl], d["A"][sl], d["l"][sl], d["u"][sl], st, nthreads=nthreads, native=native)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
         its = int(np.minimum(out["iter"], st.max_iter).sum())
-    return {"value": sample / best, "unit": UNIT, "cores": cores, "kind": "port",
+        return count / best, its / best, best, out["threads"]
+
+    qps, itps, sec, threads = timed(sample, cores)
+    extra = {}
+    try:
+        one = max(4, min(sample, 24))
+        q1, i1, s1, _ = timed(one, 1)
+        extra["one_core_O2"] = {"value": q1, "admm_iters_per_s": i1, "sample": "%d QPs, %.2f s" % (one, s1)}
+        O.lib(native=True)  # compiles on this box (outside the timed region)
+        qn, inn, sn, _ = timed(sample, cores, native=True)
+        extra["all_cores_O3_march_native"] = {"value": qn, "admm_iters_per_s": inn, "sample": "%d QPs, %.2f s" % (sample, sn)}
+    except Exception as e:  # the extra rows are informative only
+        extra["error"] = repr(e)
+    return {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "first %d QPs of the same batch, %s, gcc -O2 oracle restatement of src/qp.cpp (Eigen absent), "
-                      "OpenMP schedule(dynamic) over %d threads, %.2f s" % (sample, settings_name, out["threads"], best),
-            "admm_iters_per_s": its / best, "seconds": best}
+                      "OpenMP schedule(dynamic) over %d threads, %.2f s" % (sample, settings_name, threads, sec),
+            "admm_iters_per_s": itps, "seconds": sec, "extra": extra}
 
 
 def run_reference(args, rank, world):

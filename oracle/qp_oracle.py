@@ -17,10 +17,22 @@ SOLVED, MAX_ITER_EXCEEDED, UNSOLVED, NUMERICAL_ISSUES, UNINITIALIZED = range(5) 
 INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = range(3)  # qp.hpp:134
 
 
+def _native_path():
+    import tempfile
+
+    return os.path.join(tempfile.gettempdir(), "sqpb200_liboracle_native_%d.so" % os.getuid())
+
+
 def build(native=False):
-    """Compile the oracle with the committed recipe (oracle/Makefile). Idempotent."""
-    subprocess.check_call(["make", "-s", "-C", _HERE] + (["native"] if native else []))
-    return os.path.join(_HERE, "_build", "liboracle_native.so") if native else _LIB
+    """Compile the oracle with the committed recipe (oracle/Makefile). Idempotent.
+    native=True builds the -O3 -march=native variant on THIS machine into the temp dir (never into the tree: a
+    -march=native binary must not travel to a box with a different CPU)."""
+    if native:
+        out = _native_path()
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "native", "NATIVE_OUT=" + out])
+        return out
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _LIB
 
 
 def _mk_structs(ct):
@@ -46,8 +58,8 @@ _libs = {}
 def lib(native=False):
     key = bool(native)
     if key not in _libs:
-        path = os.path.join(_HERE, "_build", "liboracle_native.so") if native else _LIB
-        if not os.path.exists(path):
+        path = _native_path() if native else _LIB
+        if native or not os.path.exists(path):
             build(native)
         L = C.CDLL(path)
         for suf, ct, S, I in (("_f64", C.c_double, SettingsF64, InfoF64), ("_f32", C.c_float, SettingsF32, InfoF32)):
