@@ -84,7 +84,7 @@ def lib(native=False):
             fb = getattr(L, "oracle_qp_solve_batch" + suf)
             fb.restype = C.c_int
             IP = C.POINTER(C.c_int)
-            fb.argtypes = [C.POINTER(S), C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, P, IP, IP, P, P, IP, P, C.c_int]
+            fb.argtypes = [C.POINTER(S), C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, P, IP, IP, P, P, IP, P, C.c_int, C.POINTER(C.c_double)]
         L.oracle_num_procs.restype = C.c_int
         _libs[key] = L
     return _libs[key]
@@ -223,13 +223,14 @@ def solve_batch(P, q, A, l, u, settings=None, nthreads=0, native=False):
     s = settings if settings is not None else default_settings()
     out = dict(x=np.zeros((B, n)), y=np.zeros((B, m)), z=np.zeros((B, m)),
                status=np.zeros(B, np.int32), iter=np.zeros(B, np.int32), res_prim=np.zeros(B), res_dual=np.zeros(B),
-               rho_updates=np.zeros(B, np.int32), rho_estimate=np.zeros(B))
+               rho_updates=np.zeros(B, np.int32), rho_estimate=np.zeros(B), diag_min_norms=np.zeros((B, 2)))
     d, ip = C.c_double, C.POINTER(C.c_int)
     used = lib(native).oracle_qp_solve_batch_f64(
         C.byref(s), B, n, m, _ptr(P, d), _ptr(q, d), _ptr(A, d), _ptr(l, d), _ptr(u, d),
         _ptr(out["x"], d), _ptr(out["y"], d), _ptr(out["z"], d),
         out["status"].ctypes.data_as(ip), out["iter"].ctypes.data_as(ip), _ptr(out["res_prim"], d),
-        _ptr(out["res_dual"], d), out["rho_updates"].ctypes.data_as(ip), _ptr(out["rho_estimate"], d), int(nthreads))
+        _ptr(out["res_dual"], d), out["rho_updates"].ctypes.data_as(ip), _ptr(out["rho_estimate"], d), int(nthreads),
+        _ptr(out["diag_min_norms"], d))
     out["threads"] = used
     return out
 

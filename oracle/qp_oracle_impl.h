@@ -78,6 +78,9 @@ typedef struct {
     int ldlt_ok;
     /* scratch for mat-vecs */
     SCALAR *tmp_n, *tmp_n2, *tmp_m;
+    /* test diagnostics (not in the reference): smallest normalised residuals ever fed to rho_estimate. When one of them is
+     * at rounding level the adaptive-rho decision is decided by rounding noise and is not reproducible across implementations. */
+    double diag_min_rp_norm, diag_min_rd_norm;
 } FN(oracle_solver);
 
 /* include/solvers/qp.hpp:136-141 */
@@ -363,6 +366,7 @@ void FN(oracle_qp_setup)(FN(oracle_solver) * s, int n, int m, const SCALAR *P, c
         s->tmp_n2 = (SCALAR *)malloc(sizeof(SCALAR) * (n + 1));
         s->tmp_m = (SCALAR *)malloc(sizeof(SCALAR) * (m + 1));
     }
+    s->diag_min_rp_norm = s->diag_min_rd_norm = 1e300;
     for (int i = 0; i < n; ++i) s->x[i] = 0; /* qp.cpp:16-18, the only real cold start */
     for (int i = 0; i < m; ++i) { s->z[i] = 0; s->y[i] = 0; }
 
@@ -420,6 +424,8 @@ static void FN(orc_update_state)(FN(oracle_solver) * s, const SCALAR *P, const S
 static SCALAR FN(orc_rho_estimate)(FN(oracle_solver) * s, SCALAR rho0) {
     SCALAR rp_norm = s->info.res_prim / (s->max_Ax_z_norm + ORC_EPS);
     SCALAR rd_norm = s->info.res_dual / (s->max_Px_ATy_q_norm + ORC_EPS);
+    if ((double)rp_norm < s->diag_min_rp_norm) s->diag_min_rp_norm = (double)rp_norm;
+    if ((double)rd_norm < s->diag_min_rd_norm) s->diag_min_rd_norm = (double)rd_norm;
     return rho0 * ORC_SQRT(rp_norm / (rd_norm + ORC_EPS));
 }
 
@@ -508,7 +514,7 @@ void FN(oracle_qp_ldlt_dump)(FN(oracle_solver) * s, SCALAR *D, int *transp) {
 int FN(oracle_qp_solve_batch)(const FN(oracle_settings) * settings, int batch, int n, int m,
                               const SCALAR *P, const SCALAR *q, const SCALAR *A, const SCALAR *l, const SCALAR *u,
                               SCALAR *x, SCALAR *y, SCALAR *z, int *status, int *iter, SCALAR *res_prim,
-                              SCALAR *res_dual, int *rho_updates, SCALAR *rho_estimate, int nthreads) {
+                              SCALAR *res_dual, int *rho_updates, SCALAR *rho_estimate, int nthreads, double *diag_min_norms) {
     int used = 1;
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
@@ -538,6 +544,7 @@ int FN(oracle_qp_solve_batch)(const FN(oracle_settings) * settings, int batch, i
             if (res_dual) res_dual[b] = s->info.res_dual;
             if (rho_updates) rho_updates[b] = s->info.rho_updates;
             if (rho_estimate) rho_estimate[b] = s->info.rho_estimate;
+            if (diag_min_norms) { diag_min_norms[2 * b] = s->diag_min_rp_norm; diag_min_norms[2 * b + 1] = s->diag_min_rd_norm; }
         }
         FN(oracle_qp_free)(s);
     }
