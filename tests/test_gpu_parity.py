@@ -602,3 +602,21 @@ def test_randomised_shapes_and_settings(api, ctx, oracle, kernel):
         floor = np.where(ref["status"][stable] == api.MAX_ITER_EXCEEDED, 1e-2, 0.0)
         assert_parity(sub(out), sub(ref), what="fuzz case %d n=%d m=%d %s %s" % (case, n, m, out["kernel"], kw), x_norm_floor=floor)
     assert n_stable >= 0.9 * n_total, "only %d of %d fuzz instances are numerically stable in the oracle" % (n_stable, n_total)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_against_committed_golden_outputs(api, ctx, kernel):
+    """The CUDA path against the COMMITTED oracle outputs of tests/golden/oracle_synthetic.json (no oracle run involved)."""
+    import json
+    import os
+
+    from sqp_solver_b200.synth import make_batch
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_synthetic.json")) as f:
+        gold = json.load(f)
+    for c in gold["cases"]:
+        d = make_batch(c["batch"], c["n"], c["m"], seed0=c["seed0"])
+        out = run_fused(api, ctx, d, api.default_settings(**c["settings"]), kernel)
+        ref = dict(status=np.array(c["status"]), iter=np.array(c["iter"]), rho_updates=np.array(c["rho_updates"]),
+                   x=np.array(c["x"]), y=np.array(c["y"]))
+        assert_parity(out, ref, what="golden " + c["name"])

@@ -221,3 +221,22 @@ def test_batch_helper_matches_object_api(oracle):
         assert s.info().iter == out["iter"][i] and s.info().status == out["status"][i]
         np.testing.assert_array_equal(s.primal_solution(), out["x"][i])
         np.testing.assert_array_equal(s.dual_solution(), out["y"][i])
+
+
+def test_oracle_reproduces_committed_golden_outputs(oracle):
+    """tests/golden/oracle_synthetic.json (made by tests/golden/make_oracle_golden.py): the oracle built on THIS machine
+    reproduces the committed outputs -- same status / iteration counts, x and y to 1e-9."""
+    import json
+    import os
+
+    from sqp_solver_b200.synth import make_batch
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_synthetic.json")) as f:
+        gold = json.load(f)
+    for c in gold["cases"]:
+        d = make_batch(c["batch"], c["n"], c["m"], seed0=c["seed0"])
+        r = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle.default_settings(**c["settings"]), nthreads=2)
+        assert r["status"].tolist() == c["status"] and r["iter"].tolist() == c["iter"], c["name"]
+        assert r["rho_updates"].tolist() == c["rho_updates"], c["name"]
+        np.testing.assert_allclose(r["x"], np.array(c["x"]), rtol=0, atol=1e-9, err_msg=c["name"])
+        np.testing.assert_allclose(r["y"], np.array(c["y"]), rtol=0, atol=1e-8, err_msg=c["name"])
