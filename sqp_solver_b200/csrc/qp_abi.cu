@@ -40,6 +40,7 @@ struct sqpb200_qp_batch {
     double *rho_estimate = nullptr, *res_prim = nullptr, *res_dual = nullptr, *rho = nullptr;
     signed char *ctype = nullptr;
     double *fact = nullptr;  // lazily allocated
+    size_t fact_doubles = 0;  // per instance
     double *fact_rho = nullptr;
     bool fused_used = false;
     bool fact_valid = false;  // a setup()/update_qp()/solve() launch has stored H^-1, rho and classes
@@ -147,7 +148,7 @@ int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
     if (!c) return SQPB200_ERR_INVALID;
     switch (option) {
         case SQPB200_OPT_KERNEL:
-            if (value < 0 || value > 2) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_KERNEL: value must be 0, 1 or 2");
+            if (value < 0 || value > 3) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_KERNEL: value must be 0, 1, 2 or 3");
             c->opt_kernel = value;
             return SQPB200_OK;
         case SQPB200_OPT_H2D_CHUNKS:
@@ -283,9 +284,16 @@ static int ensure_scratch(sqpb200_ctx *c, size_t bytes) {
     return SQPB200_OK;
 }
 
-static int ensure_fact(sqpb200_qp_batch *b) {
-    if (b->fact) return SQPB200_OK;
-    cudaError_t e = cudaMalloc(&b->fact, sizeof(double) * (size_t)b->batch * b->n * b->n);
+static int ensure_fact(sqpb200_qp_batch *b, size_t doubles_per_qp) {
+    if (b->fact && b->fact_doubles >= doubles_per_qp) return SQPB200_OK;
+    if (b->fact) {
+        cudaDeviceSynchronize();
+        cudaFree(b->fact);
+        b->fact = nullptr;
+        b->fact_valid = false;
+    }
+    b->fact_doubles = doubles_per_qp;
+    cudaError_t e = cudaMalloc(&b->fact, sizeof(double) * (size_t)b->batch * doubles_per_qp);
     if (e != cudaSuccess) return fail(b->ctx, SQPB200_ERR_NOMEM, "factor slab cudaMalloc", e);
     return SQPB200_OK;
 }
@@ -326,25 +334,30 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     p.work_counter = c->counters + slot;
     CK(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
 
-    const bool want_tile = c->opt_kernel != 1 && tile_supported(b->n, b->m);
+    // kernel choice: register-tiled (n <= 64, m <= 128) > blocked (n <= 256, m <= 1024) > generic (anything that fits)
+    const size_t optin = c->prop.sharedMemPerBlockOptin;
+    const bool want_tile = c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
+    const bool want_block = !want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin);
     if (c->opt_kernel == 2 && !want_tile) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
+    if (c->opt_kernel == 3 && !want_block) return fail(c, SQPB200_ERR_UNSUPPORTED, "blocked kernel forced but (n, m) is outside its range");
     const bool needs_fact = !want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE));
     if (needs_fact) {
-        int rc = ensure_fact(b);
+        int rc = ensure_fact(b, want_block ? block_fact_doubles(b->n) : (size_t)b->n * b->n);
         if (rc) return rc;
     }
     p.fact = b->fact;
     cudaError_t e;
     if (want_tile) {
         e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, c->opt_tile_warps, stream, c->last_kernel, sizeof c->last_kernel);
+    } else if (want_block) {
+        e = launch_block(p, c->prop.multiProcessorCount, optin, stream, c->last_kernel, sizeof c->last_kernel);
     } else {
-        if (!generic_supported(b->n, b->m, c->prop.sharedMemPerBlockOptin))
-            return fail(c, SQPB200_ERR_UNSUPPORTED, "(n, m) too large for the generic kernel");
+        if (!generic_supported(b->n, b->m, optin)) return fail(c, SQPB200_ERR_UNSUPPORTED, "(n, m) too large for the generic kernel");
         int grid = generic_grid(count, c->prop.multiProcessorCount);
         int rc = ensure_scratch(c, generic_scratch_bytes(b->n, grid));
         if (rc) return rc;
         p.scratch = c->scratch;
-        e = launch_generic(p, c->prop.multiProcessorCount, c->prop.sharedMemPerBlockOptin, stream, nullptr);
+        e = launch_generic(p, c->prop.multiProcessorCount, optin, stream, nullptr);
         snprintf(c->last_kernel, sizeof c->last_kernel, "generic");
     }
     if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "kernel launch", e);

@@ -1,0 +1,454 @@
+// Blocked batched ADMM QP kernel for the medium shapes the register-tiled kernel cannot hold:
+// 64 < n <= 256 (or m > 128), m <= 1024 -- BASELINE.json config 5's shape (n = 256, m = 512).
+//
+// One 256-thread CTA per QP, persistent CTAs on the atomic work queue. H = P_lowsym + sigma I + A^T diag(rho) A
+// (n x n; see qp_common.cuh for why this is the reference's KKT solve) no longer fits on chip, so:
+//   * H is formed on the fp64 tensor cores (DMMA m8n8k4, fragments straight from global/L2) into a per-QP global slab;
+//   * it is factored IN PLACE by a right-looking BLOCKED L D L^T (panels of 32 columns staged in shared memory;
+//     a zero/NaN pivot reports NUMERICAL_ISSUES like Eigen::LDLT::info()); every 32x32 diagonal block's unit factor
+//     is inverted once (W_k = L_kk^-1);
+//   * the per-iteration solve is a blocked substitution: 8 forward and 8 backward block steps for n = 256, each
+//     one small triangular mat-vec with W_k plus one coalesced panel mat-vec streamed from L2 -- no explicit inverse
+//     (the generic kernel's explicit n x n inverse cost ~20 ms per factorisation at n = 256);
+//   * A may be dense (read through L2) or sparse with a batch-shared pattern: CSR and CSC copies of one instance's
+//     values live in shared memory and both A-products become register-free gathers.
+// Reference functions covered: the same list as qp_generic.cu (all of src/qp.cpp:11-371).
+#include <cstdio>
+
+#include "qp_common.cuh"
+
+namespace sqpb200 {
+
+constexpr int BT = 256;  // threads per CTA
+constexpr int BNW = BT / 32;
+constexpr int NB = 32;  // panel width
+constexpr int WBLK = NB * NB + NB;  // doubles per diagonal block record: W (32x32, column-major) + 1/d (32)
+
+__host__ __device__ inline int block_np(int n) { return (n + NB - 1) / NB * NB; }
+__host__ __device__ inline size_t block_fact_doubles_hd(int n) {
+    const size_t np = block_np(n);
+    return np * np + (np / NB) * WBLK;
+}
+size_t block_fact_doubles(int n) { return block_fact_doubles_hd(n); }
+
+struct BlockSmem {
+    double *x, *xt, *b, *q, *t;                    // np each
+    double *z, *y, *w, *l, *u, *rho, *rhoinv;      // m each
+    double *panel;                                 // np x 32 (factorisation only)
+    double *wsm;                                   // 32 x 32 + 32
+    signed char *type;                             // m
+};
+__device__ __forceinline__ BlockSmem carve_block(double *base, int np, int m) {
+    BlockSmem s;
+    s.x = base; s.xt = s.x + np; s.b = s.xt + np; s.q = s.b + np; s.t = s.q + np;
+    s.z = s.t + np; s.y = s.z + m; s.w = s.y + m; s.l = s.w + m; s.u = s.l + m; s.rho = s.u + m; s.rhoinv = s.rho + m;
+    s.panel = s.rhoinv + m + (m & 1);
+    s.wsm = s.panel + (size_t)np * NB;
+    s.type = reinterpret_cast<signed char *>(s.wsm + WBLK);
+    return s;
+}
+static size_t block_smem_bytes(int n, int m) {
+    const size_t np = block_np(n);
+    return sizeof(double) * (5 * np + 7 * (size_t)m + 1 + np * NB + WBLK) + (size_t)m + 16;
+}
+bool block_supported(int n, int m, size_t smem_optin) { return n >= 1 && n <= 256 && m >= 0 && m <= 1024 && block_smem_bytes(n, m) <= smem_optin; }
+
+// ---- H = P_lowsym + sigma I + A^T diag(rho) A, lower triangle, into Hw (np x np, column-major) --------------------
+__device__ void form_H(const double *__restrict__ P, const double *__restrict__ A, const BlockSmem &s, int n, int np, int m,
+                       double sigma, double *Hw) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int nt = np / 8;                 // 8x8 tiles per side
+    const int ntiles = nt * (nt + 1) / 2;  // lower tiles ib >= jb
+    const int ksteps = (m + 3) / 4;
+    // each warp takes a row block ib and sweeps its jb <= ib tiles four at a time, so one A-fragment feeds four DMMAs
+    for (int ib = warp; ib < nt; ib += BNW) {
+        const int ci = 8 * ib + fr;
+        for (int jb0 = 0; jb0 <= ib; jb0 += 4) {
+            double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int k = 4 * ks + fk;
+                const bool kv = k < m;
+                const double af = (kv && ci < n) ? A[k + (size_t)m * ci] * s.rho[k] : 0.0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int cj = 8 * (jb0 + t) + fr;
+                    const double bf = (kv && jb0 + t <= ib && cj < n) ? A[k + (size_t)m * cj] : 0.0;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c0[t]), "+d"(c1[t])
+                                 : "d"(af), "d"(bf));
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (jb0 + t > ib) continue;
+                const int i = 8 * ib + fr;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * (jb0 + t) + 2 * fk + e;
+                    if (i < j) continue;
+                    double v = e ? c1[t] : c0[t];
+                    if (i < n && j < n) v += P[i + (size_t)n * j] + (i == j ? sigma : 0.0);  // LDLT<Lower>: lower triangle of P only
+                    else v = (i == j) ? 1.0 : 0.0;                                               // padded variables: unit block
+                    Hw[i + (size_t)np * j] = v;
+                }
+            }
+        }
+    }
+    (void)ntiles;
+}
+
+// ---- blocked L D L^T in place + inverted diagonal blocks. Returns false (uniformly) on a zero/NaN pivot ---------
+__device__ bool factor_block(const BlockSmem &s, int np, double *Hw, double *Wd, int *s_fail) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = np / NB;
+    double *panel = s.panel, *Wsm = s.wsm, *dinv = s.wsm + NB * NB;
+    if (tid == 0) *s_fail = 0;
+    __syncthreads();
+    for (int kb = 0; kb < nb; ++kb) {
+        const int r0 = kb * NB, rows = np - r0;
+        // a. stage the panel: rows r0.. of columns r0..r0+31 (lower part of the trailing matrix)
+        for (int e = tid; e < rows * NB; e += BT) {
+            const int r = e % rows, c = e / rows;
+            panel[r + np * c] = (r >= c) ? Hw[(r0 + r) + (size_t)np * (r0 + c)] : 0.0;
+        }
+        __syncthreads();
+        // b. 32x32 diagonal block: unblocked L D L^T by warp 0, lane i owns row i
+        if (warp == 0) {
+            bool bad = false;
+            for (int j = 0; j < NB; ++j) {
+                const double dj = panel[j + np * j];
+                if (!(fabs(dj) > 0.0)) {
+                    bad = true;  // same value in every lane: uniform
+                    break;
+                }
+                double lij = 0.0;
+                if (lane > j) {
+                    lij = panel[lane + np * j] / dj;
+                    panel[lane + np * j] = lij;
+                }
+                __syncwarp();
+                if (lane > j) {
+                    const double t = lij * dj;
+                    for (int k = j + 1; k <= lane; ++k) panel[lane + np * k] -= t * panel[k + np * j];
+                }
+                __syncwarp();
+            }
+            if (bad) {
+                if (lane == 0) *s_fail = 1;
+            } else {
+                // c. W = L11^-1 (unit lower), lane c computes column c by forward substitution; 1/d
+                double wcol[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) wcol[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    double v = (i == lane) ? 1.0 : 0.0;
+                    if (i > lane) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NB; ++k)
+                            if (k < i) acc += panel[i + np * k] * wcol[k];
+                        v = -acc;
+                    }
+                    wcol[i] = v;
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) Wsm[i + NB * lane] = wcol[i];
+                dinv[lane] = 1.0 / panel[lane + np * lane];
+            }
+        }
+        __syncthreads();
+        if (*s_fail) return false;
+        // record W and 1/d for the substitutions; write the factored diagonal block back
+        double *wrec = Wd + (size_t)kb * WBLK;
+        for (int e = tid; e < WBLK; e += BT) wrec[e] = Wsm[e];
+        // d. L21 = A21 L11^-T D^-1 = (A21 W^T) .* dinv, one thread per row below the block
+        for (int r = NB + tid; r < rows; r += BT) {
+            double a[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) a[c] = panel[r + np * c];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    if (k <= c) acc += a[k] * Wsm[c + NB * k];
+                const double lrc = acc * dinv[c];
+                panel[r + np * c] = lrc;
+                Hw[(r0 + r) + (size_t)np * (r0 + c)] = lrc;
+            }
+        }
+        __syncthreads();
+        // f. trailing update  H22[i][j] -= sum_c L[i][c] d_c L[j][c]  (i >= j), one warp per column j, lanes over i
+        for (int j = NB + warp; j < rows; j += BNW) {
+            double tj[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) tj[c] = panel[j + np * c] / dinv[c];
+            for (int i = j + lane; i < rows; i += 32) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) acc += panel[i + np * c] * tj[c];
+                Hw[(r0 + i) + (size_t)np * (r0 + j)] -= acc;
+            }
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
+// ---- xt = H^-1 b by blocked substitution; b (in s.b) is destroyed ---------------------------------------------------
+__device__ void solve_block(const BlockSmem &s, int np, const double *__restrict__ Hw, const double *__restrict__ Wd) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = np / NB;
+    // forward: t = D^-1 L^-1 b
+    for (int kb = 0; kb < nb; ++kb) {
+        const int r0 = kb * NB;
+        const double *W = Wd + (size_t)kb * WBLK;
+        if (tid < NB) {
+            double acc = 0.0;
+            for (int c = 0; c <= tid; ++c) acc += W[tid + NB * c] * s.b[r0 + c];
+            s.t[r0 + tid] = acc;
+        }
+        __syncthreads();
+        for (int r = r0 + NB + tid; r < np; r += BT) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < NB; ++c) acc += Hw[r + (size_t)np * (r0 + c)] * s.t[r0 + c];
+            s.b[r] -= acc;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < np; i += BT) s.t[i] *= Wd[(size_t)(i / NB) * WBLK + NB * NB + (i % NB)];
+    __syncthreads();
+    // backward: xt = L^-T t
+    for (int kb = nb - 1; kb >= 0; --kb) {
+        const int r0 = kb * NB;
+        const double *W = Wd + (size_t)kb * WBLK;
+        for (int c = warp; c < NB; c += BNW) {
+            const double *col = Hw + (size_t)np * (r0 + c);
+            double acc = 0.0;
+            for (int r = r0 + NB + lane; r < np; r += 32) acc += col[r] * s.xt[r];
+            acc = warp_sum(acc);
+            if (lane == 0) s.b[r0 + c] = s.t[r0 + c] - acc;  // b is free: reuse as the block right-hand side
+        }
+        __syncthreads();
+        if (tid < NB) {
+            double acc = 0.0;
+            for (int c = tid; c < NB; ++c) acc += W[c + NB * tid] * s.b[r0 + c];
+            s.xt[r0 + tid] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
+    extern __shared__ __align__(16) double smem_raw[];
+    __shared__ int s_qp, s_fail;
+    __shared__ double s_red[7][BNW];
+    const int n = p.n, m = p.m, np = block_np(p.n);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    BlockSmem s = carve_block(smem_raw, np, m);
+    const sqpb200_qp_settings st = p.s;
+    const size_t fstride = block_fact_doubles_hd(n);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_qp = draw_qp(p);
+        __syncthreads();
+        const int local = s_qp;
+        if (local >= p.count) break;
+        const size_t b = (size_t)p.first + local;
+        const double *P = p.P + b * n * n, *A = p.A + b * m * n;
+        const double *q = p.q + b * n, *l = p.l + b * m, *u = p.u + b * m;
+        double *Hw = p.fact + b * fstride, *Wd = Hw + (size_t)np * np;
+
+        int status = p.status[b];
+        int rho_updates = p.rho_updates[b];
+        double rho_est = p.rho_estimate[b], res_prim = p.res_prim[b], res_dual = p.res_dual[b];
+        double rho = p.rho[b];
+        int iter_out = p.iter[b];
+        bool same_classes = true;
+
+        for (int i = tid; i < np; i += BT) {
+            s.q[i] = i < n ? q[i] : 0.0;
+            s.x[i] = (i < n && !(p.mode & MODE_RESET)) ? p.x[b * n + i] : 0.0;
+            s.xt[i] = 0.0;
+        }
+        for (int i = tid; i < m; i += BT) {
+            s.l[i] = l[i];
+            s.u[i] = u[i];
+            s.z[i] = (p.mode & MODE_RESET) ? 0.0 : p.z[b * m + i];
+            s.y[i] = (p.mode & MODE_RESET) ? 0.0 : p.y[b * m + i];
+        }
+        if (p.mode & MODE_FACTOR) {
+            rho = st.rho;
+            rho_updates += 1;  // rho_vec_update, qp.cpp:313
+            for (int i = tid; i < m; i += BT) {
+                const int t = classify(l[i], u[i]);
+                s.type[i] = (signed char)t;
+                if ((p.mode & MODE_REUSE) && p.ctype[b * m + i] != (signed char)t) same_classes = false;
+                p.ctype[b * m + i] = (signed char)t;
+            }
+        } else {
+            for (int i = tid; i < m; i += BT) s.type[i] = p.ctype[b * m + i];
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += BT) {
+            const double r = rho_of(s.type[i], rho);
+            s.rho[i] = r;
+            s.rhoinv[i] = 1.0 / r;
+        }
+        __syncthreads();
+        if (p.mode & MODE_FACTOR) {
+            const bool reuse = (p.mode & MODE_REUSE) && __syncthreads_and(same_classes && p.fact_rho[b] == st.rho);
+            if (reuse) {
+                status = SQPB200_UNSOLVED;
+            } else {
+                form_H(P, A, s, n, np, m, st.sigma, Hw);
+                __syncthreads();
+                const bool ok = factor_block(s, np, Hw, Wd, &s_fail);
+                status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+                if (tid == 0) p.fact_rho[b] = ok ? rho : nan("");
+            }
+        }
+
+        long long executed = 0;
+        if ((p.mode & MODE_SOLVE) && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES) {
+            const double alpha = st.alpha, sigma = st.sigma;
+            int iter;
+            for (iter = 1; iter <= st.max_iter; ++iter) {
+                for (int i = tid; i < m; i += BT) s.w[i] = s.rho[i] * s.z[i] - s.y[i];
+                __syncthreads();
+                // b = sigma x - q + A^T w   (padded entries stay 0)
+                for (int j = warp; j < np; j += BNW) {
+                    double acc = 0.0;
+                    if (j < n) {
+                        const double *cj = A + (size_t)j * m;
+                        for (int i = lane; i < m; i += 32) acc += cj[i] * s.w[i];
+                        acc = warp_sum(acc);
+                    }
+                    if (lane == 0) s.b[j] = (j < n) ? sigma * s.x[j] - s.q[j] + acc : 0.0;
+                }
+                __syncthreads();
+                solve_block(s, np, Hw, Wd);  // x~ in s.xt (qp.cpp:90)
+                for (int i = tid; i < n; i += BT) s.x[i] = alpha * s.xt[i] + (1.0 - alpha) * s.x[i];
+                // z~ = A x~ ; z, y updates (qp.cpp:93-103)
+                for (int i = tid; i < m; i += BT) {
+                    double acc = 0.0;
+                    for (int j = 0; j < n; ++j) acc += A[i + (size_t)m * j] * s.xt[j];
+                    const double zh = alpha * acc + (1.0 - alpha) * s.z[i];
+                    const double zn = box_project(zh + s.rhoinv[i] * s.y[i], s.l[i], s.u[i]);
+                    s.y[i] = s.y[i] + s.rho[i] * (zh - zn);
+                    s.z[i] = zn;
+                }
+                __syncthreads();
+
+                const bool chk = st.check_termination != 0 && iter % st.check_termination == 0;
+                const bool adapt = st.adaptive_rho && st.adaptive_rho_interval > 0 && iter % st.adaptive_rho_interval == 0;
+                if (chk || adapt) {
+                    double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
+                    for (int i = tid; i < m; i += BT) {
+                        double ax = 0.0;
+                        for (int j = 0; j < n; ++j) ax += A[i + (size_t)m * j] * s.x[j];
+                        mx[0] = absmax(mx[0], ax);
+                        mx[1] = absmax(mx[1], s.z[i]);
+                        mx[5] = absmax(mx[5], ax - s.z[i]);
+                    }
+                    for (int j = warp; j < n; j += BNW) {
+                        const double *cj = A + (size_t)j * m;
+                        double aty = 0.0, px = 0.0;
+                        for (int i = lane; i < m; i += 32) aty += cj[i] * s.y[i];
+                        for (int k = lane; k < n; k += 32) px += P[j + (size_t)n * k] * s.x[k];
+                        aty = warp_sum(aty);
+                        px = warp_sum(px);
+                        mx[2] = absmax(mx[2], px);
+                        mx[3] = absmax(mx[3], aty);
+                        mx[4] = absmax(mx[4], s.q[j]);
+                        mx[6] = absmax(mx[6], px + s.q[j] + aty);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const double v = warp_max(mx[k]);
+                        if (lane == 0) s_red[k][warp] = v;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        double v = s_red[k][0];
+                        for (int w2 = 1; w2 < BNW; ++w2) v = s_red[k][w2] > v ? s_red[k][w2] : v;
+                        mx[k] = v;
+                    }
+                    __syncthreads();
+                    const double sc_p = fmax(mx[0], mx[1]);
+                    const double sc_d = fmax(mx[2], fmax(mx[3], mx[4]));
+                    res_prim = mx[5];
+                    res_dual = mx[6];
+                    if (chk && res_prim <= st.eps_abs + st.eps_rel * sc_p && res_dual <= st.eps_abs + st.eps_rel * sc_d) {
+                        status = SQPB200_SOLVED;  // termination_criteria, qp.cpp:363-371
+                        break;
+                    }
+                    if (adapt) {  // qp.cpp:125-144
+                        const double new_rho = rho_estimate_clamped(rho, res_prim, res_dual, sc_p, sc_d);
+                        rho_est = new_rho;
+                        if (new_rho < rho / st.adaptive_rho_tolerance || new_rho > rho * st.adaptive_rho_tolerance) {
+                            rho = new_rho;
+                            rho_updates += 1;
+                            for (int i = tid; i < m; i += BT) {
+                                const double r = rho_of(s.type[i], rho);
+                                s.rho[i] = r;
+                                s.rhoinv[i] = 1.0 / r;
+                            }
+                            __syncthreads();
+                            form_H(P, A, s, n, np, m, sigma, Hw);
+                            __syncthreads();
+                            const bool ok2 = factor_block(s, np, Hw, Wd, &s_fail);
+                            if (tid == 0) p.fact_rho[b] = ok2 ? rho : nan("");
+                            if (!ok2) {
+                                status = SQPB200_NUMERICAL_ISSUES;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+            executed = iter <= st.max_iter ? iter : st.max_iter;
+            if (iter > st.max_iter) status = SQPB200_MAX_ITER_EXCEEDED;  // qp.cpp:147-149
+            iter_out = iter;                                            // qp.cpp:150
+        }
+
+        for (int i = tid; i < n; i += BT) p.x[b * n + i] = s.x[i];
+        for (int i = tid; i < m; i += BT) {
+            p.z[b * m + i] = s.z[i];
+            p.y[b * m + i] = s.y[i];
+        }
+        if (tid == 0) {
+            p.status[b] = status;
+            p.iter[b] = iter_out;
+            p.rho_updates[b] = rho_updates;
+            p.rho_estimate[b] = rho_est;
+            p.res_prim[b] = res_prim;
+            p.res_dual[b] = res_dual;
+            p.rho[b] = rho;
+            if (executed) atomicAdd(p.total_iters, (unsigned long long)executed);
+        }
+    }
+}
+
+cudaError_t launch_block(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, char *name, size_t name_len) {
+    const size_t smem = block_smem_bytes(p.n, p.m);
+    if (smem > smem_optin) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(qp_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qp_block_kernel, BT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    long long grid = (long long)sm_count * occ;
+    if (grid > p.count) grid = p.count;
+    if (name) snprintf(name, name_len, "block<%d>x%d", NB, occ);
+    qp_block_kernel<<<(int)grid, BT, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace sqpb200

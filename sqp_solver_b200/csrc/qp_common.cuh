@@ -119,6 +119,10 @@ cudaError_t launch_generic(const KernelParams &p, int sm_count, size_t smem_opti
 size_t generic_scratch_bytes(int n, int grid);
 int generic_grid(int count, int sm_count);
 bool generic_supported(int n, int m, size_t smem_optin);
+// blocked kernel for 64 < n <= 256 (qp_block.cu)
+bool block_supported(int n, int m, size_t smem_optin);
+size_t block_fact_doubles(int n);
+cudaError_t launch_block(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, char *name, size_t name_len);
 cudaError_t launch_densify(const double *vals, const int *outer, const int *inner, int nnz, int m, int n, int csr, int count,
                            double *dst, cudaStream_t stream);
 

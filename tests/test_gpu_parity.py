@@ -31,7 +31,7 @@ def select_kernel(api, ctx, kernel, n, m):
     if kernel == "tile8" and not (n > 16 or m > 32):
         pytest.skip("alternative warps-per-QP variants only exist for the 32x64 and 64x128 classes")
     ctx.set_option(api.OPT_KERNEL, {"generic": api.KERNEL_GENERIC, "tile": api.KERNEL_TILE, "tile8": api.KERNEL_TILE,
-                                    "auto": api.KERNEL_AUTO}[kernel])
+                                    "auto": api.KERNEL_AUTO, "block": api.KERNEL_BLOCK}[kernel])
     ctx.set_option(api.OPT_TILE_WARPS, (8 if (n > 32 or m > 64) else 2) if kernel == "tile8" else 0)
 
 
@@ -332,17 +332,44 @@ def test_full_size_properties_config3(api, ctx, oracle):
     assert_parity(sub, ref, what="config 3 sample")
 
 
-def test_generic_kernel_beyond_tile_range(api, ctx, oracle):
-    """Shapes outside the register-tiled kernel (n > 64 or m > 128) dispatch to the generic kernel automatically."""
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
+def test_kernels_beyond_tile_range(api, ctx, oracle, kernel):
+    """Shapes outside the register-tiled kernel (n > 64 or m > 128) dispatch to the blocked kernel (n <= 256, m <= 1024)
+    and beyond that to the generic one; both are also checked when forced."""
     from sqp_solver_b200.synth import make_batch
 
-    for n, m, batch in ((80, 150, 6), (100, 40, 4), (20, 300, 4)):
+    for n, m, batch in ((80, 150, 6), (100, 40, 4), (20, 300, 4), (129, 257, 3), (256, 512, 3), (300, 100, 2)):
         d = make_batch(batch, n, m, seed0=9000)
-        s = api.default_settings(max_iter=300)
-        out = run_fused(api, ctx, d, s, "auto")
-        assert out["kernel"] == "generic"
-        ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
-        assert_parity(out, ref, what="generic n=%d m=%d" % (n, m))
+        for s in (api.default_settings(max_iter=300), api.default_settings(max_iter=200, alpha=1.6, adaptive_rho=1)):
+            out = run_fused(api, ctx, d, s, kernel)
+            expect = "generic" if (kernel == "generic" or n > 256 or m > 1024) else "block"
+            assert out["kernel"].startswith(expect), out["kernel"]
+            ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+            assert_parity(out, ref, what="%s n=%d m=%d" % (out["kernel"], n, m))
+
+
+def test_blocked_kernel_object_api_and_numerical_issues(api, ctx, oracle):
+    """setup / solve / update_qp as separate launches and a NaN instance through the blocked kernel (n = 96, m = 160)."""
+    from sqp_solver_b200.synth import make_batch
+
+    B, n, m = 4, 96, 160
+    d = make_batch(B, n, m, seed0=9500)
+    d["P"][1, 5 * n + 5] = np.nan
+    args = (d["P"], d["q"], d["A"], d["l"], d["u"])
+    b = api.QPBatch(ctx, B, n, m)
+    b.settings = api.default_settings(adaptive_rho=1, alpha=1.6)
+    b.setup(*args)
+    assert ctx.last_kernel.startswith("block")
+    st = b.info()["status"]
+    assert st[1] == api.NUMERICAL_ISSUES and (np.delete(st, 1) == api.UNSOLVED).all()
+    b.solve(*args)
+    got = b.get()
+    ref = oracle.solve_batch(*args, oracle_settings_from(oracle, b.settings))
+    np.testing.assert_array_equal(got["status"], ref["status"])
+    ok = ref["status"] != api.NUMERICAL_ISSUES
+    sub = lambda o: {k: v[ok] for k, v in o.items() if isinstance(v, np.ndarray) and v.shape[:1] == (B,)}
+    assert_parity(sub(got), sub(ref), what="blocked kernel, separate setup/solve")
+    b.close()
 
 
 def test_api_argument_errors(api, ctx):
