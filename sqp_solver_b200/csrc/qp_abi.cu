@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "qp_common.cuh"
 #include "qp_tile.cuh"
@@ -51,6 +52,7 @@ struct sqpb200_qp_batch {
     int *sp_outer = nullptr, *sp_inner = nullptr;
     double *sp_vals = nullptr;
     int sp_nnz_cap = 0;
+    int *sp2_outer = nullptr, *sp2_inner = nullptr, *sp2_perm = nullptr;  // the other compressed view of the pattern
 };
 
 static int fail(sqpb200_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -189,7 +191,7 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
-                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals};
+                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -313,7 +315,7 @@ static int ensure_staging(sqpb200_qp_batch *b) {
 // One kernel launch over QPs [first, first+count) of the batch arrays.
 static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode, int first, int count,
                         const double *P, const double *q, const double *A, const double *l, const double *u,
-                        cudaStream_t stream, const int *ready = nullptr) {
+                        cudaStream_t stream, const int *ready = nullptr, const SparseA *sp = nullptr) {
     sqpb200_ctx *c = b->ctx;
     KernelParams p{};
     p.first = first;
@@ -330,14 +332,15 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     p.mode = mode;
     p.ready = ready;
     p.s = *st;
+    if (sp) p.sp = *sp;
     int slot = (int)(c->launches % sqpb200_ctx::kCounters);
     p.work_counter = c->counters + slot;
     CK(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
 
     // kernel choice: register-tiled (n <= 64, m <= 128) > blocked (n <= 256, m <= 1024) > generic (anything that fits)
     const size_t optin = c->prop.sharedMemPerBlockOptin;
-    const bool want_tile = c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
-    const bool want_block = !want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin);
+    const bool want_tile = !sp && c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
+    const bool want_block = sp || (!want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin));
     if (c->opt_kernel == 2 && !want_tile) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
     if (c->opt_kernel == 3 && !want_block) return fail(c, SQPB200_ERR_UNSUPPORTED, "blocked kernel forced but (n, m) is outside its range");
     const bool needs_fact = !want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE));
@@ -475,27 +478,51 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
     CK(c, cudaSetDevice(c->device));
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t n = b->n, m = b->m, B = count;
-    const int n_outer = layout == SQPB200_SPARSE_CSR ? b->m : b->n;
+    const bool csr = layout == SQPB200_SPARSE_CSR;
+    const int n_outer = csr ? b->m : b->n, n_innerdim = csr ? b->n : b->m;
     int rc = ensure_staging(b);
     if (rc) return rc;
     const bool dev = (flags & SQPB200_DEVICE_PTRS) != 0;
+
+    // host copy of the (small, batch-shared) pattern: validated here, and converted to the other compressed view
+    std::vector<int> h_outer(n_outer + 1), h_inner(nnz > 0 ? nnz : 1);
+    if (dev) {
+        CK(c, cudaMemcpyAsync(h_outer.data(), A_outer, sizeof(int) * (n_outer + 1), cudaMemcpyDeviceToHost, stream));
+        if (nnz > 0) CK(c, cudaMemcpyAsync(h_inner.data(), A_inner, sizeof(int) * nnz, cudaMemcpyDeviceToHost, stream));
+        CK(c, cudaStreamSynchronize(stream));
+    } else {
+        memcpy(h_outer.data(), A_outer, sizeof(int) * (n_outer + 1));
+        if (nnz > 0) memcpy(h_inner.data(), A_inner, sizeof(int) * nnz);
+    }
+    if (h_outer[0] != 0 || h_outer[n_outer] != nnz) return fail(c, SQPB200_ERR_INVALID, "sparse pattern: outer[0] must be 0 and outer[last] must be nnz");
+    for (int o = 0; o < n_outer; ++o)
+        if (h_outer[o] > h_outer[o + 1]) return fail(c, SQPB200_ERR_INVALID, "sparse pattern: outer pointers must be non-decreasing");
+    for (int e = 0; e < nnz; ++e)
+        if (h_inner[e] < 0 || h_inner[e] >= n_innerdim) return fail(c, SQPB200_ERR_INVALID, "sparse pattern: inner index out of range");
+
+    // device copies of the pattern, values and (for host callers) the dense vectors
+    if (nnz > b->sp_nnz_cap || !b->sp_outer) {
+        CK(c, cudaStreamSynchronize(stream));
+        int **ip[] = {&b->sp_outer, &b->sp_inner, &b->sp2_outer, &b->sp2_inner, &b->sp2_perm};
+        for (int **q2 : ip) {
+            if (*q2) cudaFree(*q2);
+            *q2 = nullptr;
+        }
+        if (b->sp_vals) cudaFree(b->sp_vals);
+        b->sp_vals = nullptr;
+        const size_t cap = nnz > 0 ? nnz : 1, od = (size_t)(b->m > b->n ? b->m : b->n) + 1;
+        cudaError_t e = cudaMalloc(&b->sp_outer, sizeof(int) * od);
+        if (e == cudaSuccess) e = cudaMalloc(&b->sp2_outer, sizeof(int) * od);
+        if (e == cudaSuccess) e = cudaMalloc(&b->sp_inner, sizeof(int) * cap);
+        if (e == cudaSuccess) e = cudaMalloc(&b->sp2_inner, sizeof(int) * cap);
+        if (e == cudaSuccess) e = cudaMalloc(&b->sp2_perm, sizeof(int) * cap);
+        if (e == cudaSuccess) e = cudaMalloc(&b->sp_vals, sizeof(double) * cap * b->batch);
+        if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "sparse staging cudaMalloc", e);
+        b->sp_nnz_cap = (int)cap;
+    }
     const int *d_outer = A_outer, *d_inner = A_inner;
     const double *d_vals = A_values, *dP = P, *dq = q, *dl = l, *du = u;
     if (!dev) {
-        if (nnz > b->sp_nnz_cap || !b->sp_outer) {
-            CK(c, cudaStreamSynchronize(stream));
-            if (b->sp_outer) cudaFree(b->sp_outer);
-            if (b->sp_inner) cudaFree(b->sp_inner);
-            if (b->sp_vals) cudaFree(b->sp_vals);
-            b->sp_outer = b->sp_inner = nullptr;
-            b->sp_vals = nullptr;
-            const size_t cap = nnz > 0 ? nnz : 1;
-            cudaError_t e = cudaMalloc(&b->sp_outer, sizeof(int) * ((b->m > b->n ? b->m : b->n) + 1));
-            if (e == cudaSuccess) e = cudaMalloc(&b->sp_inner, sizeof(int) * cap);
-            if (e == cudaSuccess) e = cudaMalloc(&b->sp_vals, sizeof(double) * cap * b->batch);
-            if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "sparse staging cudaMalloc", e);
-            b->sp_nnz_cap = (int)cap;
-        }
         CK(c, cudaMemcpyAsync(b->sp_outer, A_outer, sizeof(int) * (n_outer + 1), cudaMemcpyHostToDevice, stream));
         if (nnz > 0) {
             CK(c, cudaMemcpyAsync(b->sp_inner, A_inner, sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
@@ -510,13 +537,50 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         d_outer = b->sp_outer; d_inner = b->sp_inner; d_vals = b->sp_vals;
         dP = b->dP; dq = b->dq; dl = b->dl; du = b->du;
     }
-    cudaError_t e = launch_densify(d_vals, d_outer, d_inner, nnz, b->m, b->n, layout == SQPB200_SPARSE_CSR, count, b->dA, stream);
-    if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "densify launch", e);
-    c->launches += nnz > 0 ? 1 : 0;
     CK(c, cudaMemsetAsync(b->total_iters, 0, sizeof(unsigned long long), stream));
     b->fact_valid = false;
     b->fused_used = true;
-    rc = launch_range(b, s, MODE_RESET | MODE_FACTOR | MODE_SOLVE, 0, count, dP, dq, b->dA, dl, du, stream);
+    const unsigned mode = MODE_RESET | MODE_FACTOR | MODE_SOLVE;
+
+    // Shapes the register-tiled kernel covers keep A in registers anyway: densify. Larger ones run the blocked kernel with the
+    // values of one instance staged in shared memory and both compressed views of the pattern.
+    const bool sparse_kernel = (c->opt_kernel == 0 || c->opt_kernel == 3) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
+                               m > 0 && block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin);
+    if (!sparse_kernel) {
+        cudaError_t e = launch_densify(d_vals, d_outer, d_inner, nnz, b->m, b->n, csr, count, b->dA, stream);
+        if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "densify launch", e);
+        c->launches += nnz > 0 ? 1 : 0;
+        rc = launch_range(b, s, mode, 0, count, dP, dq, b->dA, dl, du, stream);
+    } else {
+        // the other compressed view by a counting sort over the inner index; perm maps its positions to the given order
+        std::vector<int> o2(n_innerdim + 1, 0), i2(nnz > 0 ? nnz : 1), perm(nnz > 0 ? nnz : 1);
+        for (int e = 0; e < nnz; ++e) o2[h_inner[e] + 1]++;
+        for (int k = 0; k < n_innerdim; ++k) o2[k + 1] += o2[k];
+        std::vector<int> cursor(o2.begin(), o2.end() - 1);
+        for (int o = 0; o < n_outer; ++o)
+            for (int e = h_outer[o]; e < h_outer[o + 1]; ++e) {
+                const int dst = cursor[h_inner[e]]++;
+                i2[dst] = o;
+                perm[dst] = e;
+            }
+        CK(c, cudaMemcpyAsync(b->sp2_outer, o2.data(), sizeof(int) * (n_innerdim + 1), cudaMemcpyHostToDevice, stream));
+        if (nnz > 0) {
+            CK(c, cudaMemcpyAsync(b->sp2_inner, i2.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
+            CK(c, cudaMemcpyAsync(b->sp2_perm, perm.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
+        }
+        CK(c, cudaStreamSynchronize(stream));  // the host vectors above go out of scope
+        SparseA sp{};
+        sp.vals = d_vals;
+        sp.nnz = nnz;
+        if (csr) {
+            sp.row_outer = d_outer; sp.row_inner = d_inner; sp.row_perm = nullptr;
+            sp.col_outer = b->sp2_outer; sp.col_inner = b->sp2_inner; sp.col_perm = b->sp2_perm;
+        } else {
+            sp.col_outer = d_outer; sp.col_inner = d_inner; sp.col_perm = nullptr;
+            sp.row_outer = b->sp2_outer; sp.row_inner = b->sp2_inner; sp.row_perm = b->sp2_perm;
+        }
+        rc = launch_range(b, s, mode, 0, count, dP, dq, nullptr, dl, du, stream, nullptr, &sp);
+    }
     if (rc) return rc;
     if (!dev) CK(c, cudaStreamSynchronize(stream));
     return SQPB200_OK;

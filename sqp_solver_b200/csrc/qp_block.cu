@@ -36,22 +36,75 @@ struct BlockSmem {
     double *z, *y, *w, *l, *u, *rho, *rhoinv;      // m each
     double *panel;                                 // np x 32 (factorisation only)
     double *wsm;                                   // 32 x 32 + 32
+    double *vals;                                  // nnz (sparse A: this instance's values), else unused
     signed char *type;                             // m
 };
-__device__ __forceinline__ BlockSmem carve_block(double *base, int np, int m) {
+__device__ __forceinline__ BlockSmem carve_block(double *base, int np, int m, int nnz) {
     BlockSmem s;
     s.x = base; s.xt = s.x + np; s.b = s.xt + np; s.q = s.b + np; s.t = s.q + np;
     s.z = s.t + np; s.y = s.z + m; s.w = s.y + m; s.l = s.w + m; s.u = s.l + m; s.rho = s.u + m; s.rhoinv = s.rho + m;
     s.panel = s.rhoinv + m + (m & 1);
     s.wsm = s.panel + (size_t)np * NB;
-    s.type = reinterpret_cast<signed char *>(s.wsm + WBLK);
+    s.vals = s.wsm + WBLK;
+    s.type = reinterpret_cast<signed char *>(s.vals + nnz);
     return s;
 }
-static size_t block_smem_bytes(int n, int m) {
+static size_t block_smem_bytes(int n, int m, int nnz = 0) {
     const size_t np = block_np(n);
-    return sizeof(double) * (5 * np + 7 * (size_t)m + 1 + np * NB + WBLK) + (size_t)m + 16;
+    return sizeof(double) * (5 * np + 7 * (size_t)m + 1 + np * NB + WBLK + (size_t)nnz) + (size_t)m + 16;
 }
 bool block_supported(int n, int m, size_t smem_optin) { return n >= 1 && n <= 256 && m >= 0 && m <= 1024 && block_smem_bytes(n, m) <= smem_optin; }
+// sparse A: this instance's nnz values are staged in shared memory next to the vectors
+bool block_sparse_supported(int n, int m, int nnz, size_t smem_optin) {
+    return n >= 1 && n <= 256 && m >= 1 && m <= 1024 && nnz >= 0 && block_smem_bytes(n, m, nnz) <= smem_optin;
+}
+
+// sparse row / column dot products against a shared-memory vector
+__device__ __forceinline__ double sp_rowdot(const SparseA &sp, const double *vals, int i, const double *vec) {
+    double acc = 0.0;
+    const int e = sp.row_outer[i + 1];
+    if (sp.row_perm) for (int p = sp.row_outer[i]; p < e; ++p) acc = fma(vals[sp.row_perm[p]], vec[sp.row_inner[p]], acc);
+    else for (int p = sp.row_outer[i]; p < e; ++p) acc = fma(vals[p], vec[sp.row_inner[p]], acc);
+    return acc;
+}
+__device__ __forceinline__ double sp_coldot(const SparseA &sp, const double *vals, int j, const double *vec) {
+    double acc = 0.0;
+    const int e = sp.col_outer[j + 1];
+    if (sp.col_perm) for (int p = sp.col_outer[j]; p < e; ++p) acc = fma(vals[sp.col_perm[p]], vec[sp.col_inner[p]], acc);
+    else for (int p = sp.col_outer[j]; p < e; ++p) acc = fma(vals[p], vec[sp.col_inner[p]], acc);
+    return acc;
+}
+
+// H (lower triangle) for sparse A: column j of A^T diag(rho) A is sum over the stored (k, j) of rho_k A_kj * (row k of A).
+// One warp per column, the entries of row k spread over the lanes (distinct i per lane: deterministic, no atomics);
+// the column is accumulated in a per-warp shared buffer (carved from the panel region, idle at this point).
+__device__ void form_H_sparse(const double *__restrict__ P, const SparseA &sp, const double *vals, const BlockSmem &s, int n, int np,
+                              double sigma, double *Hw) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *col = s.panel + (size_t)warp * np;
+    for (int j = warp; j < np; j += BNW) {
+        for (int i = lane; i < np; i += 32) col[i] = 0.0;
+        __syncwarp();
+        if (j < n) {
+            for (int pc = sp.col_outer[j]; pc < sp.col_outer[j + 1]; ++pc) {
+                const int k = sp.col_inner[pc];
+                const double f = s.rho[k] * vals[sp.col_perm ? sp.col_perm[pc] : pc];
+                for (int pr = sp.row_outer[k] + lane; pr < sp.row_outer[k + 1]; pr += 32) {
+                    const int i = sp.row_inner[pr];
+                    if (i >= j) col[i] = fma(f, vals[sp.row_perm ? sp.row_perm[pr] : pr], col[i]);
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = j + lane; i < np; i += 32) {
+            double v;
+            if (i < n && j < n) v = col[i] + P[i + (size_t)n * j] + (i == j ? sigma : 0.0);
+            else v = (i == j) ? 1.0 : 0.0;
+            Hw[i + (size_t)np * j] = v;
+        }
+        __syncwarp();
+    }
+}
 
 // ---- H = P_lowsym + sigma I + A^T diag(rho) A, lower triangle, into Hw (np x np, column-major) --------------------
 __device__ void form_H(const double *__restrict__ P, const double *__restrict__ A, const BlockSmem &s, int n, int np, int m,
@@ -248,7 +301,10 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
     __shared__ double s_red[7][BNW];
     const int n = p.n, m = p.m, np = block_np(p.n);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    BlockSmem s = carve_block(smem_raw, np, m);
+    const bool sparse = p.sp.row_outer != nullptr;
+    const int nnz = sparse ? p.sp.nnz : 0;
+    BlockSmem s = carve_block(smem_raw, np, m, nnz);
+    const SparseA sp = p.sp;
     const sqpb200_qp_settings st = p.s;
     const size_t fstride = block_fact_doubles_hd(n);
 
@@ -259,7 +315,12 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
         const int local = s_qp;
         if (local >= p.count) break;
         const size_t b = (size_t)p.first + local;
-        const double *P = p.P + b * n * n, *A = p.A + b * m * n;
+        const double *P = p.P + b * n * n, *A = sparse ? nullptr : p.A + b * m * n;
+        if (sparse) {
+            const double *gv = sp.vals + b * (size_t)nnz;
+            for (int e = tid; e < nnz; e += BT) s.vals[e] = gv[e];
+        }
+        const double *vals = s.vals;
         const double *q = p.q + b * n, *l = p.l + b * m, *u = p.u + b * m;
         double *Hw = p.fact + b * fstride, *Wd = Hw + (size_t)np * np;
 
@@ -305,7 +366,8 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
             if (reuse) {
                 status = SQPB200_UNSOLVED;
             } else {
-                form_H(P, A, s, n, np, m, st.sigma, Hw);
+                if (sparse) form_H_sparse(P, sp, vals, s, n, np, st.sigma, Hw);
+                else form_H(P, A, s, n, np, m, st.sigma, Hw);
                 __syncthreads();
                 const bool ok = factor_block(s, np, Hw, Wd, &s_fail);
                 status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
@@ -321,12 +383,22 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                 for (int i = tid; i < m; i += BT) s.w[i] = s.rho[i] * s.z[i] - s.y[i];
                 __syncthreads();
                 // b = sigma x - q + A^T w   (padded entries stay 0)
+                if (sparse) {
+                    for (int j = tid; j < np; j += BT) s.b[j] = (j < n) ? sigma * s.x[j] - s.q[j] + sp_coldot(sp, vals, j, s.w) : 0.0;
+                } else
                 for (int j = warp; j < np; j += BNW) {
                     double acc = 0.0;
                     if (j < n) {
                         const double *cj = A + (size_t)j * m;
-                        for (int i = lane; i < m; i += 32) acc += cj[i] * s.w[i];
-                        acc = warp_sum(acc);
+                        double a1 = 0.0;
+                        int i = lane;
+#pragma unroll 4
+                        for (; i + 32 < m; i += 64) {
+                            acc = fma(cj[i], s.w[i], acc);
+                            a1 = fma(cj[i + 32], s.w[i + 32], a1);
+                        }
+                        for (; i < m; i += 32) acc = fma(cj[i], s.w[i], acc);
+                        acc = warp_sum(acc + a1);
                     }
                     if (lane == 0) s.b[j] = (j < n) ? sigma * s.x[j] - s.q[j] + acc : 0.0;
                 }
@@ -335,8 +407,22 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                 for (int i = tid; i < n; i += BT) s.x[i] = alpha * s.xt[i] + (1.0 - alpha) * s.x[i];
                 // z~ = A x~ ; z, y updates (qp.cpp:93-103)
                 for (int i = tid; i < m; i += BT) {
-                    double acc = 0.0;
-                    for (int j = 0; j < n; ++j) acc += A[i + (size_t)m * j] * s.xt[j];
+                    double acc;
+                    if (sparse) {
+                        acc = sp_rowdot(sp, vals, i, s.xt);
+                    } else {
+                        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;  // independent chains: the loads are L2/HBM latency bound
+                        int j = 0;
+#pragma unroll 2
+                        for (; j + 3 < n; j += 4) {
+                            acc0 = fma(A[i + (size_t)m * j], s.xt[j], acc0);
+                            acc1 = fma(A[i + (size_t)m * (j + 1)], s.xt[j + 1], acc1);
+                            acc2 = fma(A[i + (size_t)m * (j + 2)], s.xt[j + 2], acc2);
+                            acc3 = fma(A[i + (size_t)m * (j + 3)], s.xt[j + 3], acc3);
+                        }
+                        for (; j < n; ++j) acc0 = fma(A[i + (size_t)m * j], s.xt[j], acc0);
+                        acc = (acc0 + acc1) + (acc2 + acc3);
+                    }
                     const double zh = alpha * acc + (1.0 - alpha) * s.z[i];
                     const double zn = box_project(zh + s.rhoinv[i] * s.y[i], s.l[i], s.u[i]);
                     s.y[i] = s.y[i] + s.rho[i] * (zh - zn);
@@ -350,15 +436,20 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                     double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
                     for (int i = tid; i < m; i += BT) {
                         double ax = 0.0;
-                        for (int j = 0; j < n; ++j) ax += A[i + (size_t)m * j] * s.x[j];
+                        if (sparse) ax = sp_rowdot(sp, vals, i, s.x);
+                        else for (int j = 0; j < n; ++j) ax += A[i + (size_t)m * j] * s.x[j];
                         mx[0] = absmax(mx[0], ax);
                         mx[1] = absmax(mx[1], s.z[i]);
                         mx[5] = absmax(mx[5], ax - s.z[i]);
                     }
                     for (int j = warp; j < n; j += BNW) {
-                        const double *cj = A + (size_t)j * m;
                         double aty = 0.0, px = 0.0;
-                        for (int i = lane; i < m; i += 32) aty += cj[i] * s.y[i];
+                        if (sparse) {
+                            if (lane == 0) aty = sp_coldot(sp, vals, j, s.y);
+                        } else {
+                            const double *cj = A + (size_t)j * m;
+                            for (int i = lane; i < m; i += 32) aty += cj[i] * s.y[i];
+                        }
                         for (int k = lane; k < n; k += 32) px += P[j + (size_t)n * k] * s.x[k];
                         aty = warp_sum(aty);
                         px = warp_sum(px);
@@ -400,7 +491,8 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                                 s.rhoinv[i] = 1.0 / r;
                             }
                             __syncthreads();
-                            form_H(P, A, s, n, np, m, sigma, Hw);
+                            if (sparse) form_H_sparse(P, sp, vals, s, n, np, sigma, Hw);
+                            else form_H(P, A, s, n, np, m, sigma, Hw);
                             __syncthreads();
                             const bool ok2 = factor_block(s, np, Hw, Wd, &s_fail);
                             if (tid == 0) p.fact_rho[b] = ok2 ? rho : nan("");
@@ -436,7 +528,7 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
 }
 
 cudaError_t launch_block(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, char *name, size_t name_len) {
-    const size_t smem = block_smem_bytes(p.n, p.m);
+    const size_t smem = block_smem_bytes(p.n, p.m, p.sp.row_outer ? p.sp.nnz : 0);
     if (smem > smem_optin) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(qp_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -446,7 +538,7 @@ cudaError_t launch_block(const KernelParams &p, int sm_count, size_t smem_optin,
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     long long grid = (long long)sm_count * occ;
     if (grid > p.count) grid = p.count;
-    if (name) snprintf(name, name_len, "block<%d>x%d", NB, occ);
+    if (name) snprintf(name, name_len, "block<%d>%sx%d", NB, p.sp.row_outer ? "/sparse" : "", occ);
     qp_block_kernel<<<(int)grid, BT, smem, stream>>>(p);
     return cudaGetLastError();
 }

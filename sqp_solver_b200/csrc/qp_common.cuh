@@ -40,6 +40,16 @@ enum : unsigned {
                              // instance whose constraint classes and rho are unchanged (the TODO at reference sqp.cpp:273)
 };
 
+// Sparse constraint matrix with one pattern shared by the batch (blocked kernel). Both a row-compressed and a
+// column-compressed view of the pattern are given; `vals` is stored in the order of ONE of them (perm == nullptr) and the
+// other view reaches it through its perm array. row_outer == nullptr means "A is dense".
+struct SparseA {
+    const int *row_outer, *row_inner, *row_perm;  // CSR view: row_outer[m+1], row_inner[nnz] = column indices
+    const int *col_outer, *col_inner, *col_perm;  // CSC view: col_outer[n+1], col_inner[nnz] = row indices
+    const double *vals;                           // [B][nnz]
+    int nnz;
+};
+
 struct KernelParams {
     int first;  // index of the first QP of this launch inside the batch arrays
     int count;  // QPs in this launch
@@ -58,6 +68,7 @@ struct KernelParams {
     unsigned long long *total_iters;
     unsigned mode;
     sqpb200_qp_settings s;
+    SparseA sp;  // all-zero for dense A
 };
 
 #ifdef __CUDACC__
@@ -121,6 +132,7 @@ int generic_grid(int count, int sm_count);
 bool generic_supported(int n, int m, size_t smem_optin);
 // blocked kernel for 64 < n <= 256 (qp_block.cu)
 bool block_supported(int n, int m, size_t smem_optin);
+bool block_sparse_supported(int n, int m, int nnz, size_t smem_optin);
 size_t block_fact_doubles(int n);
 cudaError_t launch_block(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, char *name, size_t name_len);
 cudaError_t launch_densify(const double *vals, const int *outer, const int *inner, int nnz, int m, int n, int csr, int count,

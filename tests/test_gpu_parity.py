@@ -563,9 +563,16 @@ def test_sparse_A_entry_point(api, ctx, oracle, layout, n, m, batch, density):
     b.setup_solve_sparse(d["P"], d["q"], vals, outer, inner, d["l"], d["u"],
                          layout=api.SPARSE_CSC if layout == "csc" else api.SPARSE_CSR)
     got = b.get()
+    kernel = ctx.last_kernel
     dense = run_fused(api, ctx, d, s, "auto")
-    for k in ("x", "y", "iter", "status"):
-        np.testing.assert_array_equal(got[k], dense[k], err_msg=k)
+    if n <= 64:  # register-tile shapes densify on the device: the very same kernel and arithmetic
+        assert "sparse" not in kernel
+        for k in ("x", "y", "iter", "status"):
+            np.testing.assert_array_equal(got[k], dense[k], err_msg=k)
+    else:  # blocked kernel walks the compressed pattern: different summation order, same algorithm
+        assert "/sparse" in kernel, kernel
+        np.testing.assert_array_equal(got["status"], dense["status"])
+        np.testing.assert_allclose(got["x"], dense["x"], rtol=1e-6, atol=1e-9)
     ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
     assert_parity(got, ref, what="sparse %s n=%d m=%d" % (layout, n, m))
     b.close()
