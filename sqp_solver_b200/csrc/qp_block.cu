@@ -32,7 +32,7 @@ __host__ __device__ inline size_t block_fact_doubles_hd(int n) {
 size_t block_fact_doubles(int n) { return block_fact_doubles_hd(n); }
 
 struct BlockSmem {
-    double *x, *xt, *b, *q, *t;                    // np each
+    double *x, *xt, *b, *q, *t, *dinv;             // np each
     double *z, *y, *w, *l, *u, *rho, *rhoinv;      // m each
     double *panel;                                 // np x 32 (factorisation only)
     double *wsm;                                   // 32 x 32 + 32
@@ -41,8 +41,8 @@ struct BlockSmem {
 };
 __device__ __forceinline__ BlockSmem carve_block(double *base, int np, int m, int nnz) {
     BlockSmem s;
-    s.x = base; s.xt = s.x + np; s.b = s.xt + np; s.q = s.b + np; s.t = s.q + np;
-    s.z = s.t + np; s.y = s.z + m; s.w = s.y + m; s.l = s.w + m; s.u = s.l + m; s.rho = s.u + m; s.rhoinv = s.rho + m;
+    s.x = base; s.xt = s.x + np; s.b = s.xt + np; s.q = s.b + np; s.t = s.q + np; s.dinv = s.t + np;
+    s.z = s.dinv + np; s.y = s.z + m; s.w = s.y + m; s.l = s.w + m; s.u = s.l + m; s.rho = s.u + m; s.rhoinv = s.rho + m;
     s.panel = s.rhoinv + m + (m & 1);
     s.wsm = s.panel + (size_t)np * NB;
     s.vals = s.wsm + WBLK;
@@ -51,7 +51,7 @@ __device__ __forceinline__ BlockSmem carve_block(double *base, int np, int m, in
 }
 static size_t block_smem_bytes(int n, int m, int nnz = 0) {
     const size_t np = block_np(n);
-    return sizeof(double) * (5 * np + 7 * (size_t)m + 1 + np * NB + WBLK + (size_t)nnz) + (size_t)m + 16;
+    return sizeof(double) * (6 * np + 7 * (size_t)m + 1 + np * NB + WBLK + (size_t)nnz) + (size_t)m + 16;
 }
 bool block_supported(int n, int m, size_t smem_optin) { return n >= 1 && n <= 256 && m >= 0 && m <= 1024 && block_smem_bytes(n, m) <= smem_optin; }
 // sparse A: this instance's nnz values are staged in shared memory next to the vectors
@@ -250,46 +250,97 @@ __device__ bool factor_block(const BlockSmem &s, int np, double *Hw, double *Wd,
     return true;
 }
 
-// ---- xt = H^-1 b by blocked substitution; b (in s.b) is destroyed ---------------------------------------------------
-__device__ void solve_block(const BlockSmem &s, int np, const double *__restrict__ Hw, const double *__restrict__ Wd) {
+// ---- the inverted diagonal blocks W_k and 1/d of the factor in the slab -> shared memory (the panel region is idle
+// outside the factorisation): the substitutions below read them every iteration ----------------------------------------
+__device__ void stage_W(const BlockSmem &s, int np, const double *Wd) {
+    const int nb = np / NB;
+    for (int e = threadIdx.x; e < nb * NB * NB; e += BT) s.panel[e] = Wd[(size_t)(e / (NB * NB)) * WBLK + (e % (NB * NB))];
+    for (int i = threadIdx.x; i < np; i += BT) s.dinv[i] = Wd[(size_t)(i / NB) * WBLK + NB * NB + (i % NB)];
+    __syncthreads();
+}
+
+// ---- xt = H^-1 b by blocked substitution; b (in s.b) is destroyed. W_k, 1/d from shared memory (stage_W), the
+// off-diagonal panels of L streamed from the slab (L2) with every load of a step in flight at once -----------------------
+__device__ void solve_block(const BlockSmem &s, int np, const double *Hw) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = np / NB;
     // forward: t = D^-1 L^-1 b
     for (int kb = 0; kb < nb; ++kb) {
         const int r0 = kb * NB;
-        const double *W = Wd + (size_t)kb * WBLK;
+        const double *W = s.panel + (size_t)kb * NB * NB;
         if (tid < NB) {
-            double acc = 0.0;
-            for (int c = 0; c <= tid; ++c) acc += W[tid + NB * c] * s.b[r0 + c];
-            s.t[r0 + tid] = acc;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int c = 0;
+            for (; c + 3 <= tid; c += 4) {
+                a0 = fma(W[tid + NB * c], s.b[r0 + c], a0);
+                a1 = fma(W[tid + NB * (c + 1)], s.b[r0 + c + 1], a1);
+                a2 = fma(W[tid + NB * (c + 2)], s.b[r0 + c + 2], a2);
+                a3 = fma(W[tid + NB * (c + 3)], s.b[r0 + c + 3], a3);
+            }
+            for (; c <= tid; ++c) a0 = fma(W[tid + NB * c], s.b[r0 + c], a0);
+            s.t[r0 + tid] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
-        for (int r = r0 + NB + tid; r < np; r += BT) {
-            double acc = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < NB; ++c) acc += Hw[r + (size_t)np * (r0 + c)] * s.t[r0 + c];
-            s.b[r] -= acc;
+        const int r = r0 + NB + tid;  // np - r0 - NB <= 224 < BT rows remain: one per thread
+        if (r < np) {
+            const double *col = Hw + r + (size_t)np * r0;
+            double v[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) v[c] = col[(size_t)np * c];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int c = 0; c < NB; c += 4) {
+                a0 = fma(v[c], s.t[r0 + c], a0);
+                a1 = fma(v[c + 1], s.t[r0 + c + 1], a1);
+                a2 = fma(v[c + 2], s.t[r0 + c + 2], a2);
+                a3 = fma(v[c + 3], s.t[r0 + c + 3], a3);
+            }
+            s.b[r] -= (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
     }
-    for (int i = tid; i < np; i += BT) s.t[i] *= Wd[(size_t)(i / NB) * WBLK + NB * NB + (i % NB)];
+    for (int i = tid; i < np; i += BT) s.t[i] *= s.dinv[i];
     __syncthreads();
     // backward: xt = L^-T t
     for (int kb = nb - 1; kb >= 0; --kb) {
         const int r0 = kb * NB;
-        const double *W = Wd + (size_t)kb * WBLK;
-        for (int c = warp; c < NB; c += BNW) {
-            const double *col = Hw + (size_t)np * (r0 + c);
-            double acc = 0.0;
-            for (int r = r0 + NB + lane; r < np; r += 32) acc += col[r] * s.xt[r];
-            acc = warp_sum(acc);
-            if (lane == 0) s.b[r0 + c] = s.t[r0 + c] - acc;  // b is free: reuse as the block right-hand side
+        const double *W = s.panel + (size_t)kb * NB * NB;
+        const int chunks = (np - r0 - NB) / 32;  // <= 7 chunks of 32 rows below the block
+        if (chunks > 0) {
+            // warp w owns columns r0 + w + 8 q (q = 0..3) of the panel; all 4 x chunks loads are issued before the first use
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double *base = Hw + (size_t)np * (r0 + warp);
+#pragma unroll
+            for (int ch = 0; ch < 7; ++ch) {
+                const bool live = ch < chunks;
+                const int r = live ? r0 + NB + 32 * ch + lane : r0 + NB + lane;
+                const double xr = live ? s.xt[r] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = fma(base[r + (size_t)np * 8 * q], xr, acc[q]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+            if (lane < 4) {
+                const double a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+                s.b[r0 + warp + 8 * lane] = s.t[r0 + warp + 8 * lane] - a;  // b is free: reuse as the block right-hand side
+            }
+        } else if (tid < NB) {
+            s.b[r0 + tid] = s.t[r0 + tid];
         }
         __syncthreads();
         if (tid < NB) {
-            double acc = 0.0;
-            for (int c = tid; c < NB; ++c) acc += W[c + NB * tid] * s.b[r0 + c];
-            s.xt[r0 + tid] = acc;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int c = tid;
+            for (; c + 3 < NB; c += 4) {
+                a0 = fma(W[c + NB * tid], s.b[r0 + c], a0);
+                a1 = fma(W[c + 1 + NB * tid], s.b[r0 + c + 1], a1);
+                a2 = fma(W[c + 2 + NB * tid], s.b[r0 + c + 2], a2);
+                a3 = fma(W[c + 3 + NB * tid], s.b[r0 + c + 3], a3);
+            }
+            for (; c < NB; ++c) a0 = fma(W[c + NB * tid], s.b[r0 + c], a0);
+            s.xt[r0 + tid] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
     }
@@ -378,6 +429,7 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
         long long executed = 0;
         if ((p.mode & MODE_SOLVE) && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES) {
             const double alpha = st.alpha, sigma = st.sigma;
+            stage_W(s, np, Wd);
             int iter;
             for (iter = 1; iter <= st.max_iter; ++iter) {
                 for (int i = tid; i < m; i += BT) s.w[i] = s.rho[i] * s.z[i] - s.y[i];
@@ -403,7 +455,7 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                     if (lane == 0) s.b[j] = (j < n) ? sigma * s.x[j] - s.q[j] + acc : 0.0;
                 }
                 __syncthreads();
-                solve_block(s, np, Hw, Wd);  // x~ in s.xt (qp.cpp:90)
+                solve_block(s, np, Hw);  // x~ in s.xt (qp.cpp:90)
                 for (int i = tid; i < n; i += BT) s.x[i] = alpha * s.xt[i] + (1.0 - alpha) * s.x[i];
                 // z~ = A x~ ; z, y updates (qp.cpp:93-103)
                 for (int i = tid; i < m; i += BT) {
@@ -500,6 +552,7 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                                 status = SQPB200_NUMERICAL_ISSUES;
                                 break;
                             }
+                            stage_W(s, np, Wd);
                         }
                     }
                 }
