@@ -84,7 +84,7 @@ typedef enum sqpb200_error {
 
 /* context options for sqpb200_ctx_set_option */
 #define SQPB200_OPT_KERNEL 1       /* 0 = auto (default), 1 = force the generic kernel, 2 = force the register-tiled kernel,
-                                      3 = force the blocked kernel (tests / tuning) */
+                                      3 = force the blocked kernel, 4 = force the cluster kernel (sparse A only) (tests / tuning) */
 #define SQPB200_OPT_H2D_CHUNKS 2   /* number of staging chunks for HOST_PTRS calls (default 16) */
 #define SQPB200_OPT_CTAS_PER_SM 3  /* 0 = auto */
 #define SQPB200_OPT_TILE_WARPS 4   /* warps per QP of the register-tiled kernel: 0 = default; 4 (default) or 8 for the 64x128 class, 1 (default) or 2 for the 32x64 class (tuning/tests) */

@@ -22,7 +22,7 @@ INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = range(3)  # qp.hpp:13
 STATUS_NAMES = ["SOLVED", "MAX_ITER_EXCEEDED", "UNSOLVED", "NUMERICAL_ISSUES", "UNINITIALIZED"]
 HOST_PTRS, DEVICE_PTRS = 0, 1
 OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS = 1, 2, 3, 4
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE, KERNEL_BLOCK = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE, KERNEL_BLOCK, KERNEL_CLUSTER = 0, 1, 2, 3, 4
 KEEP_FACTOR, REUSE_FACTOR = 1, 2
 SPARSE_CSC, SPARSE_CSR = 0, 1
 

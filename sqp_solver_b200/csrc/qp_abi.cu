@@ -53,6 +53,7 @@ struct sqpb200_qp_batch {
     double *sp_vals = nullptr;
     int sp_nnz_cap = 0;
     int *sp2_outer = nullptr, *sp2_inner = nullptr, *sp2_perm = nullptr;  // the other compressed view of the pattern
+    unsigned *sp_pack = nullptr;  // [2][cap]: packed (index | value position << 10) entries of the CSC and the CSR view (cluster kernel)
 };
 
 static int fail(sqpb200_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -150,7 +151,7 @@ int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
     if (!c) return SQPB200_ERR_INVALID;
     switch (option) {
         case SQPB200_OPT_KERNEL:
-            if (value < 0 || value > 3) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_KERNEL: value must be 0, 1, 2 or 3");
+            if (value < 0 || value > 4) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_KERNEL: value must be 0..4");
             c->opt_kernel = value;
             return SQPB200_OK;
         case SQPB200_OPT_H2D_CHUNKS:
@@ -191,7 +192,7 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
-                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm};
+                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm, b->sp_pack};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -340,17 +341,29 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     // kernel choice: register-tiled (n <= 64, m <= 128) > blocked (n <= 256, m <= 1024) > generic (anything that fits)
     const size_t optin = c->prop.sharedMemPerBlockOptin;
     const bool want_tile = !sp && c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
-    const bool want_block = sp || (!want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin));
+    // sparse A: a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
+    int clusters = 0;
+    if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && cluster_sparse_supported(b->n, b->m, sp->nnz, optin) &&
+        mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE) && !ready)
+        clusters = cluster_max_clusters(b->n, b->m, sp->nnz);
+    if (c->opt_kernel == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
+    const bool want_cluster = clusters >= 1;
+    const bool want_block = !want_cluster && (sp || (!want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin)));
     if (c->opt_kernel == 2 && !want_tile) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
     if (c->opt_kernel == 3 && !want_block) return fail(c, SQPB200_ERR_UNSUPPORTED, "blocked kernel forced but (n, m) is outside its range");
-    const bool needs_fact = !want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE));
+    const bool needs_fact = !want_cluster && (!want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE)));
     if (needs_fact) {
         int rc = ensure_fact(b, want_block ? block_fact_doubles(b->n) : (size_t)b->n * b->n);
         if (rc) return rc;
     }
     p.fact = b->fact;
     cudaError_t e;
-    if (want_tile) {
+    if (want_cluster) {
+        if (clusters > count) clusters = count;
+        int rc = ensure_scratch(c, cluster_scratch_bytes(clusters));
+        if (rc) return rc;
+        e = launch_cluster(p, clusters, (double *)c->scratch, stream, c->last_kernel, sizeof c->last_kernel);
+    } else if (want_tile) {
         e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, c->opt_tile_warps, stream, c->last_kernel, sizeof c->last_kernel);
     } else if (want_block) {
         e = launch_block(p, c->prop.multiProcessorCount, optin, stream, c->last_kernel, sizeof c->last_kernel);
@@ -510,6 +523,8 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         }
         if (b->sp_vals) cudaFree(b->sp_vals);
         b->sp_vals = nullptr;
+        if (b->sp_pack) cudaFree(b->sp_pack);
+        b->sp_pack = nullptr;
         const size_t cap = nnz > 0 ? nnz : 1, od = (size_t)(b->m > b->n ? b->m : b->n) + 1;
         cudaError_t e = cudaMalloc(&b->sp_outer, sizeof(int) * od);
         if (e == cudaSuccess) e = cudaMalloc(&b->sp2_outer, sizeof(int) * od);
@@ -517,6 +532,7 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         if (e == cudaSuccess) e = cudaMalloc(&b->sp2_inner, sizeof(int) * cap);
         if (e == cudaSuccess) e = cudaMalloc(&b->sp2_perm, sizeof(int) * cap);
         if (e == cudaSuccess) e = cudaMalloc(&b->sp_vals, sizeof(double) * cap * b->batch);
+        if (e == cudaSuccess) e = cudaMalloc(&b->sp_pack, sizeof(unsigned) * 2 * cap);
         if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "sparse staging cudaMalloc", e);
         b->sp_nnz_cap = (int)cap;
     }
@@ -544,8 +560,9 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
 
     // Shapes the register-tiled kernel covers keep A in registers anyway: densify. Larger ones run the blocked kernel with the
     // values of one instance staged in shared memory and both compressed views of the pattern.
-    const bool sparse_kernel = (c->opt_kernel == 0 || c->opt_kernel == 3) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
-                               m > 0 && block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin);
+    const bool sparse_kernel = (c->opt_kernel == 0 || c->opt_kernel == 3 || c->opt_kernel == 4) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
+                               m > 0 && (block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin) ||
+                                         cluster_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin));
     if (!sparse_kernel) {
         cudaError_t e = launch_densify(d_vals, d_outer, d_inner, nnz, b->m, b->n, csr, count, b->dA, stream);
         if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "densify launch", e);
@@ -568,8 +585,22 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
             CK(c, cudaMemcpyAsync(b->sp2_inner, i2.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
             CK(c, cudaMemcpyAsync(b->sp2_perm, perm.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
         }
+        // packed entries for the cluster kernel: inner index (10 bits) | position of the value in the caller's order
+        std::vector<unsigned> pack(2 * (size_t)(nnz > 0 ? nnz : 1));
+        {
+            unsigned *pc = pack.data(), *pr = pack.data() + nnz;  // CSC view, CSR view
+            for (int e = 0; e < nnz; ++e) {
+                const unsigned given = (unsigned)h_inner[e] | ((unsigned)e << 10);
+                const unsigned other = (unsigned)i2[e] | ((unsigned)perm[e] << 10);
+                (csr ? pr : pc)[e] = given;
+                (csr ? pc : pr)[e] = other;
+            }
+        }
+        if (nnz > 0) CK(c, cudaMemcpyAsync(b->sp_pack, pack.data(), sizeof(unsigned) * 2 * nnz, cudaMemcpyHostToDevice, stream));
         CK(c, cudaStreamSynchronize(stream));  // the host vectors above go out of scope
         SparseA sp{};
+        sp.col_pack = b->sp_pack;
+        sp.row_pack = b->sp_pack + nnz;
         sp.vals = d_vals;
         sp.nnz = nnz;
         if (csr) {

@@ -1,0 +1,619 @@
+// Thread-block-cluster batched ADMM QP kernel for sparse constraint matrices with 64 < n <= 256 -- BASELINE.json config 5
+// (n = 256, m = 512, one sparsity pattern shared by the batch).
+//
+// One CLUSTER of CS = 4 CTAs (4 SMs) per QP, persistent clusters on the atomic work queue. H^-1 (n x n fp64, 512 KB at
+// n = 256) does not fit in one SM's shared memory, but it fits in the cluster's: CTA r keeps rows [r n/4, (r+1) n/4) of it
+// (all columns) in its own shared memory for the whole solve, so the per-iteration KKT solve (reference qp.cpp:90) is ONE
+// dense mat-vec out of shared memory -- no substitution chain, no L2 traffic. Per iteration the CTAs exchange only vectors
+// over distributed shared memory (w = rho.*z - y, m doubles, and x~, n doubles: two all-gathers, two cluster barriers).
+//   * A stays compressed: the values of this instance (nnz doubles) sit in every CTA's shared memory, the batch-shared
+//     pattern (CSR and CSC views) is read through L1/L2. Every CTA forms b = sigma x - q + A^T w redundantly (one column
+//     per thread) and z~ = A x~ for the constraint rows it owns.
+//   * H = P_lowsym + sigma I + A^T diag(rho) A is formed slice by slice straight from the pattern and inverted in place by a
+//     BLOCKED symmetric sweep (Gauss-Jordan on 32-pivot blocks): per block the owner CTA inverts the 32 x 32 pivot block (its
+//     pivots are the D of the unpivoted L D L^T of H: a zero/NaN pivot reports NUMERICAL_ISSUES like Eigen::LDLT::info()) and
+//     publishes it with its 32 pivot rows through a small global (L2) scratch; every CTA then applies the rank-32 update to
+//     its own row slice on the fp64 tensor cores (mma.sync m8n8k4 DMMA, operands from shared memory).
+// Reference functions covered: the same list as qp_generic.cu (all of src/qp.cpp:11-371), fused setup + solve only (the sparse
+// entry point has no separate setup/solve launches).
+#include <cooperative_groups.h>
+
+#include <cstdio>
+
+#include "qp_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sqpb200 {
+
+#ifdef SQPB200_CLUSTER_TIMING
+#define TCK(i) { long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; }
+#else
+#define TCK(i)
+#endif
+
+constexpr int CS = 4;    // CTAs per cluster
+constexpr int CT = 256;  // threads per CTA
+constexpr int CNW = CT / 32;
+constexpr int KB = 32;   // pivot block
+constexpr int RCH = 64;  // columns of the pivot row panel staged per chunk
+constexpr int LDR = KB + 4;  // leading dimension of a staged chunk (k contiguous): conflict-free B fragments
+constexpr int LDE = KB + 1;
+
+__host__ __device__ inline int cluster_np(int n) { return n <= 128 ? 128 : 256; }
+__host__ __device__ inline size_t cluster_scratch_doubles() { return 2 * ((size_t)KB * 256 + KB * KB + 8); }  // per cluster
+
+struct ClusterSmem {
+    double *S;     // (RS + 2) x np: this CTA's row slice, column-major
+    double *X;     // aliased region: nnz values of this instance | sweep buffers (R chunks, T, E)
+    double *sw;    // m (+1)
+    double *sb, *sxt, *sx, *sq;  // np each
+    double *part;  // 2 * CT
+    double *red;   // CS * 8
+};
+__host__ __device__ inline size_t cluster_x_doubles(int np, int m, int nnz) {
+    const size_t RS = np / CS;
+    const size_t sweep = 2 * (size_t)LDR * RCH + (RS + 4) * KB + 2 * (size_t)LDE * KB;
+    // sparse data of the instance: values | packed CSC entries | packed CSR entries | column pointers | row pointers
+    size_t v = (size_t)nnz + (nnz & 1) + (2 * (size_t)nnz + (size_t)np + 1 + (size_t)m + 1 + 1) / 2;
+    v += v & 1;  // keeps every region behind it 16-byte aligned
+    return v > sweep ? v : sweep;
+}
+__host__ __device__ inline size_t cluster_smem_doubles(int np, int m, int nnz) {
+    const size_t RS = np / CS;
+    return (RS + 2) * np + cluster_x_doubles(np, m, nnz) + (size_t)(m + (m & 1)) + 4 * (size_t)np + 2 * CT + CS * 8;
+}
+__device__ __forceinline__ ClusterSmem carve_cluster(double *base, int np, int m, int nnz) {
+    ClusterSmem s;
+    const int RS = np / CS;
+    s.S = base;
+    s.X = s.S + (size_t)(RS + 2) * np;
+    s.sw = s.X + cluster_x_doubles(np, m, nnz);
+    s.sb = s.sw + (m + (m & 1));
+    s.sxt = s.sb + np;
+    s.sx = s.sxt + np;
+    s.sq = s.sx + np;
+    s.part = s.sq + np;
+    s.red = s.part + 2 * CT;
+    return s;
+}
+
+bool cluster_sparse_supported(int n, int m, int nnz, size_t smem_optin) {
+    return n > 64 && n <= 256 && m >= 1 && m <= CS * CT && nnz >= 0 &&
+           sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz) + 64 <= smem_optin;
+}
+
+__device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
+
+// sparse dot product of one compressed row / column (entries [p0, p1) of a packed view: inner index | value position << 10)
+// with a shared-memory vector; everything it touches is in shared memory
+__device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p1, const double *vals, const double *vec) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int p = p0;
+    for (; p + 3 < p1; p += 4) {
+        const unsigned e0 = pack[p], e1 = pack[p + 1], e2 = pack[p + 2], e3 = pack[p + 3];
+        a0 = fma(vals[e0 >> 10], vec[e0 & 1023u], a0);
+        a1 = fma(vals[e1 >> 10], vec[e1 & 1023u], a1);
+        a2 = fma(vals[e2 >> 10], vec[e2 & 1023u], a2);
+        a3 = fma(vals[e3 >> 10], vec[e3 & 1023u], a3);
+    }
+    for (; p < p1; ++p) {
+        const unsigned e0 = pack[p];
+        a0 = fma(vals[e0 >> 10], vec[e0 & 1023u], a0);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, double *scratch) {
+    extern __shared__ __align__(16) double smem_raw[];
+    __shared__ int s_qp;
+    __shared__ double s_wred[7][CNW];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / CS;
+    const int n = p.n, m = p.m, np = cluster_np(p.n);
+    const int RS = np / CS, LD = RS + 2, LDT = RS + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const SparseA sp = p.sp;
+    const int nnz = sp.nnz;
+    ClusterSmem s = carve_cluster(smem_raw, np, m, nnz);
+    double *vals = s.X;
+    unsigned *cpack = reinterpret_cast<unsigned *>(s.X + nnz + (nnz & 1));
+    unsigned *rpack = cpack + nnz;
+    int *couter = reinterpret_cast<int *>(rpack + nnz), *router = couter + np + 1;
+    double *Rb = s.X, *Tm = s.X + 2 * LDR * RCH, *Eb = Tm + (size_t)LDT * KB;
+    const sqpb200_qp_settings st = p.s;
+    const double sigma = st.sigma, alpha = st.alpha;
+    // constraint rows owned by this CTA: one per thread
+    const int RM = (m + CS - 1) / CS;
+    const int row_lo = rank * RM;
+    const int rows_own = max(0, min(m, row_lo + RM) - row_lo);
+    const bool has_row = tid < rows_own;
+    const int my_row = row_lo + tid;
+    // peers' copies of the exchanged vectors
+    double *peer_sw[CS], *peer_sxt[CS], *peer_red[CS];
+    int *peer_qp[CS];
+#pragma unroll
+    for (int r = 0; r < CS; ++r) {
+        peer_sw[r] = cluster.map_shared_rank(s.sw, r);
+        peer_sxt[r] = cluster.map_shared_rank(s.sxt, r);
+        peer_red[r] = cluster.map_shared_rank(s.red, r);
+        peer_qp[r] = cluster.map_shared_rank(&s_qp, r);
+    }
+    double *scr_base = scratch + (size_t)cid * cluster_scratch_doubles();
+
+#ifdef SQPB200_CLUSTER_TIMING
+    long long tph[16] = {0}, tlast = 0;
+#endif
+    for (;;) {
+        if (rank == 0 && tid == 0) {
+            const int v = draw_qp(p);
+#pragma unroll
+            for (int r = 0; r < CS; ++r) *peer_qp[r] = v;
+        }
+        cluster.sync();
+        const int local = s_qp;
+        if (local >= p.count) break;
+        const size_t b = (size_t)p.first + local;
+        const double *P = p.P + b * n * n, *q = p.q + b * n, *l = p.l + b * m, *u = p.u + b * m;
+        const double *gvals = sp.vals + b * (size_t)nnz;
+
+        int status = SQPB200_UNSOLVED;
+        int rho_updates = p.rho_updates[b] + 1;  // rho_vec_update, qp.cpp:313
+        double rho_est = p.rho_estimate[b], res_prim = p.res_prim[b], res_dual = p.res_dual[b];
+        double rho = st.rho;
+        int iter_out = p.iter[b];
+
+        // values of this instance + the batch-shared pattern -> shared memory (the region is reused by the sweep: restaged after it)
+        auto stage_sparse = [&]() {
+            for (int e = tid; e < nnz; e += CT) {
+                vals[e] = gvals[e];
+                cpack[e] = __ldg(sp.col_pack + e);
+                rpack[e] = __ldg(sp.row_pack + e);
+            }
+            for (int j = tid; j <= np; j += CT) couter[j] = j <= n ? __ldg(sp.col_outer + j) : nnz;
+            for (int i = tid; i <= m; i += CT) router[i] = __ldg(sp.row_outer + i);
+        };
+        stage_sparse();
+        for (int j = tid; j < np; j += CT) {
+            s.sq[j] = j < n ? q[j] : 0.0;
+            s.sx[j] = 0.0;
+            s.sxt[j] = 0.0;
+        }
+        // per-row state of the owned constraint rows lives in registers (qp.cpp:16-18, 31-32)
+        double zr = 0.0, yr = 0.0, lo = 0.0, up = 0.0, rhor = 1.0, rinv = 1.0;
+        int typ = SQPB200_LOOSE_BOUNDS;
+        if (has_row) {
+            lo = l[my_row];
+            up = u[my_row];
+            typ = classify(lo, up);
+            p.ctype[b * m + my_row] = (signed char)typ;
+            rhor = rho_of(typ, rho);
+            rinv = 1.0 / rhor;
+        }
+        __syncthreads();
+
+        // ---- (re)factorisation: S <- -(P_lowsym + sigma I + A^T diag(rho) A)^-1, row slice by row slice -----------------
+        // Needs vals staged; leaves vals staged. Returns the same value in every thread of the cluster.
+        auto factorize = [&]() -> bool {
+#ifdef SQPB200_CLUSTER_TIMING
+            tlast = clock64();
+#endif
+            // rho of every row (form H touches all rows of a column): recomputed from the bounds, as classified at setup
+            for (int i = tid; i < m; i += CT) s.sw[i] = rho_of(classify(l[i], u[i]), rho);
+            // P_lowsym + sigma I (LDLT<Lower> reads the lower triangle only); padded variables get a unit diagonal
+            for (int e = tid; e < RS * np; e += CT) {
+                const int r = e % RS, j = e / RS, i = RS * rank + r;
+                double v;
+                if (i < n && j < n) v = (i >= j ? P[i + (size_t)n * j] : P[j + (size_t)n * i]) + (i == j ? sigma : 0.0);
+                else v = (i == j) ? 1.0 : 0.0;
+                s.S[r + LD * j] = v;
+            }
+            __syncthreads();
+            // + A^T diag(rho) A: row i of H gathers, for every stored (k, i), rho_k A_ki times row k of A. One warp per row,
+            // the entries of row k over the lanes (distinct columns: no conflicts, fixed order)
+            for (int r = warp; r < RS; r += CNW) {
+                const int i = RS * rank + r;
+                if (i >= n) continue;
+                for (int pc = couter[i]; pc < couter[i + 1]; ++pc) {
+                    const unsigned ec = cpack[pc];
+                    const int k = (int)(ec & 1023u);
+                    const double f = s.sw[k] * vals[ec >> 10];
+                    for (int pr = router[k] + lane; pr < router[k + 1]; pr += 32) {
+                        const unsigned er = rpack[pr];
+                        double *dst = s.S + r + LD * (int)(er & 1023u);
+                        *dst = fma(f, vals[er >> 10], *dst);
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();  // the sweep buffers alias vals from here on
+            TCK(0)
+
+            bool ok = true;
+            const int nblk = np / KB;
+            for (int kb = 0; kb < nblk; ++kb) {
+                const int k0 = kb * KB;
+                const int owner = k0 / RS, k0l = k0 - owner * RS;
+                double *scr = scr_base + (size_t)(kb & 1) * ((size_t)KB * 256 + KB * KB + 8);
+                double *scrR = scr, *scrE = scr + (size_t)KB * np, *scrF = scrE + KB * KB;
+                if (rank == owner) {
+                    // publish the (old) pivot rows S[K, :] first: coalesced over k
+                    for (int e = tid; e < KB * np; e += CT) {
+                        const int k = e % KB, j = e / KB;
+                        scrR[e] = s.S[(k0l + k) + LD * j];
+                    }
+                    TCK(13)
+                    // pivot block -> Eb[0], then an in-place symmetric sweep, one pivot per barrier (double buffered)
+                    double *E0 = Eb, *E1 = Eb + LDE * KB;
+                    for (int e = tid; e < KB * KB; e += CT) {
+                        const int i = e % KB, j = e / KB;
+                        E0[i * LDE + j] = s.S[(k0l + i) + LD * (k0 + j)];
+                    }
+                    __syncthreads();
+                    bool bad = false;
+                    const int ei = tid >> 3, ej0 = (tid & 7) * 4;
+                    for (int pv = 0; pv < KB; ++pv) {
+                        const double *src = (pv & 1) ? E1 : E0;
+                        double *dst = (pv & 1) ? E0 : E1;
+                        const double d = src[pv * LDE + pv];
+                        if (!(fabs(d) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
+                            bad = true;
+                            break;
+                        }
+                        const double inv_d = 1.0 / d;
+                        const double ci = src[ei * LDE + pv], ti = ci * inv_d;
+                        double sv[4], cj[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            sv[t] = src[ei * LDE + ej0 + t];
+                            cj[t] = src[pv * LDE + ej0 + t];
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int ej = ej0 + t;
+                            double v = fma(-ti, cj[t], sv[t]);
+                            v = (ej == pv) ? ti : v;
+                            const double rowv = (ej == pv) ? -inv_d : cj[t] * inv_d;
+                            dst[ei * LDE + ej] = (ei == pv) ? rowv : v;
+                        }
+                        __syncthreads();
+                    }
+                    TCK(14)
+                    // KB is even: the result (-E^-1) is back in E0
+                    for (int e = tid; e < KB * KB; e += CT) scrE[e] = bad ? 0.0 : -E0[(e % KB) * LDE + (e / KB)];
+                    if (tid == 0) scrF[0] = bad ? 1.0 : 0.0;
+                    __threadfence();
+                }
+                TCK(1)
+                cluster.sync();
+                TCK(2)
+                if (ldcg(scrF) != 0.0) {
+                    ok = false;
+                    break;
+                }
+                // E^-1 -> Eb (every CTA)
+                for (int e = tid; e < KB * KB; e += CT) Eb[(e % KB) * LDE + (e / KB)] = ldcg(scrE + e);
+                __syncthreads();
+                // T = S[own rows, K] E^-1 on the tensor cores (8-row block x four 8-column tiles per warp, K = 32); the owner's
+                // pivot rows carry -E^-1 instead (their update then yields E^-1 S[K, :])
+                {
+                    const int RBN = RS / 8, rb = warp % RBN, tsplit = CNW / RBN, tpart = warp / RBN;
+                    const bool pivot_rb = rank == owner && 8 * rb >= k0l && 8 * rb < k0l + KB;
+                    double t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int ks = 0; ks < KB / 4; ++ks) {
+                        const double av = s.S[(8 * rb + fr) + LD * (k0 + 4 * ks + fk)];
+#pragma unroll
+                        for (int jt = 0; jt < 4; ++jt) {
+                            if (jt % tsplit != tpart) continue;
+                            const double bv = Eb[(4 * ks + fk) * LDE + 8 * jt + fr];
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                         : "+d"(t0[jt]), "+d"(t1[jt])
+                                         : "d"(av), "d"(bv));
+                        }
+                    }
+#pragma unroll
+                    for (int jt = 0; jt < 4; ++jt) {
+                        if (jt % tsplit != tpart) continue;
+                        const int r = 8 * rb + fr, c = 8 * jt + 2 * fk;
+                        Tm[r + LDT * c] = pivot_rb ? -Eb[(r - k0l) * LDE + c] : t0[jt];
+                        Tm[r + LDT * (c + 1)] = pivot_rb ? -Eb[(r - k0l) * LDE + c + 1] : t1[jt];
+                    }
+                }
+                __syncthreads();
+                TCK(3)
+                // rank-32 update of the slice on the fp64 tensor cores: S[own, j] <- S[own, j] - T R[:, j] (pivot rows start from 0)
+                {
+                    const int RBN = RS / 8;        // 8-row blocks of the slice: 8 or 4
+                    const int rb = warp % RBN;     // this warp's row block
+                    const int tsplit = CNW / RBN;  // warps sharing a row block split the column tiles: 1 or 2
+                    const int tpart = warp / RBN;
+                    const bool pivot_rb = rank == owner && 8 * rb >= k0l && 8 * rb < k0l + KB;
+                    double af[KB / 4];
+#pragma unroll
+                    for (int ks = 0; ks < KB / 4; ++ks) af[ks] = -Tm[(8 * rb + fr) + LDT * (4 * ks + fk)];
+                    const int nch = np / RCH;
+                    for (int ch = 0; ch < nch; ++ch) {
+                        double *Rc = Rb + (size_t)(ch & 1) * LDR * RCH;
+                        for (int e = tid; e < KB * RCH; e += CT) {
+                            const int k = e % KB, jj = e / KB;
+                            Rc[k + LDR * jj] = ldcg(scrR + k + (size_t)KB * (ch * RCH + jj));
+                        }
+                        __syncthreads();  // chunk ch staged; chunk ch-1's readers finished before they staged ch (two buffers)
+                        for (int g = tpart; g < RCH / KB; g += tsplit) {  // groups of four 8-column tiles: four independent DMMA chains
+                            const int col0 = ch * RCH + KB * g;
+                            if (col0 == k0) continue;  // the pivot columns become T below
+                            double *cp = s.S + (8 * rb + fr) + LD * (col0 + 2 * fk);
+                            double c0[4], c1[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                c0[t] = pivot_rb ? 0.0 : cp[LD * 8 * t];
+                                c1[t] = pivot_rb ? 0.0 : cp[LD * (8 * t + 1)];
+                            }
+                            const double *bp = Rc + fk + LDR * (KB * g + fr);
+#pragma unroll
+                            for (int ks = 0; ks < KB / 4; ++ks) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const double bf = bp[4 * ks + LDR * 8 * t];
+                                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                                 : "+d"(c0[t]), "+d"(c1[t])
+                                                 : "d"(af[ks]), "d"(bf));
+                                }
+                            }
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                cp[LD * 8 * t] = c0[t];
+                                cp[LD * (8 * t + 1)] = c1[t];
+                            }
+                        }
+                    }
+                }
+                TCK(4)
+                // pivot columns of the slice <- T (nobody reads S[own, K] any more: T was formed before the last barrier)
+                for (int e = tid; e < RS * KB; e += CT) {
+                    const int r = e % RS, c = e / RS;
+                    s.S[r + LD * (k0 + c)] = Tm[r + LDT * c];
+                }
+                __syncthreads();
+            }
+            TCK(5)
+            // the instance's sparse data comes back into the aliased region
+            __syncthreads();
+            stage_sparse();
+            __syncthreads();
+            TCK(6)
+            return ok;
+        };
+
+#ifdef SQPB200_CLUSTER_TIMING
+        long long tq0 = clock64();
+#endif
+        bool ok = factorize();
+#ifdef SQPB200_CLUSTER_TIMING
+        long long tq1 = clock64();
+#endif
+        status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+
+        long long executed = 0;
+        if ((p.mode & MODE_SOLVE) && ok) {
+            int iter;
+            for (iter = 1; iter <= st.max_iter; ++iter) {
+#ifdef SQPB200_CLUSTER_TIMING
+                tlast = clock64();
+#endif
+                // w = rho .* z - y for the owned rows -> every CTA's copy
+                if (has_row) {
+                    const double wv = rhor * zr - yr;
+#pragma unroll
+                    for (int r = 0; r < CS; ++r) peer_sw[r][my_row] = wv;
+                }
+                cluster.sync();
+                TCK(8)
+                // b = sigma x - q + A^T w (every CTA, one column per thread; padded entries stay 0)
+                for (int j = tid; j < np; j += CT) s.sb[j] = j < n ? fma(sigma, s.sx[j], packed_dot(cpack, couter[j], couter[j + 1], vals, s.sw) - s.sq[j]) : 0.0;
+                __syncthreads();
+                TCK(9)
+                // x~ (own slice) = -(S slice) b: two rows per thread, the columns split over CT / (RS/2) thread groups
+                {
+                    const int RP = RS / 2, CGN = CT / RP, CPG = np / CGN;
+                    const int rp = tid % RP, cgp = tid / RP;
+                    const double *col = s.S + 2 * rp + (size_t)LD * (cgp * CPG);
+                    const double *bv = s.sb + cgp * CPG;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+                    for (int j = 0; j < CPG; j += 2) {
+                        const double2 s0 = *reinterpret_cast<const double2 *>(col + (size_t)LD * j);
+                        const double2 s1 = *reinterpret_cast<const double2 *>(col + (size_t)LD * (j + 1));
+                        const double2 b2 = *reinterpret_cast<const double2 *>(bv + j);
+                        a0 = fma(s0.x, b2.x, a0);
+                        a1 = fma(s0.y, b2.x, a1);
+                        a2 = fma(s1.x, b2.y, a2);
+                        a3 = fma(s1.y, b2.y, a3);
+                    }
+                    *reinterpret_cast<double2 *>(s.part + cgp * RS + 2 * rp) = make_double2(a0 + a2, a1 + a3);
+                    __syncthreads();
+                    if (tid < RS) {
+                        double acc = 0.0;
+                        for (int g = 0; g < CGN; ++g) acc += s.part[g * RS + tid];
+                        const double xt = -acc;
+#pragma unroll
+                        for (int r = 0; r < CS; ++r) peer_sxt[r][RS * rank + tid] = xt;
+                    }
+                }
+                TCK(10)
+                cluster.sync();
+                TCK(11)
+                // x = alpha x~ + (1 - alpha) x (every CTA keeps all of x); z~ = A x~ and the z, y updates for the owned rows
+                for (int j = tid; j < np; j += CT) s.sx[j] = alpha * s.sxt[j] + (1.0 - alpha) * s.sx[j];
+                if (has_row) {
+                    const double zt = packed_dot(rpack, router[my_row], router[my_row + 1], vals, s.sxt);
+                    const double zh = alpha * zt + (1.0 - alpha) * zr;
+                    const double zn = box_project(zh + rinv * yr, lo, up);
+                    yr = yr + rhor * (zh - zn);
+                    zr = zn;
+                }
+
+                TCK(12)
+                const bool chk = st.check_termination != 0 && iter % st.check_termination == 0;
+                const bool adapt = st.adaptive_rho && st.adaptive_rho_interval > 0 && iter % st.adaptive_rho_interval == 0;
+                if (chk || adapt) {
+                    __syncthreads();  // s.sx complete
+                    double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
+                    if (has_row) {
+                        const double ax = packed_dot(rpack, router[my_row], router[my_row + 1], vals, s.sx);
+                        mx[0] = fabs(ax);
+                        mx[1] = fabs(zr);
+                        mx[5] = fabs(ax - zr);
+#pragma unroll
+                        for (int r = 0; r < CS; ++r) peer_sw[r][my_row] = yr;  // all-gather y (w is rebuilt next iteration)
+                    }
+                    // P x for the rows of the own slice: partial sums over CT / RS column groups
+                    {
+                        const int KG = CT / RS, r = tid % RS, kg = tid / RS, j = RS * rank + r;
+                        double acc = 0.0;
+                        if (j < n)
+                            for (int k = kg; k < n; k += KG) acc = fma(P[j + (size_t)n * k], s.sx[k], acc);
+                        s.part[kg * RS + r] = acc;
+                    }
+                    cluster.sync();
+                    if (tid < RS) {
+                        const int KG = CT / RS, j = RS * rank + tid;
+                        if (j < n) {
+                            double px = 0.0;
+                            for (int g = 0; g < KG; ++g) px += s.part[g * RS + tid];
+                            const double aty = packed_dot(cpack, couter[j], couter[j + 1], vals, s.sw);
+                            const double qv = s.sq[j];
+                            mx[2] = fabs(px);
+                            mx[3] = fabs(aty);
+                            mx[4] = fabs(qv);
+                            mx[6] = fabs(px + qv + aty);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const double v = warp_max(mx[k]);
+                        if (lane == 0) s_wred[k][warp] = v;
+                    }
+                    __syncthreads();
+                    if (tid < 7) {
+                        double v = s_wred[tid][0];
+                        for (int w2 = 1; w2 < CNW; ++w2) v = s_wred[tid][w2] > v ? s_wred[tid][w2] : v;
+#pragma unroll
+                        for (int r = 0; r < CS; ++r) peer_red[r][rank * 8 + tid] = v;
+                    }
+                    cluster.sync();
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        double v = s.red[k];
+#pragma unroll
+                        for (int r = 1; r < CS; ++r) v = s.red[r * 8 + k] > v ? s.red[r * 8 + k] : v;
+                        mx[k] = v;
+                    }
+                    const double sc_p = fmax(mx[0], mx[1]);
+                    const double sc_d = fmax(mx[2], fmax(mx[3], mx[4]));
+                    res_prim = mx[5];
+                    res_dual = mx[6];
+                    if (chk && res_prim <= st.eps_abs + st.eps_rel * sc_p && res_dual <= st.eps_abs + st.eps_rel * sc_d) {
+                        status = SQPB200_SOLVED;  // termination_criteria, qp.cpp:363-371
+                        break;
+                    }
+                    if (adapt) {  // qp.cpp:125-144
+                        const double new_rho = rho_estimate_clamped(rho, res_prim, res_dual, sc_p, sc_d);
+                        rho_est = new_rho;
+                        if (new_rho < rho / st.adaptive_rho_tolerance || new_rho > rho * st.adaptive_rho_tolerance) {
+                            rho = new_rho;
+                            rho_updates += 1;
+                            rhor = rho_of(typ, rho);
+                            rinv = 1.0 / rhor;
+                            cluster.sync();  // every CTA is done with s.sw (y) before it is reused for the rho vector
+                            if (!factorize()) {
+                                status = SQPB200_NUMERICAL_ISSUES;  // qp.cpp:139-142
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+            executed = iter <= st.max_iter ? iter : st.max_iter;
+            if (iter > st.max_iter) status = SQPB200_MAX_ITER_EXCEEDED;  // qp.cpp:147-149
+            iter_out = iter;                                            // qp.cpp:150
+        }
+
+#ifdef SQPB200_CLUSTER_TIMING
+        if (tid == 0 && blockIdx.x < CS) { printf("qp %d rank %d: factor %lld cyc, solve %lld cyc, iters %d, rho_updates %d | formH %lld owner %lld sync %lld T %lld dmma %lld tail %lld restage %lld | it: sync1 %lld coldot %lld matvec %lld sync2 %lld rowdot %lld | own: publishR %lld sweep %lld\n", local, rank, tq1 - tq0, clock64() - tq1, iter_out, rho_updates, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[8], tph[9], tph[10], tph[11], tph[12], tph[13], tph[14]); for (int i_ = 0; i_ < 16; ++i_) tph[i_] = 0; }
+#endif
+        __syncthreads();
+        if (tid < RS && RS * rank + tid < n) p.x[b * n + RS * rank + tid] = s.sx[RS * rank + tid];
+        if (has_row) {
+            p.z[b * m + my_row] = zr;
+            p.y[b * m + my_row] = yr;
+        }
+        if (rank == 0 && tid == 0) {
+            p.status[b] = status;
+            p.iter[b] = iter_out;
+            p.rho_updates[b] = rho_updates;
+            p.rho_estimate[b] = rho_est;
+            p.res_prim[b] = res_prim;
+            p.res_dual[b] = res_dual;
+            p.rho[b] = rho;
+            if (executed) atomicAdd(p.total_iters, (unsigned long long)executed);
+        }
+        cluster.sync();  // nobody is still reading this QP's exchanged vectors (or s_qp) when the next one starts
+    }
+    cluster.sync();  // no CTA exits while a peer may still touch its shared memory
+}
+
+static cudaError_t cluster_config(size_t smem, int *max_clusters) {
+    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * 64, 1, 1);
+    cfg.blockDim = dim3(CT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(max_clusters, qp_cluster_kernel, &cfg);
+}
+
+int cluster_max_clusters(int n, int m, int nnz) {
+    int mc = 0;
+    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz);
+    if (cluster_config(smem, &mc) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return mc;
+}
+size_t cluster_scratch_bytes(int clusters) { return sizeof(double) * cluster_scratch_doubles() * (size_t)clusters; }
+
+cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len) {
+    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(p.n), p.m, p.sp.nnz);
+    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (clusters > p.count) clusters = p.count;
+    if (clusters < 1) return cudaErrorLaunchOutOfResources;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * clusters, 1, 1);
+    cfg.blockDim = dim3(CT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (name) snprintf(name, name_len, "cluster<%d>/sparse x%d", CS, clusters);
+    return cudaLaunchKernelEx(&cfg, qp_cluster_kernel, p, scratch);
+}
+
+}  // namespace sqpb200

@@ -47,6 +47,7 @@ struct SparseA {
     const int *row_outer, *row_inner, *row_perm;  // CSR view: row_outer[m+1], row_inner[nnz] = column indices
     const int *col_outer, *col_inner, *col_perm;  // CSC view: col_outer[n+1], col_inner[nnz] = row indices
     const double *vals;                           // [B][nnz]
+    const unsigned *col_pack, *row_pack;          // per stored entry of the CSC / CSR view: inner index | (position in vals << 10)
     int nnz;
 };
 
@@ -135,6 +136,11 @@ bool block_supported(int n, int m, size_t smem_optin);
 bool block_sparse_supported(int n, int m, int nnz, size_t smem_optin);
 size_t block_fact_doubles(int n);
 cudaError_t launch_block(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, char *name, size_t name_len);
+// cluster kernel for sparse A, 64 < n <= 256 (qp_cluster.cu)
+bool cluster_sparse_supported(int n, int m, int nnz, size_t smem_optin);
+int cluster_max_clusters(int n, int m, int nnz);
+size_t cluster_scratch_bytes(int clusters);
+cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len);
 cudaError_t launch_densify(const double *vals, const int *outer, const int *inner, int nnz, int m, int n, int csr, int count,
                            double *dst, cudaStream_t stream);
 

@@ -654,3 +654,55 @@ def test_against_committed_golden_outputs(api, ctx, kernel):
         ref = dict(status=np.array(c["status"]), iter=np.array(c["iter"]), rho_updates=np.array(c["rho_updates"]),
                    x=np.array(c["x"]), y=np.array(c["y"]))
         assert_parity(out, ref, what="golden " + c["name"])
+
+
+@pytest.mark.parametrize("settings_name", ["S1", "S2"])
+@pytest.mark.parametrize("n,m,batch,density,layout", [(100, 150, 6, 0.08, "csr"), (128, 257, 5, 0.05, "csc"),
+                                                      (200, 701, 5, 0.02, "csr"), (256, 512, 5, 0.03, "csc")])
+def test_cluster_kernel_parity(api, ctx, oracle, n, m, batch, density, layout, settings_name):
+    """The thread-block-cluster kernel (sparse A, 64 < n <= 256: H^-1 distributed over the shared memory of 4 CTAs) against the
+    oracle on the densified problem: ragged n (padded to 128 / 256), m not divisible by the cluster size, both layouts, the
+    reference defaults and the SQP regime, and one NaN instance (NUMERICAL_ISSUES, iter untouched)."""
+    d, vals, outer, inner = _sparse_batch(batch, n, m, density, 16000 + n, layout)
+    d["P"][1, 0] = np.nan  # instance 1: NaN pivot -> Eigen::LDLT::info() != Success -> NUMERICAL_ISSUES (qp.cpp:39-43)
+    s = api.default_settings(max_iter=300) if settings_name == "S1" else api.default_settings(alpha=1.6, adaptive_rho=1, max_iter=300)
+    ctx.set_option(api.OPT_KERNEL, api.KERNEL_CLUSTER)
+    b = api.QPBatch(ctx, batch, n, m)
+    b.settings = s
+    b.setup_solve_sparse(d["P"], d["q"], vals, outer, inner, d["l"], d["u"],
+                         layout=api.SPARSE_CSC if layout == "csc" else api.SPARSE_CSR)
+    got = b.get()
+    assert ctx.last_kernel.startswith("cluster"), ctx.last_kernel
+    assert got["status"][1] == api.NUMERICAL_ISSUES
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    keep = np.array([i for i in range(batch) if i != 1])
+    sub = lambda o: {k: np.asarray(v)[keep] for k, v in o.items() if isinstance(v, np.ndarray) and v.shape[:1] == (batch,)}
+    assert ref["status"][1] == api.NUMERICAL_ISSUES
+    assert_parity(sub(got), sub(ref), what="cluster kernel %s n=%d m=%d %s" % (layout, n, m, settings_name))
+    # second call on the same batch object: rho_updates is cumulative (qp.cpp:313), everything else identical
+    b.setup_solve_sparse(d["P"], d["q"], vals, outer, inner, d["l"], d["u"],
+                         layout=api.SPARSE_CSC if layout == "csc" else api.SPARSE_CSR)
+    again = b.get()
+    np.testing.assert_array_equal(again["x"][keep], got["x"][keep])
+    np.testing.assert_array_equal(again["iter"][keep], got["iter"][keep])
+    b.close()
+
+
+def test_cluster_kernel_many_waves_matches_blocked_kernel(api, ctx):
+    """More QPs than resident clusters (the atomic work queue hands every cluster several QPs) and agreement with the blocked
+    kernel on the same sparse inputs (same algorithm, different factorisation order: status identical, x to 1e-6)."""
+    n, m, batch = 160, 300, 150
+    d, vals, outer, inner = _sparse_batch(batch, n, m, 0.04, 17000, "csr")
+    s = api.default_settings(alpha=1.6, adaptive_rho=1, max_iter=200)
+    outs = {}
+    for name, opt in (("cluster", api.KERNEL_CLUSTER), ("block", api.KERNEL_BLOCK)):
+        ctx.set_option(api.OPT_KERNEL, opt)
+        b = api.QPBatch(ctx, batch, n, m)
+        b.settings = s
+        b.setup_solve_sparse(d["P"], d["q"], vals, outer, inner, d["l"], d["u"], layout=api.SPARSE_CSR)
+        outs[name] = b.get()
+        assert ctx.last_kernel.startswith(name), ctx.last_kernel
+        b.close()
+    np.testing.assert_array_equal(outs["cluster"]["status"], outs["block"]["status"])
+    np.testing.assert_array_equal(outs["cluster"]["iter"], outs["block"]["iter"])
+    np.testing.assert_allclose(outs["cluster"]["x"], outs["block"]["x"], rtol=1e-6, atol=1e-9)
