@@ -84,6 +84,18 @@ bool cluster_sparse_supported(int n, int m, int nnz, size_t smem_optin) {
 }
 
 __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
+// branch-free reciprocal (MUFU.RCP64H seed + two Newton steps; ~1 ulp): keeps the pivot chain of the sweep free of the
+// slow-path branch of an IEEE division so the compiler can interleave it with the row update
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
 
 // sparse dot product of one compressed row / column (entries [p0, p1) of a packed view: inner index | value position << 10)
 // with a shared-memory vector; everything it touches is in shared memory
@@ -129,8 +141,10 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
     const int RM = (m + CS - 1) / CS;
     const int row_lo = rank * RM;
     const int rows_own = max(0, min(m, row_lo + RM) - row_lo);
-    const bool has_row = tid < rows_own;
-    const int my_row = row_lo + tid;
+    const int TPR = (2 * RM <= CT) ? 2 : 1;  // threads per owned row (they split its stored entries)
+    const bool has_row = tid / TPR < rows_own;
+    const int my_row = row_lo + tid / TPR, row_half = tid % TPR;
+    const bool row_writer = has_row && row_half == 0;
     // peers' copies of the exchanged vectors
     double *peer_sw[CS], *peer_sxt[CS], *peer_red[CS];
     int *peer_qp[CS];
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         // values of this instance + the batch-shared pattern -> shared memory (the region is reused by the sweep: restaged after it)
         auto stage_sparse = [&]() {
             for (int e = tid; e < nnz; e += CT) {
-                vals[e] = gvals[e];
+                vals[e] = __ldg(gvals + e);
                 cpack[e] = __ldg(sp.col_pack + e);
                 rpack[e] = __ldg(sp.row_pack + e);
             }
@@ -176,8 +190,20 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             for (int i = tid; i <= m; i += CT) router[i] = __ldg(sp.row_outer + i);
         };
         stage_sparse();
+        // (A v)_i for the owned row of this thread: the TPR threads of a row split its entries and add the halves
+        auto own_rowdot = [&](const double *vec) -> double {
+            double acc = 0.0;
+            if (has_row) {
+                const int p0 = router[my_row], p1 = router[my_row + 1];
+                const int pm = TPR == 2 ? p0 + (((p1 - p0 + 1) / 2 + 3) & ~3) : p1;  // first half: a multiple of 4 entries
+                const int lo_ = row_half == 0 ? p0 : min(pm, p1), hi_ = row_half == 0 ? min(pm, p1) : p1;
+                acc = packed_dot(rpack, lo_, hi_, vals, vec);
+            }
+            if (TPR == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            return acc;
+        };
         for (int j = tid; j < np; j += CT) {
-            s.sq[j] = j < n ? q[j] : 0.0;
+            s.sq[j] = j < n ? __ldg(q + j) : 0.0;
             s.sx[j] = 0.0;
             s.sxt[j] = 0.0;
         }
@@ -188,7 +214,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             lo = l[my_row];
             up = u[my_row];
             typ = classify(lo, up);
-            p.ctype[b * m + my_row] = (signed char)typ;
+            if (row_half == 0) p.ctype[b * m + my_row] = (signed char)typ;
             rhor = rho_of(typ, rho);
             rinv = 1.0 / rhor;
         }
@@ -201,31 +227,53 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             tlast = clock64();
 #endif
             // rho of every row (form H touches all rows of a column): recomputed from the bounds, as classified at setup
-            for (int i = tid; i < m; i += CT) s.sw[i] = rho_of(classify(l[i], u[i]), rho);
+            for (int i = tid; i < m; i += CT) s.sw[i] = rho_of(classify(__ldg(l + i), __ldg(u + i)), rho);
             // P_lowsym + sigma I (LDLT<Lower> reads the lower triangle only); padded variables get a unit diagonal
+            // (two passes so that both triangles are read along P's columns: lanes over rows for j <= i, lanes over columns above)
+#pragma unroll 8
             for (int e = tid; e < RS * np; e += CT) {
                 const int r = e % RS, j = e / RS, i = RS * rank + r;
-                double v;
-                if (i < n && j < n) v = (i >= j ? P[i + (size_t)n * j] : P[j + (size_t)n * i]) + (i == j ? sigma : 0.0);
-                else v = (i == j) ? 1.0 : 0.0;
-                s.S[r + LD * j] = v;
+                if (i < n && j < n) {
+                    if (i >= j) s.S[r + LD * j] = __ldg(P + i + (size_t)n * j) + (i == j ? sigma : 0.0);
+                } else {
+                    s.S[r + LD * j] = (i == j) ? 1.0 : 0.0;
+                }
+            }
+#pragma unroll 8
+            for (int e = tid; e < RS * np; e += CT) {
+                const int j = e % np, r = e / np, i = RS * rank + r;
+                if (i < n && j < n && j > i) s.S[r + LD * j] = __ldg(P + j + (size_t)n * i);
             }
             __syncthreads();
             // + A^T diag(rho) A: row i of H gathers, for every stored (k, i), rho_k A_ki times row k of A. One warp per row,
             // the entries of row k over the lanes (distinct columns: no conflicts, fixed order)
+            // (the stored entries of column i are fetched by the lanes in one batch and handed round by shuffles, so the per-entry
+            // chain is only pattern -> value/accumulator -> store)
             for (int r = warp; r < RS; r += CNW) {
                 const int i = RS * rank + r;
                 if (i >= n) continue;
-                for (int pc = couter[i]; pc < couter[i + 1]; ++pc) {
-                    const unsigned ec = cpack[pc];
-                    const int k = (int)(ec & 1023u);
-                    const double f = s.sw[k] * vals[ec >> 10];
-                    for (int pr = router[k] + lane; pr < router[k + 1]; pr += 32) {
-                        const unsigned er = rpack[pr];
-                        double *dst = s.S + r + LD * (int)(er & 1023u);
-                        *dst = fma(f, vals[er >> 10], *dst);
+                const int c0 = couter[i], c1 = couter[i + 1];
+                for (int base = c0; base < c1; base += 32) {
+                    const int cnt = min(32, c1 - base);
+                    double f_l = 0.0;
+                    int r0_l = 0, r1_l = 0;
+                    if (lane < cnt) {
+                        const unsigned ec = cpack[base + lane];
+                        const int k = (int)(ec & 1023u);
+                        f_l = s.sw[k] * vals[ec >> 10];
+                        r0_l = router[k];
+                        r1_l = router[k + 1];
                     }
-                    __syncwarp();
+                    for (int t = 0; t < cnt; ++t) {
+                        const double f = __shfl_sync(0xffffffffu, f_l, t);
+                        const int r0 = __shfl_sync(0xffffffffu, r0_l, t), r1 = __shfl_sync(0xffffffffu, r1_l, t);
+                        for (int pr = r0 + lane; pr < r1; pr += 32) {
+                            const unsigned er = rpack[pr];
+                            double *dst = s.S + r + LD * (int)(er & 1023u);
+                            *dst = fma(f, vals[er >> 10], *dst);
+                        }
+                        __syncwarp();
+                    }
                 }
             }
             __syncthreads();  // the sweep buffers alias vals from here on
@@ -252,36 +300,59 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                         E0[i * LDE + j] = s.S[(k0l + i) + LD * (k0 + j)];
                     }
                     __syncthreads();
-                    bool bad = false;
-                    const int ei = tid >> 3, ej0 = (tid & 7) * 4;
-                    for (int pv = 0; pv < KB; ++pv) {
-                        const double *src = (pv & 1) ? E1 : E0;
-                        double *dst = (pv & 1) ? E0 : E1;
-                        const double d = src[pv * LDE + pv];
-                        if (!(fabs(d) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
-                            bad = true;
-                            break;
-                        }
-                        const double inv_d = 1.0 / d;
-                        const double ci = src[ei * LDE + pv], ti = ci * inv_d;
-                        double sv[4], cj[4];
+                    // Symmetric sweep of the 32 x 32 pivot block by ONE warp, a row per lane in registers (the 32 pivots are a
+                    // serial chain: a CTA-wide version pays a barrier per pivot). Per pivot the lanes exchange column p through
+                    // shared memory; the reciprocal of the NEXT pivot is formed by every lane from the exchanged values (bit-identical
+                    // to the owner lane's update) so the division overlaps the row update instead of heading the next step.
+                    __shared__ int s_bad;
+                    if (warp == 0) {
+                        double row[KB];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            sv[t] = src[ei * LDE + ej0 + t];
-                            cj[t] = src[pv * LDE + ej0 + t];
+                        for (int j = 0; j < KB; ++j) row[j] = E0[lane * LDE + j];
+                        double *cv = E1;
+                        bool bad = false;
+                        double inv_d = 0.0;
+                        {
+                            const double d = __shfl_sync(0xffffffffu, row[0], 0);
+                            if (!(fabs(d) > 0.0)) bad = true;  // zero or NaN pivot: Eigen::LDLT::info() != Success
+                            else inv_d = fast_rcp(d);
                         }
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int ej = ej0 + t;
-                            double v = fma(-ti, cj[t], sv[t]);
-                            v = (ej == pv) ? ti : v;
-                            const double rowv = (ej == pv) ? -inv_d : cj[t] * inv_d;
-                            dst[ei * LDE + ej] = (ei == pv) ? rowv : v;
+                        for (int pv = 0; pv < KB; ++pv) {
+                            if (bad) break;
+                            double *cvp = cv + (pv & 1) * (KB + 2);
+                            cvp[lane] = row[pv];
+                            if (pv + 1 < KB && lane == pv + 1) cvp[KB] = row[pv + 1];  // diagonal of the next pivot, before this update
+                            __syncwarp();
+                            const double ti = row[pv] * inv_d;
+                            const bool piv = lane == pv;
+                            const double mult = piv ? inv_d : -ti;
+                            double d_next = 1.0, inv_next = 0.0;
+                            if (pv + 1 < KB) {
+                                const double cn = cvp[pv + 1];
+                                d_next = fma(-(cn * inv_d), cn, cvp[KB]);
+                                inv_next = fast_rcp(d_next);
+                            }
+#pragma unroll
+                            for (int j = 0; j < KB; j += 2) {
+                                const double2 c2 = *reinterpret_cast<const double2 *>(cvp + j);
+                                const double b0 = piv ? 0.0 : row[j], b1 = piv ? 0.0 : row[j + 1];
+                                row[j] = fma(mult, c2.x, b0);
+                                row[j + 1] = fma(mult, c2.y, b1);
+                            }
+                            row[pv] = piv ? -inv_d : ti;
+                            if (pv + 1 < KB) {
+                                if (!(fabs(d_next) > 0.0)) bad = true;
+                                inv_d = inv_next;
+                            }
                         }
-                        __syncthreads();
+#pragma unroll
+                        for (int j = 0; j < KB; ++j) E0[lane * LDE + j] = row[j];  // -(E^-1)
+                        if (lane == 0) s_bad = bad ? 1 : 0;
                     }
+                    __syncthreads();
+                    const bool bad = s_bad != 0;
                     TCK(14)
-                    // KB is even: the result (-E^-1) is back in E0
                     for (int e = tid; e < KB * KB; e += CT) scrE[e] = bad ? 0.0 : -E0[(e % KB) * LDE + (e / KB)];
                     if (tid == 0) scrF[0] = bad ? 1.0 : 0.0;
                     __threadfence();
@@ -293,8 +364,20 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                     ok = false;
                     break;
                 }
+                double rpre[KB * RCH / CT];  // this thread's share of the next chunk of pivot rows (prefetched from L2)
+#pragma unroll
+                for (int t = 0; t < KB * RCH / CT; ++t) rpre[t] = ldcg(scrR + tid + CT * t);
                 // E^-1 -> Eb (every CTA)
-                for (int e = tid; e < KB * KB; e += CT) Eb[(e % KB) * LDE + (e / KB)] = ldcg(scrE + e);
+                {
+                    double ev[KB * KB / CT];
+#pragma unroll
+                    for (int t = 0; t < KB * KB / CT; ++t) ev[t] = ldcg(scrE + tid + CT * t);
+#pragma unroll
+                    for (int t = 0; t < KB * KB / CT; ++t) {
+                        const int e = tid + CT * t;
+                        Eb[(e % KB) * LDE + (e / KB)] = ev[t];
+                    }
+                }
                 __syncthreads();
                 // T = S[own rows, K] E^-1 on the tensor cores (8-row block x four 8-column tiles per warp, K = 32); the owner's
                 // pivot rows carry -E^-1 instead (their update then yields E^-1 S[K, :])
@@ -337,9 +420,14 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                     const int nch = np / RCH;
                     for (int ch = 0; ch < nch; ++ch) {
                         double *Rc = Rb + (size_t)(ch & 1) * LDR * RCH;
-                        for (int e = tid; e < KB * RCH; e += CT) {
-                            const int k = e % KB, jj = e / KB;
-                            Rc[k + LDR * jj] = ldcg(scrR + k + (size_t)KB * (ch * RCH + jj));
+#pragma unroll
+                        for (int t = 0; t < KB * RCH / CT; ++t) {
+                            const int e = tid + CT * t;
+                            Rc[(e % KB) + LDR * (e / KB)] = rpre[t];
+                        }
+                        if (ch + 1 < nch) {  // the next chunk's L2 loads are in flight while this one is consumed
+#pragma unroll
+                            for (int t = 0; t < KB * RCH / CT; ++t) rpre[t] = ldcg(scrR + (size_t)KB * RCH * (ch + 1) + tid + CT * t);
                         }
                         __syncthreads();  // chunk ch staged; chunk ch-1's readers finished before they staged ch (two buffers)
                         for (int g = tpart; g < RCH / KB; g += tsplit) {  // groups of four 8-column tiles: four independent DMMA chains
@@ -391,7 +479,26 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
 #ifdef SQPB200_CLUSTER_TIMING
         long long tq0 = clock64();
 #endif
+        // The mat-vec operands of this thread (2 rows x CPG columns of the slice) are copied into registers after every
+        // factorisation: the iteration then reads only b from shared memory.
+        const int RP = RS / 2, CGN = CT / RP, CPG = np / CGN;  // CPG = 32 (np = 256) or 8 (np = 128)
+        const int rp = tid % RP, cgp = tid / RP;
+        double sreg[64];
+        auto load_slice = [&]() {
+            const double *col = s.S + 2 * rp + (size_t)LD * (cgp * CPG);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < CPG) {
+                    const double2 v = *reinterpret_cast<const double2 *>(col + (size_t)LD * j);
+                    sreg[2 * j] = v.x;
+                    sreg[2 * j + 1] = v.y;
+                } else {
+                    sreg[2 * j] = sreg[2 * j + 1] = 0.0;
+                }
+            }
+        };
         bool ok = factorize();
+        load_slice();
 #ifdef SQPB200_CLUSTER_TIMING
         long long tq1 = clock64();
 #endif
@@ -405,7 +512,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 tlast = clock64();
 #endif
                 // w = rho .* z - y for the owned rows -> every CTA's copy
-                if (has_row) {
+                if (row_writer) {
                     const double wv = rhor * zr - yr;
 #pragma unroll
                     for (int r = 0; r < CS; ++r) peer_sw[r][my_row] = wv;
@@ -418,20 +525,17 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 TCK(9)
                 // x~ (own slice) = -(S slice) b: two rows per thread, the columns split over CT / (RS/2) thread groups
                 {
-                    const int RP = RS / 2, CGN = CT / RP, CPG = np / CGN;
-                    const int rp = tid % RP, cgp = tid / RP;
-                    const double *col = s.S + 2 * rp + (size_t)LD * (cgp * CPG);
                     const double *bv = s.sb + cgp * CPG;
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 4
-                    for (int j = 0; j < CPG; j += 2) {
-                        const double2 s0 = *reinterpret_cast<const double2 *>(col + (size_t)LD * j);
-                        const double2 s1 = *reinterpret_cast<const double2 *>(col + (size_t)LD * (j + 1));
-                        const double2 b2 = *reinterpret_cast<const double2 *>(bv + j);
-                        a0 = fma(s0.x, b2.x, a0);
-                        a1 = fma(s0.y, b2.x, a1);
-                        a2 = fma(s1.x, b2.y, a2);
-                        a3 = fma(s1.y, b2.y, a3);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        if (j < CPG) {
+                            const double2 b2 = *reinterpret_cast<const double2 *>(bv + j);
+                            a0 = fma(sreg[2 * j], b2.x, a0);
+                            a1 = fma(sreg[2 * j + 1], b2.x, a1);
+                            a2 = fma(sreg[2 * j + 2], b2.y, a2);
+                            a3 = fma(sreg[2 * j + 3], b2.y, a3);
+                        }
                     }
                     *reinterpret_cast<double2 *>(s.part + cgp * RS + 2 * rp) = make_double2(a0 + a2, a1 + a3);
                     __syncthreads();
@@ -448,8 +552,8 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 TCK(11)
                 // x = alpha x~ + (1 - alpha) x (every CTA keeps all of x); z~ = A x~ and the z, y updates for the owned rows
                 for (int j = tid; j < np; j += CT) s.sx[j] = alpha * s.sxt[j] + (1.0 - alpha) * s.sx[j];
+                const double zt = own_rowdot(s.sxt);
                 if (has_row) {
-                    const double zt = packed_dot(rpack, router[my_row], router[my_row + 1], vals, s.sxt);
                     const double zh = alpha * zt + (1.0 - alpha) * zr;
                     const double zn = box_project(zh + rinv * yr, lo, up);
                     yr = yr + rhor * (zh - zn);
@@ -462,20 +566,32 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 if (chk || adapt) {
                     __syncthreads();  // s.sx complete
                     double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
+                    const double ax = own_rowdot(s.sx);
                     if (has_row) {
-                        const double ax = packed_dot(rpack, router[my_row], router[my_row + 1], vals, s.sx);
                         mx[0] = fabs(ax);
                         mx[1] = fabs(zr);
                         mx[5] = fabs(ax - zr);
 #pragma unroll
-                        for (int r = 0; r < CS; ++r) peer_sw[r][my_row] = yr;  // all-gather y (w is rebuilt next iteration)
+                        if (row_half == 0)
+                            for (int r = 0; r < CS; ++r) peer_sw[r][my_row] = yr;  // all-gather y (w is rebuilt next iteration)
                     }
                     // P x for the rows of the own slice: partial sums over CT / RS column groups
                     {
                         const int KG = CT / RS, r = tid % RS, kg = tid / RS, j = RS * rank + r;
                         double acc = 0.0;
-                        if (j < n)
-                            for (int k = kg; k < n; k += KG) acc = fma(P[j + (size_t)n * k], s.sx[k], acc);
+                        if (j < n) {
+                            double a4[4] = {0.0, 0.0, 0.0, 0.0};
+                            int k = kg;
+                            for (; k + 7 * KG < n; k += 8 * KG) {  // eight independent L2 loads in flight
+                                double pv[8];
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) pv[t] = __ldg(P + j + (size_t)n * (k + t * KG));
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) a4[t & 3] = fma(pv[t], s.sx[k + t * KG], a4[t & 3]);
+                            }
+                            for (; k < n; k += KG) a4[0] = fma(P[j + (size_t)n * k], s.sx[k], a4[0]);
+                            acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+                        }
                         s.part[kg * RS + r] = acc;
                     }
                     cluster.sync();
@@ -533,6 +649,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                                 status = SQPB200_NUMERICAL_ISSUES;  // qp.cpp:139-142
                                 break;
                             }
+                            load_slice();
                         }
                     }
                 }
@@ -547,7 +664,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
 #endif
         __syncthreads();
         if (tid < RS && RS * rank + tid < n) p.x[b * n + RS * rank + tid] = s.sx[RS * rank + tid];
-        if (has_row) {
+        if (row_writer) {
             p.z[b * m + my_row] = zr;
             p.y[b * m + my_row] = yr;
         }
