@@ -343,9 +343,9 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     const bool want_tile = !sp && c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
     // sparse A: a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
     int clusters = 0;
-    if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && cluster_sparse_supported(b->n, b->m, sp->nnz, optin) &&
+    if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && cluster_sparse_supported(b->n, b->m, sp->nnz, sp->col_slice_cap, optin) &&
         mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE) && !ready)
-        clusters = cluster_max_clusters(b->n, b->m, sp->nnz);
+        clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap);
     if (c->opt_kernel == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
     const bool want_cluster = clusters >= 1;
     const bool want_block = !want_cluster && (sp || (!want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin)));
@@ -560,9 +560,22 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
 
     // Shapes the register-tiled kernel covers keep A in registers anyway: densify. Larger ones run the blocked kernel with the
     // values of one instance staged in shared memory and both compressed views of the pattern.
+    // cluster kernel: the most stored entries in the n/4-column slice one CTA owns (sizes its shared-memory copy of them)
+    int col_slice_cap = 0;
+    if (b->n > 64 && b->n <= 256) {
+        std::vector<int> colcount(b->n, 0);
+        if (csr) for (int e = 0; e < nnz; ++e) colcount[h_inner[e]]++;
+        else for (int j = 0; j < b->n; ++j) colcount[j] = h_outer[j + 1] - h_outer[j];
+        const int rs = cluster_rows_per_cta(b->n);
+        for (int j0 = 0; j0 < b->n; j0 += rs) {
+            int cnt = 0;
+            for (int j = j0; j < j0 + rs && j < b->n; ++j) cnt += colcount[j];
+            if (cnt > col_slice_cap) col_slice_cap = cnt;
+        }
+    }
     const bool sparse_kernel = (c->opt_kernel == 0 || c->opt_kernel == 3 || c->opt_kernel == 4) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
                                m > 0 && (block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin) ||
-                                         cluster_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin));
+                                         cluster_sparse_supported(b->n, b->m, nnz, col_slice_cap, c->prop.sharedMemPerBlockOptin));
     if (!sparse_kernel) {
         cudaError_t e = launch_densify(d_vals, d_outer, d_inner, nnz, b->m, b->n, csr, count, b->dA, stream);
         if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "densify launch", e);
@@ -599,6 +612,7 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         if (nnz > 0) CK(c, cudaMemcpyAsync(b->sp_pack, pack.data(), sizeof(unsigned) * 2 * nnz, cudaMemcpyHostToDevice, stream));
         CK(c, cudaStreamSynchronize(stream));  // the host vectors above go out of scope
         SparseA sp{};
+        sp.col_slice_cap = col_slice_cap;
         sp.col_pack = b->sp_pack;
         sp.row_pack = b->sp_pack + nnz;
         sp.vals = d_vals;

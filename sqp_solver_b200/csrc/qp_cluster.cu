@@ -45,43 +45,45 @@ __host__ __device__ inline size_t cluster_scratch_doubles() { return 2 * ((size_
 
 struct ClusterSmem {
     double *S;     // (RS + 2) x np: this CTA's row slice, column-major
-    double *X;     // aliased region: nnz values of this instance | sweep buffers (R chunks, T, E)
+    double *X;     // aliased region: sparse data of this instance | sweep buffers (R chunks, T, E)
     double *sw;    // m (+1)
     double *sb, *sxt, *sx, *sq;  // np each
-    double *part;  // 2 * CT
+    double *xp;    // CS * np: partial x~ of every CTA of the cluster (also scratch for P x at the checks)
     double *red;   // CS * 8
 };
-__host__ __device__ inline size_t cluster_x_doubles(int np, int m, int nnz) {
+// ccap = the largest number of stored entries in the n/CS columns one CTA owns
+__host__ __device__ inline size_t cluster_x_doubles(int np, int m, int nnz, int ccap) {
     const size_t RS = np / CS;
     const size_t sweep = 2 * (size_t)LDR * RCH + (RS + 4) * KB + 2 * (size_t)LDE * KB;
-    // sparse data of the instance: values | packed CSC entries | packed CSR entries | column pointers | row pointers
-    size_t v = (size_t)nnz + (nnz & 1) + (2 * (size_t)nnz + (size_t)np + 1 + (size_t)m + 1 + 1) / 2;
+    // sparse data of the instance: values | packed CSC entries of the own columns | packed CSR entries | own column pointers | row pointers
+    size_t v = (size_t)(nnz + 2 - (nnz & 1)) + ((size_t)ccap + (size_t)nnz + RS + 1 + (size_t)m + 1 + 1) / 2;
     v += v & 1;  // keeps every region behind it 16-byte aligned
     return v > sweep ? v : sweep;
 }
-__host__ __device__ inline size_t cluster_smem_doubles(int np, int m, int nnz) {
+__host__ __device__ inline size_t cluster_smem_doubles(int np, int m, int nnz, int ccap) {
     const size_t RS = np / CS;
-    return (RS + 2) * np + cluster_x_doubles(np, m, nnz) + (size_t)(m + (m & 1)) + 4 * (size_t)np + 2 * CT + CS * 8;
+    return (RS + 2) * np + cluster_x_doubles(np, m, nnz, ccap) + (size_t)(m + (m & 1)) + 4 * (size_t)np + (size_t)CS * np + CS * 8;
 }
-__device__ __forceinline__ ClusterSmem carve_cluster(double *base, int np, int m, int nnz) {
+__device__ __forceinline__ ClusterSmem carve_cluster(double *base, int np, int m, int nnz, int ccap) {
     ClusterSmem s;
     const int RS = np / CS;
     s.S = base;
     s.X = s.S + (size_t)(RS + 2) * np;
-    s.sw = s.X + cluster_x_doubles(np, m, nnz);
+    s.sw = s.X + cluster_x_doubles(np, m, nnz, ccap);
     s.sb = s.sw + (m + (m & 1));
     s.sxt = s.sb + np;
     s.sx = s.sxt + np;
     s.sq = s.sx + np;
-    s.part = s.sq + np;
-    s.red = s.part + 2 * CT;
+    s.xp = s.sq + np;
+    s.red = s.xp + (size_t)CS * np;
     return s;
 }
 
-bool cluster_sparse_supported(int n, int m, int nnz, size_t smem_optin) {
+bool cluster_sparse_supported(int n, int m, int nnz, int ccap, size_t smem_optin) {
     return n > 64 && n <= 256 && m >= 1 && m <= CS * CT && nnz >= 0 &&
-           sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz) + 64 <= smem_optin;
+           sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz, ccap) + 1024 <= smem_optin;
 }
+int cluster_rows_per_cta(int n) { return cluster_np(n) / CS; }
 
 __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
 // branch-free reciprocal (MUFU.RCP64H seed + two Newton steps; ~1 ulp): keeps the pivot chain of the sweep free of the
@@ -99,19 +101,18 @@ __device__ __forceinline__ double fast_rcp(double d) {
 
 // sparse dot product of one compressed row / column (entries [p0, p1) of a packed view: inner index | value position << 10)
 // with a shared-memory vector; everything it touches is in shared memory
-__device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p1, const double *vals, const double *vec) {
+// `dummy` is a packed entry whose value slot holds 0.0: the last group of four is padded with it instead of a serial tail loop.
+__device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p1, const double *vals, const double *vec, unsigned dummy) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int p = p0;
-    for (; p + 3 < p1; p += 4) {
-        const unsigned e0 = pack[p], e1 = pack[p + 1], e2 = pack[p + 2], e3 = pack[p + 3];
+    for (int p = p0; p < p1; p += 4) {
+        const unsigned e0 = pack[p];
+        const unsigned e1 = p + 1 < p1 ? pack[p + 1] : dummy;
+        const unsigned e2 = p + 2 < p1 ? pack[p + 2] : dummy;
+        const unsigned e3 = p + 3 < p1 ? pack[p + 3] : dummy;
         a0 = fma(vals[e0 >> 10], vec[e0 & 1023u], a0);
         a1 = fma(vals[e1 >> 10], vec[e1 & 1023u], a1);
         a2 = fma(vals[e2 >> 10], vec[e2 & 1023u], a2);
         a3 = fma(vals[e3 >> 10], vec[e3 & 1023u], a3);
-    }
-    for (; p < p1; ++p) {
-        const unsigned e0 = pack[p];
-        a0 = fma(vals[e0 >> 10], vec[e0 & 1023u], a0);
     }
     return (a0 + a1) + (a2 + a3);
 }
@@ -129,11 +130,13 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
     const int fr = lane >> 2, fk = lane & 3;
     const SparseA sp = p.sp;
     const int nnz = sp.nnz;
-    ClusterSmem s = carve_cluster(smem_raw, np, m, nnz);
+    const int ccap = sp.col_slice_cap;
+    ClusterSmem s = carve_cluster(smem_raw, np, m, nnz, ccap);
     double *vals = s.X;
-    unsigned *cpack = reinterpret_cast<unsigned *>(s.X + nnz + (nnz & 1));
-    unsigned *rpack = cpack + nnz;
-    int *couter = reinterpret_cast<int *>(rpack + nnz), *router = couter + np + 1;
+    unsigned *cpack = reinterpret_cast<unsigned *>(s.X + (nnz + 2 - (nnz & 1)));  // vals has one extra slot holding 0.0
+    const unsigned dummy = (unsigned)nnz << 10;
+    unsigned *rpack = cpack + ccap;
+    int *couter = reinterpret_cast<int *>(rpack + nnz), *router = couter + RS + 1;  // couter: own columns, relative to the slice
     double *Rb = s.X, *Tm = s.X + 2 * LDR * RCH, *Eb = Tm + (size_t)LDT * KB;
     const sqpb200_qp_settings st = p.s;
     const double sigma = st.sigma, alpha = st.alpha;
@@ -146,12 +149,12 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
     const int my_row = row_lo + tid / TPR, row_half = tid % TPR;
     const bool row_writer = has_row && row_half == 0;
     // peers' copies of the exchanged vectors
-    double *peer_sw[CS], *peer_sxt[CS], *peer_red[CS];
+    double *peer_sw[CS], *peer_xp[CS], *peer_red[CS];
     int *peer_qp[CS];
 #pragma unroll
     for (int r = 0; r < CS; ++r) {
         peer_sw[r] = cluster.map_shared_rank(s.sw, r);
-        peer_sxt[r] = cluster.map_shared_rank(s.sxt, r);
+        peer_xp[r] = cluster.map_shared_rank(s.xp, r);
         peer_red[r] = cluster.map_shared_rank(s.red, r);
         peer_qp[r] = cluster.map_shared_rank(&s_qp, r);
     }
@@ -183,10 +186,12 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         auto stage_sparse = [&]() {
             for (int e = tid; e < nnz; e += CT) {
                 vals[e] = __ldg(gvals + e);
-                cpack[e] = __ldg(sp.col_pack + e);
                 rpack[e] = __ldg(sp.row_pack + e);
             }
-            for (int j = tid; j <= np; j += CT) couter[j] = j <= n ? __ldg(sp.col_outer + j) : nnz;
+            if (tid == 0) vals[nnz] = 0.0;
+            const int cb = __ldg(sp.col_outer + min(n, RS * rank)), ce = __ldg(sp.col_outer + min(n, RS * rank + RS));
+            for (int e = tid; e < ce - cb; e += CT) cpack[e] = __ldg(sp.col_pack + cb + e);
+            for (int j = tid; j <= RS; j += CT) couter[j] = __ldg(sp.col_outer + min(n, RS * rank + j)) - cb;
             for (int i = tid; i <= m; i += CT) router[i] = __ldg(sp.row_outer + i);
         };
         stage_sparse();
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 const int p0 = router[my_row], p1 = router[my_row + 1];
                 const int pm = TPR == 2 ? p0 + (((p1 - p0 + 1) / 2 + 3) & ~3) : p1;  // first half: a multiple of 4 entries
                 const int lo_ = row_half == 0 ? p0 : min(pm, p1), hi_ = row_half == 0 ? min(pm, p1) : p1;
-                acc = packed_dot(rpack, lo_, hi_, vals, vec);
+                acc = packed_dot(rpack, lo_, hi_, vals, vec, dummy);
             }
             if (TPR == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             return acc;
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             for (int r = warp; r < RS; r += CNW) {
                 const int i = RS * rank + r;
                 if (i >= n) continue;
-                const int c0 = couter[i], c1 = couter[i + 1];
+                const int c0 = couter[r], c1 = couter[r + 1];
                 for (int base = c0; base < c1; base += 32) {
                     const int cnt = min(32, c1 - base);
                     double f_l = 0.0;
@@ -481,21 +486,30 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
 #endif
         // The mat-vec operands of this thread (2 rows x CPG columns of the slice) are copied into registers after every
         // factorisation: the iteration then reads only b from shared memory.
-        const int RP = RS / 2, CGN = CT / RP, CPG = np / CGN;  // CPG = 32 (np = 256) or 8 (np = 128)
-        const int rp = tid % RP, cgp = tid / RP;
+        // thread j keeps column j of the slice (RS <= 64 values): x~ = -(S^T-slice) b_slice summed over the cluster (S is symmetric)
         double sreg[64];
         auto load_slice = [&]() {
-            const double *col = s.S + 2 * rp + (size_t)LD * (cgp * CPG);
+            const double *col = s.S + (size_t)LD * min(tid, np - 1);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j < CPG) {
-                    const double2 v = *reinterpret_cast<const double2 *>(col + (size_t)LD * j);
-                    sreg[2 * j] = v.x;
-                    sreg[2 * j + 1] = v.y;
+            for (int r = 0; r < 64; r += 2) {
+                if (r < RS) {
+                    const double2 v = *reinterpret_cast<const double2 *>(col + r);
+                    sreg[r] = v.x;
+                    sreg[r + 1] = v.y;
                 } else {
-                    sreg[2 * j] = sreg[2 * j + 1] = 0.0;
+                    sreg[r] = sreg[r + 1] = 0.0;
                 }
             }
+        };
+        // b (own slice) = sigma x - q + A^T w for the own columns: TPC threads per column split its stored entries
+        const int TPC = CT / RS, bcol = tid / TPC, bpart = tid % TPC;
+        auto own_coldot = [&](const double *vec) -> double {
+            const int p0 = couter[bcol], p1 = couter[bcol + 1];
+            const int chunk = (((p1 - p0) + TPC - 1) / TPC + 3) & ~3;
+            const int lo_ = min(p0 + bpart * chunk, p1), hi_ = min(lo_ + chunk, p1);
+            double acc = packed_dot(cpack, lo_, hi_, vals, vec, dummy);
+            for (int o = 1; o < TPC; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            return acc;
         };
         bool ok = factorize();
         load_slice();
@@ -519,39 +533,45 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 }
                 cluster.sync();
                 TCK(8)
-                // b = sigma x - q + A^T w (every CTA, one column per thread; padded entries stay 0)
-                for (int j = tid; j < np; j += CT) s.sb[j] = j < n ? fma(sigma, s.sx[j], packed_dot(cpack, couter[j], couter[j + 1], vals, s.sw) - s.sq[j]) : 0.0;
+                // b (own columns) = sigma x - q + A^T w; padded entries stay 0
+                {
+                    const int j = RS * rank + bcol;
+                    const double g = own_coldot(s.sw);
+                    if (bpart == 0) s.sb[bcol] = j < n ? fma(sigma, s.sx[j], g - s.sq[j]) : 0.0;
+                }
                 __syncthreads();
                 TCK(9)
-                // x~ (own slice) = -(S slice) b: two rows per thread, the columns split over CT / (RS/2) thread groups
-                {
-                    const double *bv = s.sb + cgp * CPG;
+                // partial x~ = (S slice)^T b_slice, one column per thread out of registers -> every CTA's xp[rank]
+                if (tid < np) {
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        if (j < CPG) {
-                            const double2 b2 = *reinterpret_cast<const double2 *>(bv + j);
-                            a0 = fma(sreg[2 * j], b2.x, a0);
-                            a1 = fma(sreg[2 * j + 1], b2.x, a1);
-                            a2 = fma(sreg[2 * j + 2], b2.y, a2);
-                            a3 = fma(sreg[2 * j + 3], b2.y, a3);
+                    for (int r = 0; r < 64; r += 4) {
+                        if (r < RS) {
+                            const double2 b0 = *reinterpret_cast<const double2 *>(s.sb + r);
+                            const double2 b1 = *reinterpret_cast<const double2 *>(s.sb + r + 2);
+                            a0 = fma(sreg[r], b0.x, a0);
+                            a1 = fma(sreg[r + 1], b0.y, a1);
+                            a2 = fma(sreg[r + 2], b1.x, a2);
+                            a3 = fma(sreg[r + 3], b1.y, a3);
                         }
                     }
-                    *reinterpret_cast<double2 *>(s.part + cgp * RS + 2 * rp) = make_double2(a0 + a2, a1 + a3);
-                    __syncthreads();
-                    if (tid < RS) {
-                        double acc = 0.0;
-                        for (int g = 0; g < CGN; ++g) acc += s.part[g * RS + tid];
-                        const double xt = -acc;
+                    const double xpart = (a0 + a1) + (a2 + a3);
 #pragma unroll
-                        for (int r = 0; r < CS; ++r) peer_sxt[r][RS * rank + tid] = xt;
-                    }
+                    for (int r = 0; r < CS; ++r) peer_xp[r][rank * np + tid] = xpart;
                 }
                 TCK(10)
                 cluster.sync();
                 TCK(11)
                 // x = alpha x~ + (1 - alpha) x (every CTA keeps all of x); z~ = A x~ and the z, y updates for the owned rows
-                for (int j = tid; j < np; j += CT) s.sx[j] = alpha * s.sxt[j] + (1.0 - alpha) * s.sx[j];
+                if (tid < np) {
+                    double xt = s.xp[tid];
+#pragma unroll
+                    for (int r = 1; r < CS; ++r) xt += s.xp[r * np + tid];
+                    xt = -xt;  // S = -(H^-1)
+                    s.sxt[tid] = xt;
+                    s.sx[tid] = alpha * xt + (1.0 - alpha) * s.sx[tid];
+                }
+                __syncthreads();
                 const double zt = own_rowdot(s.sxt);
                 if (has_row) {
                     const double zh = alpha * zt + (1.0 - alpha) * zr;
@@ -564,7 +584,6 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 const bool chk = st.check_termination != 0 && iter % st.check_termination == 0;
                 const bool adapt = st.adaptive_rho && st.adaptive_rho_interval > 0 && iter % st.adaptive_rho_interval == 0;
                 if (chk || adapt) {
-                    __syncthreads();  // s.sx complete
                     double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
                     const double ax = own_rowdot(s.sx);
                     if (has_row) {
@@ -582,25 +601,25 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                         if (j < n) {
                             double a4[4] = {0.0, 0.0, 0.0, 0.0};
                             int k = kg;
-                            for (; k + 7 * KG < n; k += 8 * KG) {  // eight independent L2 loads in flight
-                                double pv[8];
+                            for (; k + 15 * KG < n; k += 16 * KG) {  // sixteen independent L2 loads in flight
+                                double pv[16];
 #pragma unroll
-                                for (int t = 0; t < 8; ++t) pv[t] = __ldg(P + j + (size_t)n * (k + t * KG));
+                                for (int t = 0; t < 16; ++t) pv[t] = __ldg(P + j + (size_t)n * (k + t * KG));
 #pragma unroll
-                                for (int t = 0; t < 8; ++t) a4[t & 3] = fma(pv[t], s.sx[k + t * KG], a4[t & 3]);
+                                for (int t = 0; t < 16; ++t) a4[t & 3] = fma(pv[t], s.sx[k + t * KG], a4[t & 3]);
                             }
                             for (; k < n; k += KG) a4[0] = fma(P[j + (size_t)n * k], s.sx[k], a4[0]);
                             acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
                         }
-                        s.part[kg * RS + r] = acc;
+                        s.xp[kg * RS + r] = acc;
                     }
                     cluster.sync();
                     if (tid < RS) {
                         const int KG = CT / RS, j = RS * rank + tid;
                         if (j < n) {
                             double px = 0.0;
-                            for (int g = 0; g < KG; ++g) px += s.part[g * RS + tid];
-                            const double aty = packed_dot(cpack, couter[j], couter[j + 1], vals, s.sw);
+                            for (int g = 0; g < KG; ++g) px += s.xp[g * RS + tid];
+                            const double aty = packed_dot(cpack, couter[tid], couter[tid + 1], vals, s.sw, dummy);
                             const double qv = s.sq[j];
                             mx[2] = fabs(px);
                             mx[3] = fabs(aty);
@@ -700,9 +719,9 @@ static cudaError_t cluster_config(size_t smem, int *max_clusters) {
     return cudaOccupancyMaxActiveClusters(max_clusters, qp_cluster_kernel, &cfg);
 }
 
-int cluster_max_clusters(int n, int m, int nnz) {
+int cluster_max_clusters(int n, int m, int nnz, int ccap) {
     int mc = 0;
-    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz);
+    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz, ccap);
     if (cluster_config(smem, &mc) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -712,7 +731,7 @@ int cluster_max_clusters(int n, int m, int nnz) {
 size_t cluster_scratch_bytes(int clusters) { return sizeof(double) * cluster_scratch_doubles() * (size_t)clusters; }
 
 cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len) {
-    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(p.n), p.m, p.sp.nnz);
+    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(p.n), p.m, p.sp.nnz, p.sp.col_slice_cap);
     cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (clusters > p.count) clusters = p.count;
