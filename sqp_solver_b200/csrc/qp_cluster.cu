@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdio>
+#include <type_traits>
 
 #include "qp_common.cuh"
 
@@ -286,92 +287,175 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
 
             bool ok = true;
             const int nblk = np / KB;
+            const size_t SCR1 = (size_t)KB * 256 + KB * KB + 8;
+            // ---- pieces of one block step -------------------------------------------------------------------------------------
+            // publish the pivot rows S[K, :] of block kb (owned by this CTA) with `nthr` threads (t = index among them; a multiple of 32)
+            auto publish_R = [&](int kb, int t, int nthr) {
+                const int k0l = kb * KB - (kb * KB / RS) * RS;
+                double *scrR = scr_base + (size_t)(kb & 1) * SCR1;
+                for (int e = t; e < KB * np; e += nthr) scrR[e] = s.S[(k0l + (e % KB)) + LD * (e / KB)];
+                __threadfence();
+            };
+            // Symmetric sweep of the 32 x 32 pivot block of block kb by ONE warp, a row per lane in registers (the 32 pivots are a
+            // serial chain: a CTA-wide version pays a barrier per pivot), published as E^-1 with the failure flag. Per pivot the lanes
+            // exchange column p through shared memory; the reciprocal of the NEXT pivot is formed by every lane from the exchanged
+            // values (bit-identical to the owner lane's update) so it overlaps the row update instead of heading the next step.
+            auto sweep_block = [&](int kb) {
+                const int k0 = kb * KB, k0l = k0 - (k0 / RS) * RS;
+                double *scrE = scr_base + (size_t)(kb & 1) * SCR1 + (size_t)KB * np, *scrF = scrE + KB * KB;
+                double row[KB];
+#pragma unroll
+                for (int j = 0; j < KB; ++j) row[j] = s.S[(k0l + lane) + LD * (k0 + j)];
+                double *cv = Eb;  // 2 x (KB + 2) doubles of exchange space (E^-1 of the current step is no longer needed)
+                bool bad = false;
+                double inv_d = 0.0;
+                {
+                    const double d = __shfl_sync(0xffffffffu, row[0], 0);
+                    if (!(fabs(d) > 0.0)) bad = true;  // zero or NaN pivot: Eigen::LDLT::info() != Success
+                    else inv_d = fast_rcp(d);
+                }
+#pragma unroll
+                for (int pv = 0; pv < KB; ++pv) {
+                    if (bad) break;
+                    double *cvp = cv + (pv & 1) * (KB + 2);
+                    cvp[lane] = row[pv];
+                    if (pv + 1 < KB && lane == pv + 1) cvp[KB] = row[pv + 1];  // diagonal of the next pivot, before this update
+                    __syncwarp();
+                    const double ti = row[pv] * inv_d;
+                    const bool piv = lane == pv;
+                    const double mult = piv ? inv_d : -ti;
+                    double d_next = 1.0, inv_next = 0.0;
+                    if (pv + 1 < KB) {
+                        const double cn = cvp[pv + 1];
+                        d_next = fma(-(cn * inv_d), cn, cvp[KB]);
+                        inv_next = fast_rcp(d_next);
+                    }
+#pragma unroll
+                    for (int j = 0; j < KB; j += 2) {
+                        const double2 c2 = *reinterpret_cast<const double2 *>(cvp + j);
+                        const double b0 = piv ? 0.0 : row[j], b1 = piv ? 0.0 : row[j + 1];
+                        row[j] = fma(mult, c2.x, b0);
+                        row[j + 1] = fma(mult, c2.y, b1);
+                    }
+                    row[pv] = piv ? -inv_d : ti;
+                    if (pv + 1 < KB) {
+                        if (!(fabs(d_next) > 0.0)) bad = true;
+                        inv_d = inv_next;
+                    }
+                }
+                // row holds row `lane` of -(E^-1): publish E^-1 (column-major, coalesced over the lanes)
+#pragma unroll
+                for (int j = 0; j < KB; ++j) scrE[lane + KB * j] = bad ? 0.0 : -row[j];
+                if (lane == 0) scrF[0] = bad ? 1.0 : 0.0;
+                __threadfence();
+            };
+            // rank-32 update S[rows of block rb, j] <- S - T R[:, j] on the fp64 tensor cores for the column groups g0, g0 + gstep, ...
+            // (a group = four 8-column tiles = four independent DMMA chains); the pivot rows R of step kb are staged chunk by chunk
+            // by the NTHR participating threads (index st among them), the next chunk's L2 loads in flight while one is consumed.
+            auto update_pass = [&](auto nthr_c, int kb, int rb, int g0, int gstep, int st, bool owner_cta, int k0l) {
+                constexpr int NTHR = decltype(nthr_c)::value, PER = KB * RCH / NTHR;
+                const int k0 = kb * KB;
+                const double *scrR = scr_base + (size_t)(kb & 1) * SCR1;
+                const bool pivot_rb = owner_cta && 8 * rb >= k0l && 8 * rb < k0l + KB;
+                double af[KB / 4];
+#pragma unroll
+                for (int ks = 0; ks < KB / 4; ++ks) af[ks] = rb >= 0 ? -Tm[(8 * rb + fr) + LDT * (4 * ks + fk)] : 0.0;
+                double rpre[PER];
+#pragma unroll
+                for (int t = 0; t < PER; ++t) rpre[t] = ldcg(scrR + st + NTHR * t);
+                const int nch = np / RCH;
+                for (int ch = 0; ch < nch; ++ch) {
+                    double *Rc = Rb + (size_t)(ch & 1) * LDR * RCH;
+#pragma unroll
+                    for (int t = 0; t < PER; ++t) {
+                        const int e = st + NTHR * t;
+                        Rc[(e % KB) + LDR * (e / KB)] = rpre[t];
+                    }
+                    if (ch + 1 < nch) {
+#pragma unroll
+                        for (int t = 0; t < PER; ++t) rpre[t] = ldcg(scrR + (size_t)KB * RCH * (ch + 1) + st + NTHR * t);
+                    }
+                    // chunk ch staged; chunk ch-1's readers finished before they staged ch (two buffers)
+                    if constexpr (NTHR == CT) __syncthreads();
+                    else asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
+                    if (rb < 0) continue;
+                    if (gstep == 1) {
+                        // both column groups of the chunk at once: eight independent DMMA chains per warp (the chains are latency bound)
+                        const bool live0 = ch * RCH != k0, live1 = ch * RCH + KB != k0;
+                        double *cp = s.S + (8 * rb + fr) + LD * (ch * RCH + 2 * fk);
+                        double c0[8], c1[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            c0[t] = pivot_rb ? 0.0 : cp[LD * 8 * t];
+                            c1[t] = pivot_rb ? 0.0 : cp[LD * (8 * t + 1)];
+                        }
+                        const double *bp = Rc + fk + LDR * fr;
+#pragma unroll
+                        for (int ks = 0; ks < KB / 4; ++ks) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const double bf = bp[4 * ks + LDR * 8 * t];
+                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                             : "+d"(c0[t]), "+d"(c1[t])
+                                             : "d"(af[ks]), "d"(bf));
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            if (t < 4 ? live0 : live1) {  // the pivot columns become T
+                                cp[LD * 8 * t] = c0[t];
+                                cp[LD * (8 * t + 1)] = c1[t];
+                            }
+                        }
+                        continue;
+                    }
+                    for (int g = g0; g < RCH / KB; g += gstep) {
+                        const int col0 = ch * RCH + KB * g;
+                        if (col0 == k0) continue;  // the pivot columns become T
+                        double *cp = s.S + (8 * rb + fr) + LD * (col0 + 2 * fk);
+                        double c0[4], c1[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            c0[t] = pivot_rb ? 0.0 : cp[LD * 8 * t];
+                            c1[t] = pivot_rb ? 0.0 : cp[LD * (8 * t + 1)];
+                        }
+                        const double *bp = Rc + fk + LDR * (KB * g + fr);
+#pragma unroll
+                        for (int ks = 0; ks < KB / 4; ++ks) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const double bf = bp[4 * ks + LDR * 8 * t];
+                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                             : "+d"(c0[t]), "+d"(c1[t])
+                                             : "d"(af[ks]), "d"(bf));
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            cp[LD * 8 * t] = c0[t];
+                            cp[LD * (8 * t + 1)] = c1[t];
+                        }
+                    }
+                }
+            };
+
+            // block 0 is published up front; every later block is published by its owner DURING the previous step (look-ahead),
+            // so the serial pivot chain of the 32 x 32 sweep hides behind the tensor-core update of the other row blocks
+            if (rank == 0) {
+                publish_R(0, tid, CT);
+                if (warp == 0) sweep_block(0);
+            }
             for (int kb = 0; kb < nblk; ++kb) {
                 const int k0 = kb * KB;
                 const int owner = k0 / RS, k0l = k0 - owner * RS;
-                double *scr = scr_base + (size_t)(kb & 1) * ((size_t)KB * 256 + KB * KB + 8);
-                double *scrR = scr, *scrE = scr + (size_t)KB * np, *scrF = scrE + KB * KB;
-                if (rank == owner) {
-                    // publish the (old) pivot rows S[K, :] first: coalesced over k
-                    for (int e = tid; e < KB * np; e += CT) {
-                        const int k = e % KB, j = e / KB;
-                        scrR[e] = s.S[(k0l + k) + LD * j];
-                    }
-                    TCK(13)
-                    // pivot block -> Eb[0], then an in-place symmetric sweep, one pivot per barrier (double buffered)
-                    double *E0 = Eb, *E1 = Eb + LDE * KB;
-                    for (int e = tid; e < KB * KB; e += CT) {
-                        const int i = e % KB, j = e / KB;
-                        E0[i * LDE + j] = s.S[(k0l + i) + LD * (k0 + j)];
-                    }
-                    __syncthreads();
-                    // Symmetric sweep of the 32 x 32 pivot block by ONE warp, a row per lane in registers (the 32 pivots are a
-                    // serial chain: a CTA-wide version pays a barrier per pivot). Per pivot the lanes exchange column p through
-                    // shared memory; the reciprocal of the NEXT pivot is formed by every lane from the exchanged values (bit-identical
-                    // to the owner lane's update) so the division overlaps the row update instead of heading the next step.
-                    __shared__ int s_bad;
-                    if (warp == 0) {
-                        double row[KB];
-#pragma unroll
-                        for (int j = 0; j < KB; ++j) row[j] = E0[lane * LDE + j];
-                        double *cv = E1;
-                        bool bad = false;
-                        double inv_d = 0.0;
-                        {
-                            const double d = __shfl_sync(0xffffffffu, row[0], 0);
-                            if (!(fabs(d) > 0.0)) bad = true;  // zero or NaN pivot: Eigen::LDLT::info() != Success
-                            else inv_d = fast_rcp(d);
-                        }
-#pragma unroll
-                        for (int pv = 0; pv < KB; ++pv) {
-                            if (bad) break;
-                            double *cvp = cv + (pv & 1) * (KB + 2);
-                            cvp[lane] = row[pv];
-                            if (pv + 1 < KB && lane == pv + 1) cvp[KB] = row[pv + 1];  // diagonal of the next pivot, before this update
-                            __syncwarp();
-                            const double ti = row[pv] * inv_d;
-                            const bool piv = lane == pv;
-                            const double mult = piv ? inv_d : -ti;
-                            double d_next = 1.0, inv_next = 0.0;
-                            if (pv + 1 < KB) {
-                                const double cn = cvp[pv + 1];
-                                d_next = fma(-(cn * inv_d), cn, cvp[KB]);
-                                inv_next = fast_rcp(d_next);
-                            }
-#pragma unroll
-                            for (int j = 0; j < KB; j += 2) {
-                                const double2 c2 = *reinterpret_cast<const double2 *>(cvp + j);
-                                const double b0 = piv ? 0.0 : row[j], b1 = piv ? 0.0 : row[j + 1];
-                                row[j] = fma(mult, c2.x, b0);
-                                row[j + 1] = fma(mult, c2.y, b1);
-                            }
-                            row[pv] = piv ? -inv_d : ti;
-                            if (pv + 1 < KB) {
-                                if (!(fabs(d_next) > 0.0)) bad = true;
-                                inv_d = inv_next;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < KB; ++j) E0[lane * LDE + j] = row[j];  // -(E^-1)
-                        if (lane == 0) s_bad = bad ? 1 : 0;
-                    }
-                    __syncthreads();
-                    const bool bad = s_bad != 0;
-                    TCK(14)
-                    for (int e = tid; e < KB * KB; e += CT) scrE[e] = bad ? 0.0 : -E0[(e % KB) * LDE + (e / KB)];
-                    if (tid == 0) scrF[0] = bad ? 1.0 : 0.0;
-                    __threadfence();
-                }
+                const double *scrE = scr_base + (size_t)(kb & 1) * SCR1 + (size_t)KB * np, *scrF = scrE + KB * KB;
                 TCK(1)
-                cluster.sync();
+                cluster.sync();  // block kb is published; every CTA has finished step kb - 1
                 TCK(2)
                 if (ldcg(scrF) != 0.0) {
                     ok = false;
                     break;
                 }
-                double rpre[KB * RCH / CT];  // this thread's share of the next chunk of pivot rows (prefetched from L2)
-#pragma unroll
-                for (int t = 0; t < KB * RCH / CT; ++t) rpre[t] = ldcg(scrR + tid + CT * t);
                 // E^-1 -> Eb (every CTA)
                 {
                     double ev[KB * KB / CT];
@@ -412,65 +496,32 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 }
                 __syncthreads();
                 TCK(3)
-                // rank-32 update of the slice on the fp64 tensor cores: S[own, j] <- S[own, j] - T R[:, j] (pivot rows start from 0)
-                {
-                    const int RBN = RS / 8;        // 8-row blocks of the slice: 8 or 4
-                    const int rb = warp % RBN;     // this warp's row block
-                    const int tsplit = CNW / RBN;  // warps sharing a row block split the column tiles: 1 or 2
-                    const int tpart = warp / RBN;
-                    const bool pivot_rb = rank == owner && 8 * rb >= k0l && 8 * rb < k0l + KB;
-                    double af[KB / 4];
-#pragma unroll
-                    for (int ks = 0; ks < KB / 4; ++ks) af[ks] = -Tm[(8 * rb + fr) + LDT * (4 * ks + fk)];
-                    const int nch = np / RCH;
-                    for (int ch = 0; ch < nch; ++ch) {
-                        double *Rc = Rb + (size_t)(ch & 1) * LDR * RCH;
-#pragma unroll
-                        for (int t = 0; t < KB * RCH / CT; ++t) {
-                            const int e = tid + CT * t;
-                            Rc[(e % KB) + LDR * (e / KB)] = rpre[t];
-                        }
-                        if (ch + 1 < nch) {  // the next chunk's L2 loads are in flight while this one is consumed
-#pragma unroll
-                            for (int t = 0; t < KB * RCH / CT; ++t) rpre[t] = ldcg(scrR + (size_t)KB * RCH * (ch + 1) + tid + CT * t);
-                        }
-                        __syncthreads();  // chunk ch staged; chunk ch-1's readers finished before they staged ch (two buffers)
-                        for (int g = tpart; g < RCH / KB; g += tsplit) {  // groups of four 8-column tiles: four independent DMMA chains
-                            const int col0 = ch * RCH + KB * g;
-                            if (col0 == k0) continue;  // the pivot columns become T below
-                            double *cp = s.S + (8 * rb + fr) + LD * (col0 + 2 * fk);
-                            double c0[4], c1[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                c0[t] = pivot_rb ? 0.0 : cp[LD * 8 * t];
-                                c1[t] = pivot_rb ? 0.0 : cp[LD * (8 * t + 1)];
-                            }
-                            const double *bp = Rc + fk + LDR * (KB * g + fr);
-#pragma unroll
-                            for (int ks = 0; ks < KB / 4; ++ks) {
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const double bf = bp[4 * ks + LDR * 8 * t];
-                                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                                                 : "+d"(c0[t]), "+d"(c1[t])
-                                                 : "d"(af[ks]), "d"(bf));
-                                }
-                            }
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                cp[LD * 8 * t] = c0[t];
-                                cp[LD * (8 * t + 1)] = c1[t];
-                            }
-                        }
+                const int RBN = RS / 8;
+                const bool next_owner = kb + 1 < nblk && rank == (k0 + KB) / RS;
+                if (!next_owner) {
+                    update_pass(std::integral_constant<int, CT>{}, kb, warp % RBN, warp / RBN, CNW / RBN, tid, rank == owner, k0l);
+                    // pivot columns of the slice <- T (nobody reads S[own, K] any more: T was formed before the last barrier)
+                    for (int e = tid; e < RS * KB; e += CT) s.S[(e % RS) + LD * (k0 + e / RS)] = Tm[(e % RS) + LDT * (e / RS)];
+                    __syncthreads();
+                } else {
+                    // look-ahead: first the four row blocks that hold the NEXT pivot rows, then publish them while the rest is updated
+                    const int k1l = (k0 + KB) - ((k0 + KB) / RS) * RS, rbn0 = k1l / 8;
+                    update_pass(std::integral_constant<int, CT>{}, kb, rbn0 + (warp & 3), warp >> 2, 2, tid, rank == owner, k0l);
+                    __syncthreads();
+                    for (int e = tid; e < RS * KB; e += CT) s.S[(e % RS) + LD * (k0 + e / RS)] = Tm[(e % RS) + LDT * (e / RS)];
+                    __syncthreads();
+                    if (warp == CNW - 1) {
+                        sweep_block(kb + 1);
+                    } else if (warp >= 4) {
+                        publish_R(kb + 1, tid - 128, 32 * (CNW - 5));
+                    } else {
+                        // the four row blocks that are not the next pivot rows (none when the slice is a single 32-row block)
+                        const int rbo = RBN > 4 ? (rbn0 == 0 ? 4 : 0) + warp : -1;
+                        update_pass(std::integral_constant<int, 128>{}, kb, rbo, 0, 1, tid, rank == owner, k0l);
                     }
+                    __syncthreads();
                 }
                 TCK(4)
-                // pivot columns of the slice <- T (nobody reads S[own, K] any more: T was formed before the last barrier)
-                for (int e = tid; e < RS * KB; e += CT) {
-                    const int r = e % RS, c = e / RS;
-                    s.S[r + LD * (k0 + c)] = Tm[r + LDT * c];
-                }
-                __syncthreads();
             }
             TCK(5)
             // the instance's sparse data comes back into the aliased region
