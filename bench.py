@@ -35,9 +35,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--n", type=int, default=64)
-    ap.add_argument("--m", type=int, default=128)
+    ap.add_argument("--workload", default="config3", choices=["config3", "config2", "config5"],
+                    help="config3 (default, the headline: batch 8192 dense 64x128), config2 (batch 1024 dense 32x64, one warp per QP), "
+                         "config5 (batch 2048 sparse-A 256x512, shared CSR pattern, cluster kernel). Only config3 is the driver's bench line")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--m", type=int, default=0)
+    ap.add_argument("--density", type=float, default=0.03, help="config5: probability that an entry of A is stored")
     ap.add_argument("--settings", default="S1", choices=["S1", "S2"],
                     help="S1 = reference defaults (headline); S2 = alpha 1.6 + adaptive rho (SURVEY.md 8d)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tile"])
@@ -231,13 +235,174 @@ def run_strong(args, rank, world, ctx, api, d, settings):
                           "admm_iters_per_s": its / (ms / 1e3 / args.steps)}))
 
 
+WORKLOADS = {"config3": (8192, 64, 128), "config2": (1024, 32, 64), "config5": (2048, 256, 512)}
+
+
+def sparse_algorithmic_bytes(n, m, nnz, iters_executed, checks, factorizations, count):
+    """SURVEY.md 8(d) accounting carried over to compressed A (8-byte value + 4-byte index per stored entry):
+    per iteration A twice + packed chol(H) twice, per check P and A once, per QP compulsory I/O, per factorisation P and A once."""
+    a = 12 * nnz
+    b_iter = 2 * a + 8 * n * (n + 1)
+    b_check = 8 * n * n + a
+    b_io = 8 * (n * n + n + 2 * m) + a + 8 * (n + m) + 16
+    b_fact = 8 * n * n + a
+    return count * b_io + iters_executed * b_iter + checks * b_check + factorizations * b_fact
+
+
+def run_config5(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: sparse-A QPs (one CSR pattern for the batch) through sqpb200_qp_batch_setup_solve_sparse.
+    Same JSON keys as the headline line; weak scaling (every rank its own batch)."""
+    import torch
+    import torch.distributed as dist
+
+    from sqp_solver_b200 import api
+    from sqp_solver_b200.synth import densify, make_sparse_batch
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = api.Context(local_rank)
+    B, n, m = args.batch, args.n, args.m
+    d = make_sparse_batch(B, n, m, density=args.density, seed0=rank * B)
+    nnz = d["nnz"]
+    settings = api.default_settings(**settings_kwargs(args.settings))
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "vals", "outer", "inner", "l", "u")}
+    qb = api.QPBatch(ctx, B, n, m)
+    qb.settings = settings
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        qb.setup_solve_sparse(dev["P"], dev["q"], dev["vals"], dev["outer"], dev["inner"], dev["l"], dev["u"], layout=api.SPARSE_CSR,
+                              stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    total_iters = qb.total_iters()
+    info0 = qb.get(fields=("status", "iter", "rho_updates"))
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([float(total_iters), float(B)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms_max, all_iters, all_qps = float(t.item()), float(agg[0].item()), float(agg[1].item())
+
+    e2e = None
+    if not args.no_e2e:
+        pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ("P", "q", "vals", "l", "u")}
+        hp = {k: v.numpy() for k, v in pin.items()}
+        ox = torch.empty(B, n, dtype=torch.float64).pin_memory()
+        oy = torch.empty(B, m, dtype=torch.float64).pin_memory()
+        ost = torch.empty(B, dtype=torch.int32).pin_memory()
+        oit = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def step_host():
+            qb.setup_solve_sparse(hp["P"], hp["q"], hp["vals"], d["outer"], d["inner"], hp["l"], hp["u"], layout=api.SPARSE_CSR)
+            qb.get_into(x=ox.numpy(), y=oy.numpy(), status=ost.numpy(), iter=oit.numpy())
+
+        for _ in range(min(args.warmup, 2)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        assert (ost.numpy() == info0["status"]).all() and (oit.numpy() == info0["iter"]).all()
+        e2e = {"value": all_qps * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": B * (8 * (n * n + n + 2 * m + nnz)) + 4 * (m + 1 + nnz),
+               "d2h_bytes_per_step": B * (8 * (n + m) + 8), "ms_per_step": 1e3 * dt / args.steps,
+               "how": "pinned host buffers -> sqpb200_qp_batch_setup_solve_sparse(HOST_PTRS): one persistent launch whose work queue is gated "
+                      "on the chunk-by-chunk H2D staging -> sqpb200_qp_batch_get to pinned host; wall clock, max over ranks"}
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    executed = np.minimum(info0["iter"], settings.max_iter).astype(np.int64)
+    executed[info0["status"] == api.NUMERICAL_ISSUES] = 0
+    ct = settings.check_termination
+    checks = int((executed // ct).sum()) if ct > 0 else 0
+    # rho_updates is cumulative over the calls on this batch object (qp.cpp:313): per launch = total / launches so far
+    calls = args.warmup + args.steps + (0 if args.no_e2e else min(args.warmup, 2) + args.steps)
+    facts = int(info0["rho_updates"].sum()) // max(calls, 1)
+    bytes_per_launch = sparse_algorithmic_bytes(n, m, nnz, int(executed.sum()), checks, facts, B)
+    sec = ms / 1e3 / args.steps
+    peak, peak_src = peaks()
+    achieved = bytes_per_launch / sec / 1e9
+    line = {
+        "metric": "QP-subproblems/sec (batch=%d, n=%d, m=%d, sparse A nnz=%d)" % (B, n, m, nnz), "value": all_qps * args.steps / (ms_max / 1e3),
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[4]: batch=%d sparse-A QPs n=%d m=%d fp64 per GPU, one CSR pattern for the batch (density %.3g + one "
+                               "entry per row: nnz=%d), settings %s, fresh setup+solve per step" % (B, n, m, args.density, nnz, args.settings),
+                   "batch_per_gpu": B, "n": n, "m": m, "nnz": nnz, "kernel": ctx.last_kernel,
+                   "parallelism": "batch-sharded x%d, no collective on the data path" % world,
+                   "l2": "inputs are %.0f MB per step, larger than the 126 MB L2" % (8 * B * (n * n + n + 2 * m + nnz) / 1e6)},
+        "admm_iters_per_s": all_iters / (ms_max / 1e3 / args.steps), "admm_iters_per_step": all_iters,
+        "factorisations_per_step": facts,
+        "status_histogram": {api.STATUS_NAMES[k]: int((info0["status"] == k).sum()) for k in np.unique(info0["status"])},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": 1e3 * sec,
+                     "note": "SURVEY.md 8(d) accounting with A compressed (12 B per stored entry). H^-1 lives in the shared memory of a "
+                             "4-CTA cluster, so DRAM traffic is the compulsory I/O only; the kernel is bound by cluster barriers and the "
+                             "serial pivot chain of the factorisation (DESIGN.md 4.4), not by HBM"},
+        "clocks": clocks,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        from oracle import qp_oracle as O
+
+        O.build()
+        cores = O.num_procs()
+        sample = args.cpu_sample or min(B, 2 * cores)
+        A = densify(d, 0, sample)
+        st = O.default_settings(**settings_kwargs(args.settings))
+        t0 = time.perf_counter()
+        out = O.solve_batch(d["P"][:sample], d["q"][:sample], A, d["l"][:sample], d["u"][:sample], st, nthreads=cores)
+        dt = time.perf_counter() - t0
+        assert (out["status"] == info0["status"][:sample]).all(), "GPU and oracle disagree on the status of the sampled QPs"
+        line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "first %d QPs of the same batch (densified: the reference's sparse variant is dead code), %s, gcc -O2 "
+                                          "oracle restatement of src/qp.cpp, OpenMP over %d threads, %.2f s" % (sample, args.settings, out["threads"], dt),
+                                "admm_iters_per_s": int(np.minimum(out["iter"], st.max_iter).sum()) / dt}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    wb, wn, wm = WORKLOADS[args.workload]
+    args.batch, args.n, args.m = args.batch or wb, args.n or wn, args.m or wm
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "config5":
+        run_config5(args, rank, world, local_rank)
         return
 
     import torch
@@ -357,10 +522,11 @@ def main():
         except Exception:
             traffic = None
     line = {
-        "metric": METRIC, "value": all_qps * args.steps / (ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if (B, n, m) == WORKLOADS["config3"] else "QP-subproblems/sec (batch=%d, n=%d, m=%d)" % (B, n, m),
+        "value": all_qps * args.steps / (ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: batch=%d dense QPs n=%d m=%d fp64 per GPU, settings %s (%s), fresh setup+solve per step"
+        "config": {"workload": "configs[%d]: batch=%%d dense QPs n=%%d m=%%d fp64 per GPU, settings %%s (%%s), fresh setup+solve per step" % (1 if args.workload == "config2" else 2)
                                % (B, n, m, args.settings, "reference defaults qp.hpp:38-53" if args.settings == "S1" else
                                   "alpha=1.6 adaptive_rho"),
                    "batch_per_gpu": B, "n": n, "m": m, "kernel": ctx.last_kernel, "parallelism": "batch-sharded x%d, no collective on the data path" % world,

@@ -53,6 +53,8 @@ struct sqpb200_qp_batch {
     double *sp_vals = nullptr;
     int sp_nnz_cap = 0;
     int *sp2_outer = nullptr, *sp2_inner = nullptr, *sp2_perm = nullptr;  // the other compressed view of the pattern
+    unsigned long long sp_hash = 0;  // hash of the pattern whose derived views (sp2_*, sp_pack) are on the device; 0 = none
+    int sp_col_slice_cap = 0;
     unsigned *sp_pack = nullptr;  // [2][cap]: packed (index | value position << 10) entries of the CSC and the CSR view (cluster kernel)
 };
 
@@ -344,7 +346,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     // sparse A: a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
     int clusters = 0;
     if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && cluster_sparse_supported(b->n, b->m, sp->nnz, sp->col_slice_cap, optin) &&
-        mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE) && !ready)
+        mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE))
         clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap);
     if (c->opt_kernel == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
     const bool want_cluster = clusters >= 1;
@@ -525,6 +527,7 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         b->sp_vals = nullptr;
         if (b->sp_pack) cudaFree(b->sp_pack);
         b->sp_pack = nullptr;
+        b->sp_hash = 0;
         const size_t cap = nnz > 0 ? nnz : 1, od = (size_t)(b->m > b->n ? b->m : b->n) + 1;
         cudaError_t e = cudaMalloc(&b->sp_outer, sizeof(int) * od);
         if (e == cudaSuccess) e = cudaMalloc(&b->sp2_outer, sizeof(int) * od);
@@ -540,16 +543,9 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
     const double *d_vals = A_values, *dP = P, *dq = q, *dl = l, *du = u;
     if (!dev) {
         CK(c, cudaMemcpyAsync(b->sp_outer, A_outer, sizeof(int) * (n_outer + 1), cudaMemcpyHostToDevice, stream));
-        if (nnz > 0) {
-            CK(c, cudaMemcpyAsync(b->sp_inner, A_inner, sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
-            CK(c, cudaMemcpyAsync(b->sp_vals, A_values, sizeof(double) * B * nnz, cudaMemcpyHostToDevice, stream));
-        }
-        CK(c, cudaMemcpyAsync(b->dP, P, sizeof(double) * B * n * n, cudaMemcpyHostToDevice, stream));
-        CK(c, cudaMemcpyAsync(b->dq, q, sizeof(double) * B * n, cudaMemcpyHostToDevice, stream));
-        if (m > 0) {
-            CK(c, cudaMemcpyAsync(b->dl, l, sizeof(double) * B * m, cudaMemcpyHostToDevice, stream));
-            CK(c, cudaMemcpyAsync(b->du, u, sizeof(double) * B * m, cudaMemcpyHostToDevice, stream));
-        }
+        if (nnz > 0) CK(c, cudaMemcpyAsync(b->sp_inner, A_inner, sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
+        // the per-instance arrays (values, P, q, l, u) follow below: chunk by chunk behind the running kernel when a sparse
+        // kernel takes the call, in one piece on `stream` when the problem is densified
         d_outer = b->sp_outer; d_inner = b->sp_inner; d_vals = b->sp_vals;
         dP = b->dP; dq = b->dq; dl = b->dl; du = b->du;
     }
@@ -576,12 +572,31 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
     const bool sparse_kernel = (c->opt_kernel == 0 || c->opt_kernel == 3 || c->opt_kernel == 4) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
                                m > 0 && (block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin) ||
                                          cluster_sparse_supported(b->n, b->m, nnz, col_slice_cap, c->prop.sharedMemPerBlockOptin));
+    auto copy_instances = [&](cudaStream_t cs, size_t lo, size_t cnt) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (nnz > 0) e = cudaMemcpyAsync(b->sp_vals + lo * nnz, A_values + lo * nnz, sizeof(double) * cnt * nnz, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->dP + lo * n * n, P + lo * n * n, sizeof(double) * cnt * n * n, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->dq + lo * n, q + lo * n, sizeof(double) * cnt * n, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess && m > 0) e = cudaMemcpyAsync(b->dl + lo * m, l + lo * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess && m > 0) e = cudaMemcpyAsync(b->du + lo * m, u + lo * m, sizeof(double) * cnt * m, cudaMemcpyHostToDevice, cs);
+        return e;
+    };
+    if (!dev && !sparse_kernel) CK(c, copy_instances(stream, 0, B));
     if (!sparse_kernel) {
         cudaError_t e = launch_densify(d_vals, d_outer, d_inner, nnz, b->m, b->n, csr, count, b->dA, stream);
         if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "densify launch", e);
         c->launches += nnz > 0 ? 1 : 0;
         rc = launch_range(b, s, mode, 0, count, dP, dq, b->dA, dl, du, stream);
     } else {
+        // The derived views of the pattern (the other compressed view, the packed entries) stay on the device between calls with
+        // the same pattern (an SQP loop re-solves with new values only): rebuilt only when the pattern's hash changes.
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&h](unsigned v) { h = (h ^ v) * 1099511628211ull; };
+        mix((unsigned)layout); mix((unsigned)n_outer); mix((unsigned)nnz);
+        for (int o = 0; o <= n_outer; ++o) mix((unsigned)h_outer[o]);
+        for (int e = 0; e < nnz; ++e) mix((unsigned)h_inner[e]);
+        if (h == 0) h = 1;
+        if (h != b->sp_hash) {
         // the other compressed view by a counting sort over the inner index; perm maps its positions to the given order
         std::vector<int> o2(n_innerdim + 1, 0), i2(nnz > 0 ? nnz : 1), perm(nnz > 0 ? nnz : 1);
         for (int e = 0; e < nnz; ++e) o2[h_inner[e] + 1]++;
@@ -611,6 +626,8 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         }
         if (nnz > 0) CK(c, cudaMemcpyAsync(b->sp_pack, pack.data(), sizeof(unsigned) * 2 * nnz, cudaMemcpyHostToDevice, stream));
         CK(c, cudaStreamSynchronize(stream));  // the host vectors above go out of scope
+        b->sp_hash = h;
+        }
         SparseA sp{};
         sp.col_slice_cap = col_slice_cap;
         sp.col_pack = b->sp_pack;
@@ -624,7 +641,25 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
             sp.col_outer = d_outer; sp.col_inner = d_inner; sp.col_perm = nullptr;
             sp.row_outer = b->sp2_outer; sp.row_inner = b->sp2_inner; sp.row_perm = b->sp2_perm;
         }
-        rc = launch_range(b, s, mode, 0, count, dP, dq, nullptr, dl, du, stream, nullptr, &sp);
+        const int *ready = nullptr;
+        if (!dev) {
+            // HOST_PTRS: ONE persistent launch; the per-instance inputs are staged chunk by chunk on the copy stream while it runs
+            // (same protocol as the dense entry points: a 4-byte copy after each chunk publishes how many QPs have landed)
+            int chunks = c->opt_chunks;
+            if (chunks > count) chunks = count;
+            CK(c, cudaMemsetAsync(c->ready_dev, 0, sizeof(int), stream));
+            CK(c, cudaEventRecord(c->chunk_events[63], stream));
+            CK(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_events[63], 0));
+            for (int k = 0; k < chunks; ++k) {
+                const size_t lo = (size_t)count * k / chunks, hi = (size_t)count * (k + 1) / chunks;
+                CK(c, copy_instances(c->copy_stream, lo, hi - lo));
+                c->ready_host[k] = (int)hi;
+                CK(c, cudaMemcpyAsync(c->ready_dev, c->ready_host + k, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+            }
+            ready = c->ready_dev;
+        }
+        rc = launch_range(b, s, mode, 0, count, dP, dq, nullptr, dl, du, stream, ready, &sp);
+        if (rc && !dev) cudaStreamSynchronize(c->copy_stream);
     }
     if (rc) return rc;
     if (!dev) CK(c, cudaStreamSynchronize(stream));
