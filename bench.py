@@ -348,6 +348,11 @@ def run_config5(args, rank, world, local_rank):
     sec = ms / 1e3 / args.steps
     peak, peak_src = peaks()
     achieved = bytes_per_launch / sec / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%dx%d_b%d_%s" % (ctx.last_kernel, n, m, B, args.settings))
+    except Exception:
+        traffic = None
     line = {
         "metric": "QP-subproblems/sec (batch=%d, n=%d, m=%d, sparse A nnz=%d)" % (B, n, m, nnz), "value": all_qps * args.steps / (ms_max / 1e3),
         "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -361,7 +366,7 @@ def run_config5(args, rank, world, local_rank):
         "factorisations_per_step": facts,
         "status_histogram": {api.STATUS_NAMES[k]: int((info0["status"] == k).sum()) for k in np.unique(info0["status"])},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": 1e3 * sec,
                      "note": "SURVEY.md 8(d) accounting with A compressed (12 B per stored entry). H^-1 lives in the shared memory of a "
                              "4-CTA cluster, so DRAM traffic is the compulsory I/O only; the kernel is bound by cluster barriers and the "
