@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
 #ifdef SQPB200_CLUSTER_TIMING
     long long tph[16] = {0}, tlast = 0;
 #endif
+    cluster.sync();  // every CTA of the cluster has started: its shared memory may be written remotely from here on
     for (;;) {
         if (rank == 0 && tid == 0) {
             const int v = draw_qp(p);
@@ -384,9 +385,10 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                         double *cp = s.S + (8 * rb + fr) + LD * (ch * RCH + 2 * fk);
                         double c0[8], c1[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            c0[t] = pivot_rb ? 0.0 : cp[LD * 8 * t];
-                            c1[t] = pivot_rb ? 0.0 : cp[LD * (8 * t + 1)];
+                        for (int t = 0; t < 8; ++t) {  // (the pivot columns are neither read nor written here: other warps may already be turning them into T)
+                            const bool skip = pivot_rb || !(t < 4 ? live0 : live1);
+                            c0[t] = skip ? 0.0 : cp[LD * 8 * t];
+                            c1[t] = skip ? 0.0 : cp[LD * (8 * t + 1)];
                         }
                         const double *bp = Rc + fk + LDR * fr;
 #pragma unroll

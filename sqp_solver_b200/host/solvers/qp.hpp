@@ -169,6 +169,22 @@ class BatchQPSolver {
         call(fn, "setup_solve", P, q, A, l, u, count);
     }
 
+    // The reference's intended sparse variant (Eigen::SparseMatrix A: include/solvers/qp.hpp:22-25,
+    // include/unsupported/qp_solver.hpp:363-394; tests/qp_solver_sparse_test.cpp): A in compressed column storage
+    // (layout SQPB200_SPARSE_CSC, Eigen's outerIndexPtr / innerIndexPtr / valuePtr) or compressed row storage, ONE pattern for
+    // the batch, values[batch][nnz]. setup + solve in one launch.
+    void setup_solve_sparse(const double *P, const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
+                            int layout, const double *l, const double *u, int count = -1) {
+        if (count < 0) count = batch_;
+        sqpb200_qp_settings s = settings_.to_c();
+        dev_->check(sqpb200_qp_batch_setup_solve_sparse(h_, &s, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u,
+                                                        SQPB200_HOST_PTRS, nullptr),
+                    "setup_solve_sparse");
+        dev_->check(sqpb200_qp_batch_get(h_, count, x_.data(), y_.data(), nullptr, status_.data(), iter_.data(), rho_updates_.data(),
+                                         rho_estimate_.data(), res_prim_.data(), res_dual_.data(), SQPB200_HOST_PTRS, nullptr),
+                    "get");
+    }
+
     const double *primal_solution(int i = 0) const { return x_.data() + (size_t)i * n_; }
     const double *dual_solution(int i = 0) const { return y_.data() + (size_t)i * m_; }
     QPSolverInfo<double> info(int i) const {

@@ -137,4 +137,67 @@ TEST(BatchQPSolverTest, manyCopiesOfSimpleQP) {
     EXPECT_EQ(solver.total_iterations(), 125LL * B);
 }
 
+// tests/qp_solver_sparse_test.cpp:36-49 (dead code in the reference: QP_SOLVER_USE_SPARSE is never defined): SimpleQP with
+// A = [[1,1],[1,0],[0,1]] stored as an Eigen::SparseMatrix (compressed columns), adaptive rho -> [0.3, 0.7]
+TEST(BatchQPSolverTest, sparseSimpleQP) {
+    const int B = 8;
+    const int outer[] = {0, 2, 4}, inner[] = {0, 1, 0, 2};
+    std::vector<double> P, q, vals, l, u;
+    for (int b = 0; b < B; ++b) {
+        const double Pm[] = {4, 1, 1, 2}, qm[] = {1, 1}, vm[] = {1, 1, 1, 1}, lm[] = {1, 0, 0}, um[] = {1, 0.7, 0.7};
+        P.insert(P.end(), Pm, Pm + 4); q.insert(q.end(), qm, qm + 2); vals.insert(vals.end(), vm, vm + 4);
+        l.insert(l.end(), lm, lm + 3); u.insert(u.end(), um, um + 3);
+    }
+    BatchQPSolver solver(B, 2, 3);
+    solver.settings().max_iter = 1000;
+    solver.settings().adaptive_rho = true;
+    solver.setup_solve_sparse(P.data(), q.data(), vals.data(), outer, inner, 4, SQPB200_SPARSE_CSC, l.data(), u.data());
+    for (int b = 0; b < B; ++b) {
+        EXPECT_EQ(solver.info(b).status, SOLVED);
+        EXPECT_TRUE(std::abs(solver.primal_solution(b)[0] - 0.3) < 3e-3 && std::abs(solver.primal_solution(b)[1] - 0.7) < 3e-3);
+    }
+}
+
+// A banded sparse problem large enough for the thread-block-cluster kernel (n = 96 > 64): min 1/2 |x|^2 - sum x subject to
+// 0 <= x_i + x_{i+1} <= 1 (bidiagonal A, CSR) and x_0 = 0.25 as an equality row. Checked against the same problem through the
+// dense entry point (blocked kernel): same status and iteration count, solutions to 1e-6.
+TEST(BatchQPSolverTest, sparseBandedMatchesDense) {
+    const int B = 5, n = 96, m = 96;
+    std::vector<int> outer(m + 1), inner;
+    std::vector<double> v1, Ad((size_t)m * n, 0.0);
+    for (int i = 0; i < m; ++i) {
+        outer[i] = (int)inner.size();
+        if (i == m - 1) {
+            inner.push_back(0); v1.push_back(1.0); Ad[i + (size_t)m * 0] = 1.0;
+        } else {
+            inner.push_back(i); v1.push_back(1.0); Ad[i + (size_t)m * i] = 1.0;
+            inner.push_back(i + 1); v1.push_back(1.0 + 0.01 * i); Ad[i + (size_t)m * (i + 1)] = 1.0 + 0.01 * i;
+        }
+    }
+    outer[m] = (int)inner.size();
+    const int nnz = (int)inner.size();
+    std::vector<double> P, q, vals, A, l, u;
+    for (int b = 0; b < B; ++b) {
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) P.push_back(i == j ? 1.0 + 0.1 * b : 0.0);
+        for (int j = 0; j < n; ++j) q.push_back(-1.0);
+        vals.insert(vals.end(), v1.begin(), v1.end());
+        A.insert(A.end(), Ad.begin(), Ad.end());
+        for (int i = 0; i < m; ++i) { l.push_back(i == m - 1 ? 0.25 : 0.0); u.push_back(i == m - 1 ? 0.25 : 1.0); }
+    }
+    BatchQPSolver sparse(B, n, m), dense(B, n, m);
+    for (BatchQPSolver *s : {&sparse, &dense}) { s->settings().alpha = 1.6; s->settings().adaptive_rho = true; }
+    sparse.setup_solve_sparse(P.data(), q.data(), vals.data(), outer.data(), inner.data(), nnz, SQPB200_SPARSE_CSR, l.data(), u.data());
+    dense.setup_solve(P.data(), q.data(), A.data(), l.data(), u.data());
+    for (int b = 0; b < B; ++b) {
+        EXPECT_EQ(sparse.info(b).status, SOLVED);
+        EXPECT_EQ(sparse.info(b).status, dense.info(b).status);
+        EXPECT_EQ(sparse.info(b).iter, dense.info(b).iter);
+        double worst = 0;
+        for (int j = 0; j < n; ++j) worst = std::max(worst, std::abs(sparse.primal_solution(b)[j] - dense.primal_solution(b)[j]));
+        EXPECT_TRUE(worst < 1e-6);
+        EXPECT_TRUE(std::abs(sparse.primal_solution(b)[0] - 0.25) < 1e-2);
+    }
+}
+
 MINI_TEST_MAIN()
