@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp32", action="store_true", help="compute in fp32 (the reference's QPSolver<float>; NOT the headline: the parity bar "
+                                                       "of the metric is fp64). dtype reads f32 and the CPU baseline is skipped")
     return ap.parse_args()
 
 
@@ -435,6 +437,9 @@ def main():
     dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")}
     qb = api.QPBatch(ctx, B, n, m)
     qb.settings = settings
+    if args.fp32:
+        qb.set_precision(True)
+        args.no_cpu_baseline = True
     stream = torch.cuda.current_stream()
 
     def step_device():
@@ -530,7 +535,7 @@ def main():
         "metric": METRIC if (B, n, m) == WORKLOADS["config3"] else "QP-subproblems/sec (batch=%d, n=%d, m=%d)" % (B, n, m),
         "value": all_qps * args.steps / (ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
         "config": {"workload": "configs[%d]: batch=%%d dense QPs n=%%d m=%%d fp64 per GPU, settings %%s (%%s), fresh setup+solve per step" % (1 if args.workload == "config2" else 2)
                                % (B, n, m, args.settings, "reference defaults qp.hpp:38-53" if args.settings == "S1" else
                                   "alpha=1.6 adaptive_rho"),

@@ -117,6 +117,14 @@ int sqpb200_constr_type_init(const double *l, const double *u, int m, int *const
 int sqpb200_qp_batch_create(sqpb200_ctx *ctx, int batch, int n, int m, sqpb200_qp_batch **out);
 int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b);
 
+/* Compute precision of one batch object: 0 = fp64 (default), 1 = fp32 -- the reference's second explicit instantiation,
+ * `template class QPSolver<float>` (src/qp.cpp:386, tests/qp_solver_test.cpp:58-69). fp32 changes the ARITHMETIC (registers, shared
+ * memory, every operation; DIV_BY_ZERO_REGUL becomes numeric_limits<float>::epsilon()); the arrays of this ABI stay `double`
+ * (inputs are rounded to float on load, results are float values widened on store: lossless, so warm starts and stored factors
+ * round-trip exactly). Available for the shapes of the register-tiled kernel (n <= 64, m <= 128); larger shapes keep computing in
+ * fp64. Meets the reference's own 1e-2 float test, not the 1e-6 parity bar of the fp64 path. */
+int sqpb200_qp_batch_set_precision(sqpb200_qp_batch *b, int fp32);
+
 /* setup: zero x,z,y; classify constraints; rho vector from settings->rho (rho_updates += 1);
  * build and factor the KKT system; status = UNSOLVED or NUMERICAL_ISSUES. qp.cpp:11-44 */
 int sqpb200_qp_batch_setup(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "sqpb200_device_query", "sqpb200_launch_count", "sqpb200_last_kernel", "sqpb200_qp_default_settings",
     "sqpb200_constr_type_init", "sqpb200_qp_batch_create", "sqpb200_qp_batch_destroy", "sqpb200_qp_batch_setup",
     "sqpb200_qp_batch_update_qp", "sqpb200_qp_batch_solve", "sqpb200_qp_batch_setup_solve",
-    "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_get",
+    "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_set_precision", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
     "sqpb200_qp_solve_batch",
 ]
@@ -90,6 +90,7 @@ def load_library(path=None):
     L.sqpb200_qp_batch_setup_solve_opts.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp, C.c_uint]
     L.sqpb200_qp_batch_setup_solve_sparse.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, ip, ip, C.c_int, C.c_int, dp, dp,
                                                       C.c_uint, vp]
+    L.sqpb200_qp_batch_set_precision.argtypes = [vp, C.c_int]
     L.sqpb200_qp_batch_get.argtypes = [vp, C.c_int, dp, dp, dp, ip, ip, ip, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_set_iterates.argtypes = [vp, C.c_int, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_device_view.argtypes = [vp, C.POINTER(DeviceView)]
@@ -203,6 +204,10 @@ class QPBatch:
         ctx._check(self._L.sqpb200_qp_batch_create(ctx._h, self.batch, self.n, self.m, C.byref(h)), "qp_batch_create")
         self._h = h
         self.settings = default_settings()  # QPSolver::settings()
+
+    def set_precision(self, fp32):
+        """Compute in fp32 (QPSolver<float>, qp.cpp:386) or fp64 (default). The arrays of the interface stay float64."""
+        self.ctx._check(self._L.sqpb200_qp_batch_set_precision(self._h, 1 if fp32 else 0), "set_precision")
 
     def close(self):
         if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):

@@ -44,6 +44,7 @@ struct sqpb200_qp_batch {
     size_t fact_doubles = 0;  // per instance
     double *fact_rho = nullptr;
     bool fused_used = false;
+    int f32 = 0;  // compute precision of the register-tiled kernel for this batch (QPSolver<float>)
     bool fact_valid = false;  // a setup()/update_qp()/solve() launch has stored H^-1, rho and classes
     unsigned long long *total_iters = nullptr;
     // staging for HOST_PTRS calls (lazily allocated)
@@ -188,6 +189,14 @@ int sqpb200_device_query(const sqpb200_ctx *c, int *device, int *sm_count, int *
 
 long long sqpb200_launch_count(const sqpb200_ctx *c) { return c ? c->launches : 0; }
 const char *sqpb200_last_kernel(const sqpb200_ctx *c) { return c ? c->last_kernel : "none"; }
+
+int sqpb200_qp_batch_set_precision(sqpb200_qp_batch *b, int fp32) {
+    if (!b) return SQPB200_ERR_INVALID;
+    if (fp32 != 0 && fp32 != 1) return fail(b->ctx, SQPB200_ERR_INVALID, "sqpb200_qp_batch_set_precision: 0 (fp64) or 1 (fp32)");
+    if (b->f32 != fp32) b->fact_valid = false;  // a factor stored by the other instantiation is not this one's
+    b->f32 = fp32;
+    return SQPB200_OK;
+}
 
 int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     if (!b) return SQPB200_OK;
@@ -366,7 +375,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
         if (rc) return rc;
         e = launch_cluster(p, clusters, (double *)c->scratch, stream, c->last_kernel, sizeof c->last_kernel);
     } else if (want_tile) {
-        e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, c->opt_tile_warps, stream, c->last_kernel, sizeof c->last_kernel);
+        e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, c->opt_tile_warps, b->f32, stream, c->last_kernel, sizeof c->last_kernel);
     } else if (want_block) {
         e = launch_block(p, c->prop.multiProcessorCount, optin, stream, c->last_kernel, sizeof c->last_kernel);
     } else {

@@ -125,6 +125,44 @@ __device__ __forceinline__ double rho_estimate_clamped(double rho, double rp, do
     return fmax(RHO_MIN, fmin(r, RHO_MAX));
 }
 
+// ---- scalar-generic versions (the register-tiled kernel is instantiated for fp64 and fp32, the reference's QPSolver<double>
+// and QPSolver<float>; the constants are the reference's `Scalar` constexprs, qp.hpp:136-141) ---------------------------------
+template <typename S>
+__device__ __forceinline__ int classify_t(S l, S u) {  // qp.cpp:283-294
+    if (l < -S(LOOSE_BOUNDS_THRESH) && u > S(LOOSE_BOUNDS_THRESH)) return SQPB200_LOOSE_BOUNDS;
+    if (u - l < S(RHO_TOL)) return SQPB200_EQUALITY_CONSTRAINT;
+    return SQPB200_INEQUALITY_CONSTRAINT;
+}
+template <typename S>
+__device__ __forceinline__ S rho_of_t(int type, S rho0) {  // qp.cpp:296-310
+    return type == SQPB200_LOOSE_BOUNDS ? S(RHO_MIN) : (type == SQPB200_EQUALITY_CONSTRAINT ? S(RHO_EQ_FACTOR) * rho0 : rho0);
+}
+__device__ __forceinline__ float box_project(float z, float l, float u) {
+    z = (z < l) ? l : z;
+    z = (u < z) ? u : z;
+    return z;
+}
+__device__ __forceinline__ float absmax(float r, float v) {
+    v = fabsf(v);
+    return v > r ? v : r;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+template <typename S>
+__device__ __forceinline__ S rho_estimate_clamped_t(S rho, S rp, S rd, S sc_p, S sc_d) {  // qp.cpp:130-132 and :333-341
+    const S eps = sizeof(S) == 8 ? S(DIV_BY_ZERO_REGUL) : S(1.1920928955078125e-7);  // numeric_limits<Scalar>::epsilon()
+    S rp_norm = rp / (sc_p + eps);
+    S rd_norm = rd / (sc_d + eps);
+    S r = rho * sqrt(rp_norm / (rd_norm + eps));
+    return fmax(S(RHO_MIN), fmin(r, S(RHO_MAX)));
+}
+
 #endif  // __CUDACC__
 
 // launchers implemented in the kernel translation units

@@ -25,8 +25,19 @@ namespace sqpb200 {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-template <int NP_, int MP_, int NW_, int LC_, int HR_, int MINB_>
+// S_ is the COMPUTE scalar: registers, shared memory and all arithmetic. The arrays in HBM are fp64 either way (the fp32
+// instantiation converts at its loads and stores: every fp32 value is exactly representable, so x, z, y and the stored factor
+// round-trip losslessly between launches). fp32 is the reference's QPSolver<float> (qp.cpp:386).
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+
+template <int NP_, int MP_, int NW_, int LC_, int HR_, int MINB_, typename S_ = double>
 struct TileCfg {
+    using S = S_;
+    static constexpr bool F64 = sizeof(S_) == 8;
     static constexpr int NP = NP_, MP = MP_, NW = NW_, LC = LC_, HR = HR_, MINB = MINB_;
     static constexpr int T = 32 * NW;
     static constexpr int LR = 32 / LC;   // lanes along the row direction inside a warp
@@ -47,7 +58,7 @@ struct TileCfg {
     static_assert(R == 1 || R % 2 == 0, "row tile must be vectorisable");
     static_assert(T >= NP, "b stage needs one thread per variable");
     // A^T diag(rho) A on the fp64 tensor cores (mma.sync m8n8k4): warp w owns IB 8-row blocks of H x all JB 8-column blocks
-    static constexpr bool DMMA = (NP % (8 * NW) == 0);
+    static constexpr bool DMMA = F64 && (NP % (8 * NW) == 0);
     static constexpr int IB = DMMA ? NP / (8 * NW) : 1, JB = NP / 8;
     // shared memory carve-up (doubles)
     // The padded staging copy of A (needed only while H is formed) and the padded copy of P (needed afterwards, for
@@ -70,7 +81,7 @@ struct TileCfg {
     static constexpr int OFF_BND = OFF_PIV + 2 * PIVS;  // (l, u) pairs per row: read once per iteration by the row owner
     static constexpr int OFF_RED = OFF_BND + 2 * MP;
     static constexpr int SMEM_DOUBLES = OFF_RED + 8 * NW;
-    static constexpr size_t SMEM_BYTES = sizeof(double) * SMEM_DOUBLES;
+    static constexpr size_t SMEM_BYTES = sizeof(S) * SMEM_DOUBLES;
 };
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ---------------------------------
@@ -118,14 +129,15 @@ __device__ __forceinline__ void cta_sync() {
 // plain butterfly (the result is then duplicated over those lanes).
 template <int V, int HI, int LO>
 struct Halve {
-    static __device__ __forceinline__ void run(double *v, int lane) {
+    template <typename T>
+    static __device__ __forceinline__ void run(T *v, int lane) {
         if constexpr (HI >= LO && HI >= 1) {
             if constexpr (V > 1) {
                 const bool up = (lane & HI) != 0;
 #pragma unroll
                 for (int k = 0; k < V / 2; ++k) {
-                    const double send = up ? v[k] : v[k + V / 2];
-                    const double keep = up ? v[k + V / 2] : v[k];
+                    const T send = up ? v[k] : v[k + V / 2];
+                    const T keep = up ? v[k + V / 2] : v[k];
                     v[k] = keep + __shfl_xor_sync(FULL, send, HI);
                 }
                 Halve<V / 2, HI / 2, LO>::run(v, lane);
@@ -155,6 +167,8 @@ __device__ __forceinline__ int halve_base(int lane, bool &primary) {
 }
 template <class Cfg>
 struct Tile {
+    using S = typename Cfg::S;
+    using V2 = typename Vec2<S>::type;
     static constexpr int NP = Cfg::NP, MP = Cfg::MP, NW = Cfg::NW, LC = Cfg::LC, LR = Cfg::LR, T = Cfg::T;
     static constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CO = Cfg::CO, CG = Cfg::CG, HC = Cfg::HC, HR = Cfg::HR;
     static constexpr int HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
@@ -164,13 +178,13 @@ struct Tile {
     static __device__ __forceinline__ int colA(int lc, int kk) { return 2 * lc + 2 * LC * (kk >> 1) + (kk & 1); }
 
     // ---- z~ = A v (v in shared memory); result: RO fully reduced rows per lane -----------------
-    static __device__ __forceinline__ void mv_A(const double (&a)[R][C], const double *sv, int lc, int lane, double (&out)[RO]) {
-        double acc[R];
+    static __device__ __forceinline__ void mv_A(const S (&a)[R][C], const S *sv, int lc, int lane, S (&out)[RO]) {
+        S acc[R];
 #pragma unroll
-        for (int kr = 0; kr < R; ++kr) acc[kr] = 0.0;
+        for (int kr = 0; kr < R; ++kr) acc[kr] = S(0);
 #pragma unroll
         for (int t = 0; t < C / 2; ++t) {
-            const double2 xv = *reinterpret_cast<const double2 *>(sv + 2 * lc + 2 * LC * t);
+            const V2 xv = *reinterpret_cast<const V2 *>(sv + 2 * lc + 2 * LC * t);
 #pragma unroll
             for (int kr = 0; kr < R; ++kr) {
                 acc[kr] = fma(a[kr][2 * t], xv.x, acc[kr]);
@@ -184,21 +198,21 @@ struct Tile {
 
     // ---- partial g = A^T v over this warp's rows -> part[warp][*] -------------------------------
     // v for the lane's R rows is read from sw (written by the row owners just before)
-    static __device__ __forceinline__ void mv_At(const double (&a)[R][C], const double *sw, double *part_w, int row0,
+    static __device__ __forceinline__ void mv_At(const S (&a)[R][C], const S *sw, S *part_w, int row0,
                                                  int lc, int lane) {
         // w is consumed in chunks of at most 4 rows so that only 4 of its values are live next to the C accumulators
         // and the R*C tile: the hot loop of the 64x128 configuration sits at the 255-register limit
-        double acc[C];
+        S acc[C];
 #pragma unroll
-        for (int kk = 0; kk < C; ++kk) acc[kk] = 0.0;
+        for (int kk = 0; kk < C; ++kk) acc[kk] = S(0);
         constexpr int WCH = (R >= 4) ? 4 : R;
 #pragma unroll
         for (int h = 0; h < R; h += WCH) {
-            double wv[WCH];
+            S wv[WCH];
             if constexpr (WCH >= 2) {
 #pragma unroll
                 for (int kr = 0; kr < WCH; kr += 2) {
-                    const double2 t2 = *reinterpret_cast<const double2 *>(sw + row0 + h + kr);
+                    const V2 t2 = *reinterpret_cast<const V2 *>(sw + row0 + h + kr);
                     wv[kr] = t2.x;
                     wv[kr + 1] = t2.y;
                 }
@@ -217,7 +231,7 @@ struct Tile {
             if constexpr (CO >= 2) {
 #pragma unroll
                 for (int t = 0; t < CO; t += 2)
-                    *reinterpret_cast<double2 *>(part_w + colA(lc, kb + t)) = make_double2(acc[t], acc[t + 1]);
+                    *reinterpret_cast<V2 *>(part_w + colA(lc, kb + t)) = mk2(acc[t], acc[t + 1]);
             } else {
                 part_w[colA(lc, kb)] = acc[0];
             }
@@ -226,14 +240,14 @@ struct Tile {
 
     // ---- y = M v for the symmetric-tile layout; each row ends fully reduced on CG/HR lanes --------
     // M in registers (H^-1)
-    static __device__ __forceinline__ double mv_sym_reg(const double (&hv)[HR][HC], const double *sv, int rg, int cg, int lane,
+    static __device__ __forceinline__ S mv_sym_reg(const S (&hv)[HR][HC], const S *sv, int rg, int cg, int lane,
                                                         int &row, bool &primary) {
-        double acc[HR], acc2[HR];  // two chains per row: the mat-vec is latency bound, not issue bound
+        S acc[HR], acc2[HR];  // two chains per row: the mat-vec is latency bound, not issue bound
 #pragma unroll
-        for (int r = 0; r < HR; ++r) acc[r] = acc2[r] = 0.0;
+        for (int r = 0; r < HR; ++r) acc[r] = acc2[r] = S(0);
 #pragma unroll
         for (int s = 0; s < HC; ++s) {
-            const double bv = sv[cg + CG * s];
+            const S bv = sv[cg + CG * s];
 #pragma unroll
             for (int r = 0; r < HR; ++r) {
                 if (s & 1) acc2[r] = fma(hv[r][s], bv, acc2[r]);
@@ -249,18 +263,18 @@ struct Tile {
         return acc[0];
     }
     // M in shared memory (P at the residual checks): padded column-major, column stride HS
-    static __device__ __forceinline__ double mv_sym_smem(const double *sM, const double *sv, int rg, int cg, int lane, int &row,
+    static __device__ __forceinline__ S mv_sym_smem(const S *sM, const S *sv, int rg, int cg, int lane, int &row,
                                                          bool &primary) {
-        double acc[HR];
+        S acc[HR];
 #pragma unroll
-        for (int r = 0; r < HR; ++r) acc[r] = 0.0;
+        for (int r = 0; r < HR; ++r) acc[r] = S(0);
 #pragma unroll
         for (int s = 0; s < HC; ++s) {
             const int k = cg + CG * s;
-            const double bv = sv[k];
+            const S bv = sv[k];
 #pragma unroll
             for (int r = 0; r < HR; r += 2) {
-                const double2 mv = *reinterpret_cast<const double2 *>(sM + HR * rg + r + HS * k);
+                const V2 mv = *reinterpret_cast<const V2 *>(sM + HR * rg + r + HS * k);
                 acc[r] = fma(mv.x, bv, acc[r]);
                 acc[r + 1] = fma(mv.y, bv, acc[r + 1]);
             }
@@ -277,18 +291,21 @@ struct Tile {
 template <class Cfg, bool SWEEP2>
 __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams p) {
     using TL = Tile<Cfg>;
+    using S = typename Cfg::S;
+    using V2 = typename Vec2<S>::type;
     constexpr int NP = Cfg::NP, MP = Cfg::MP, NW = Cfg::NW, LC = Cfg::LC, T = Cfg::T;
     constexpr int R = Cfg::R, C = Cfg::C, RO = Cfg::RO, CG = Cfg::CG, HC = Cfg::HC, HR = Cfg::HR, HS = Cfg::HS, LS = Cfg::LS, RW = Cfg::RW;
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S *smem = reinterpret_cast<S *>(smem_raw);
     __shared__ int s_qp, s_fail;
     __shared__ __align__(8) unsigned long long s_mbar;  // completion barrier of the TMA bulk copies
-    __shared__ double s_info[4];  // rho_estimate, res_prim, res_dual, rho (CTA-uniform scalars that only change at checks)
+    __shared__ S s_info[4];  // rho_estimate, res_prim, res_dual, rho (CTA-uniform scalars that only change at checks)
     __shared__ int s_cnt[1];      // rho_updates
     unsigned mbar_parity = 0;
-    double *sA = smem + Cfg::OFF_STAGE, *sP = smem + Cfg::OFF_P;
-    double *part = smem + Cfg::OFF_PART, *sx = smem + Cfg::OFF_X, *sxt = smem + Cfg::OFF_XT, *sb = smem + Cfg::OFF_B;
-    double *sq = smem + Cfg::OFF_Q, *spx = smem + Cfg::OFF_PX, *sw = smem + Cfg::OFF_W, *srho = smem + Cfg::OFF_RHO;
-    double *piv = smem + Cfg::OFF_PIV, *red = smem + Cfg::OFF_RED, *sbnd = smem + Cfg::OFF_BND;
+    S *sA = smem + Cfg::OFF_STAGE, *sP = smem + Cfg::OFF_P;
+    S *part = smem + Cfg::OFF_PART, *sx = smem + Cfg::OFF_X, *sxt = smem + Cfg::OFF_XT, *sb = smem + Cfg::OFF_B;
+    S *sq = smem + Cfg::OFF_Q, *spx = smem + Cfg::OFF_PX, *sw = smem + Cfg::OFF_W, *srho = smem + Cfg::OFF_RHO;
+    S *piv = smem + Cfg::OFF_PIV, *red = smem + Cfg::OFF_RED, *sbnd = smem + Cfg::OFF_BND;
 
     const int n = p.n, m = p.m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -299,8 +316,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     const int rg = tid / CG, cg = tid % CG;                                // symmetric-tile coordinates
     const int i0 = HR * rg;
     const sqpb200_qp_settings st = p.s;
-    const double sigma = st.sigma, alpha = st.alpha;
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const S sigma = st.sigma, alpha = st.alpha;
+    const S INF = __longlong_as_double(0x7ff0000000000000LL);
     if (tid == 0) mbar_init(&s_mbar, 1);
 
     for (;;) {
@@ -328,23 +345,23 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             s_info[3] = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
             s_cnt[0] = p.rho_updates[b] + ((p.mode & MODE_FACTOR) ? 1 : 0);  // rho_vec_update, qp.cpp:313
         }
-        const double rho0 = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
+        const S rho0 = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
         const bool reset = (p.mode & MODE_RESET) != 0;
 
         // ---- per-row state in the owner lanes' registers ----------------------------------------
-        double zr[RO], yr[RO], rhor[RO], rinv[RO];
+        S zr[RO], yr[RO], rhor[RO], rinv[RO];
         bool same_classes = true;
 #pragma unroll
         for (int t = 0; t < RO; ++t) {
             const int i = own0 + t;
             const bool real = i < m;
-            const double lo = real ? gl[i] : -INF, up = real ? gu[i] : INF;
-            if (row_primary) *reinterpret_cast<double2 *>(sbnd + 2 * i) = make_double2(lo, up);
-            zr[t] = (real && !reset) ? p.z[b * m + i] : 0.0;
-            yr[t] = (real && !reset) ? p.y[b * m + i] : 0.0;
+            const S lo = real ? gl[i] : -INF, up = real ? gu[i] : INF;
+            if (row_primary) *reinterpret_cast<V2 *>(sbnd + 2 * i) = mk2(lo, up);
+            zr[t] = (real && !reset) ? p.z[b * m + i] : S(0.0);
+            yr[t] = (real && !reset) ? p.y[b * m + i] : S(0.0);
             int typ;
             if (p.mode & MODE_FACTOR) {
-                typ = classify(lo, up);
+                typ = classify_t<S>(lo, up);
                 if (real) {
                     if ((p.mode & MODE_REUSE) && p.ctype[b * m + i] != (signed char)typ) same_classes = false;
                     if (row_primary) p.ctype[b * m + i] = (signed char)typ;
@@ -352,33 +369,33 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             } else {
                 typ = real ? p.ctype[b * m + i] : SQPB200_LOOSE_BOUNDS;
             }
-            rhor[t] = rho_of(typ, rho0);
-            rinv[t] = 1.0 / rhor[t];
+            rhor[t] = rho_of_t<S>(typ, rho0);
+            rinv[t] = S(1.0) / rhor[t];
         }
         if (tid < NP) {
-            sq[tid] = tid < n ? gq[tid] : 0.0;
-            sx[tid] = (tid < n && !reset) ? p.x[b * n + tid] : 0.0;
+            sq[tid] = tid < n ? gq[tid] : S(0.0);
+            sx[tid] = (tid < n && !reset) ? p.x[b * n + tid] : S(0.0);
         }
 
         // ---- stage A (zero padded) and pull this lane's tile into registers -----------------------
-        double a[R][C];
+        S a[R][C];
         // Full-size, 16-byte aligned problems are staged by TMA bulk copies (one per matrix column, into the
         // padded shared-memory columns) issued by warp 0 and awaited on an mbarrier; ragged or unaligned ones
         // fall back to guarded, coalesced loads with zero padding. Callers synchronise the CTA before (no reader
         // of the region is left) and after.
-        const bool bulk = n == NP && m == MP && ((reinterpret_cast<uintptr_t>(gA) | reinterpret_cast<uintptr_t>(gP)) & 15) == 0;
+        const bool bulk = Cfg::F64 && n == NP && m == MP && ((reinterpret_cast<uintptr_t>(gA) | reinterpret_cast<uintptr_t>(gP)) & 15) == 0;
         // stage(A?, P?): both land on the same mbarrier phase, so the first staging of a QP overlaps the two loads
         auto stage = [&](bool want_A, bool want_P) {
             if (bulk) {
                 if (warp == 0) {
                     fence_proxy_async();
                     if (lane == 0)
-                        mbar_expect_tx(&s_mbar, (unsigned)(((want_A ? NP * MP : 0) + (want_P ? NP * NP : 0)) * sizeof(double)));
+                        mbar_expect_tx(&s_mbar, (unsigned)(((want_A ? NP * MP : 0) + (want_P ? NP * NP : 0)) * sizeof(S)));
                     __syncwarp();
                     if (want_A)
-                        for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sA + LS * j, gA + (size_t)MP * j, (unsigned)(MP * sizeof(double)), &s_mbar);
+                        for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sA + LS * j, gA + (size_t)MP * j, (unsigned)(MP * sizeof(S)), &s_mbar);
                     if (want_P)
-                        for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sP + HS * j, gP + (size_t)NP * j, (unsigned)(NP * sizeof(double)), &s_mbar);
+                        for (int j = lane; j < NP; j += 32) tma_bulk_g2s(sP + HS * j, gP + (size_t)NP * j, (unsigned)(NP * sizeof(S)), &s_mbar);
                 }
                 mbar_wait(&s_mbar, mbar_parity);
                 mbar_parity ^= 1;
@@ -387,23 +404,23 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             if (want_A)
                 for (int e = tid; e < NP * MP; e += T) {
                     const int i = e % MP, j = e / MP;
-                    sA[i + LS * j] = (i < m && j < n) ? gA[i + (size_t)m * j] : 0.0;
+                    sA[i + LS * j] = (i < m && j < n) ? gA[i + (size_t)m * j] : S(0.0);
                 }
             if (want_P)
                 for (int e = tid; e < NP * NP; e += T) {
                     const int i = e % NP, j = e / NP;
-                    sP[i + HS * j] = (i < n && j < n) ? gP[i + (size_t)n * j] : 0.0;
+                    sP[i + HS * j] = (i < n && j < n) ? gP[i + (size_t)n * j] : S(0.0);
                 }
         };
         // H^-1 from the staged A, kept in registers hv[HR][HC]: SYRK, then symmetric elimination.
         // Requires sA staged; ends with sP valid (it replaces the staging copy) and the CTA synchronised.
-        double hv[HR][HC];
+        S hv[HR][HC];
         auto factorize = [&]() -> bool {
             // lower triangle of P mirrored (LDLT<Lower> reads nothing else), + sigma on the diagonal;
             // padded variables get a unit diagonal block
-            auto h_init = [&](int i, int j) -> double {
-                if (i >= n || j >= n) return (i == j) ? 1.0 : 0.0;
-                const double v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
+            auto h_init = [&](int i, int j) -> S {
+                if (i >= n || j >= n) return (i == j) ? S(1.0) : S(0.0);
+                const S v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
                 return (i == j) ? v + sigma : v;
             };
             if constexpr (Cfg::DMMA) {
@@ -411,17 +428,17 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 // cores: D(8x8) += A(8x4) B(4x8) with A(i,k) = rho_k A[k][i] and B(k,j) = A[k][j]; both fragments are the same
                 // one-LDS.64-per-lane read of the staged A. Accumulators start at 0; P_lowsym + sigma I is added afterwards.
                 constexpr int IB = Cfg::IB, JB = Cfg::JB;
-                double c0[IB][JB], c1[IB][JB];
+                S c0[IB][JB], c1[IB][JB];
 #pragma unroll
                 for (int ib = 0; ib < IB; ++ib)
 #pragma unroll
-                    for (int jb = 0; jb < JB; ++jb) c0[ib][jb] = c1[ib][jb] = 0.0;
+                    for (int jb = 0; jb < JB; ++jb) c0[ib][jb] = c1[ib][jb] = S(0.0);
                 const int fr = lane >> 2, fk = lane & 3;
                 const int ksteps = (m + 3) / 4;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const int k = 4 * ks + fk;
-                    const double rk = srho[k];
-                    double af[IB], bf[JB];
+                    const S rk = srho[k];
+                    S af[IB], bf[JB];
 #pragma unroll
                     for (int ib = 0; ib < IB; ++ib) af[ib] = sA[k + LS * (8 * (IB * warp + ib) + fr)] * rk;
 #pragma unroll
@@ -448,7 +465,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 for (int s = 0; s < HC; ++s)
 #pragma unroll
                     for (int r = 0; r < HR; r += 2) {
-                        const double2 h2 = *reinterpret_cast<const double2 *>(sA + i0 + r + HS * (cg + CG * s));
+                        const V2 h2 = *reinterpret_cast<const V2 *>(sA + i0 + r + HS * (cg + CG * s));
                         hv[r][s] = h_init(i0 + r, cg + CG * s) + h2.x;
                         hv[r + 1][s] = h_init(i0 + r + 1, cg + CG * s) + h2.y;
                     }
@@ -459,17 +476,17 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     for (int r = 0; r < HR; ++r) hv[r][s] = h_init(i0 + r, cg + CG * s);
                 const int mloop = (m + 1) / 2;
                 for (int kp = 0; kp < mloop; ++kp) {
-                    const double2 rr = *reinterpret_cast<const double2 *>(srho + 2 * kp);
-                    double2 ar[HR];
+                    const V2 rr = *reinterpret_cast<const V2 *>(srho + 2 * kp);
+                    V2 ar[HR];
     #pragma unroll
                     for (int r = 0; r < HR; ++r) {
-                        ar[r] = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (i0 + r));
+                        ar[r] = *reinterpret_cast<const V2 *>(sA + 2 * kp + LS * (i0 + r));
                         ar[r].x *= rr.x;
                         ar[r].y *= rr.y;
                     }
     #pragma unroll
                     for (int s = 0; s < HC; ++s) {
-                        const double2 cj = *reinterpret_cast<const double2 *>(sA + 2 * kp + LS * (cg + CG * s));
+                        const V2 cj = *reinterpret_cast<const V2 *>(sA + 2 * kp + LS * (cg + CG * s));
     #pragma unroll
                         for (int r = 0; r < HR; ++r) {
                             hv[r][s] = fma(ar[r].x, cj.x, hv[r][s]);
@@ -492,27 +509,27 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     #pragma unroll 1
                     for (int cgk = 0; cgk < CG; cgk += 2) {
                         const int k = cgk + CG * s;
-                        double *pvA = piv + ((k >> 1) & 1) * Cfg::PIVS, *pvB = pvA + NP;
+                        S *pvA = piv + ((k >> 1) & 1) * Cfg::PIVS, *pvB = pvA + NP;
                         if (cg == cgk || cg == cgk + 1) {
-                            double *dst = (cg == cgk) ? pvA : pvB;
+                            S *dst = (cg == cgk) ? pvA : pvB;
     #pragma unroll
-                            for (int r = 0; r < HR; r += 2) *reinterpret_cast<double2 *>(dst + i0 + r) = make_double2(hv[r][s], hv[r + 1][s]);
+                            for (int r = 0; r < HR; r += 2) *reinterpret_cast<V2 *>(dst + i0 + r) = mk2(hv[r][s], hv[r + 1][s]);
                         }
                         cta_sync<NW>();
-                        const double2 ab = *reinterpret_cast<const double2 *>(pvA + k);  // E00, E10
-                        const double e_c = pvB[k + 1];                                     // E11
-                        const double det = fma(ab.x, e_c, -ab.y * ab.y);
-                        if (!(fabs(ab.x) > 0.0) || !(fabs(det) > 0.0)) {
+                        const V2 ab = *reinterpret_cast<const V2 *>(pvA + k);  // E00, E10
+                        const S e_c = pvB[k + 1];                                     // E11
+                        const S det = fma(ab.x, e_c, -ab.y * ab.y);
+                        if (!(fabs(ab.x) > S(0.0)) || !(fabs(det) > S(0.0))) {
                             ok = false;
                             break;
                         }
-                        const double inv_det = 1.0 / det;
-                        const double e00 = e_c * inv_det, e01 = -ab.y * inv_det, e11 = ab.x * inv_det;  // E^-1
-                        double wA[HR], wB[HR];  // rows of S[:,K] E^-1
+                        const S inv_det = S(1.0) / det;
+                        const S e00 = e_c * inv_det, e01 = -ab.y * inv_det, e11 = ab.x * inv_det;  // E^-1
+                        S wA[HR], wB[HR];  // rows of S[:,K] E^-1
     #pragma unroll
                         for (int r = 0; r < HR; r += 2) {
-                            const double2 ca = *reinterpret_cast<const double2 *>(pvA + i0 + r);
-                            const double2 cb = *reinterpret_cast<const double2 *>(pvB + i0 + r);
+                            const V2 ca = *reinterpret_cast<const V2 *>(pvA + i0 + r);
+                            const V2 cb = *reinterpret_cast<const V2 *>(pvB + i0 + r);
                             wA[r] = fma(ca.x, e00, cb.x * e01);
                             wB[r] = fma(ca.x, e01, cb.x * e11);
                             wA[r + 1] = fma(ca.y, e00, cb.y * e01);
@@ -521,15 +538,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         const int krow = k - i0;  // pivot rows k, k+1 are rows krow, krow+1 of this lane's tile if 0 <= krow < HR
     #pragma unroll
                         for (int s2 = 0; s2 < HC; ++s2) {
-                            const double cja = pvA[cg + CG * s2], cjb = pvB[cg + CG * s2];
+                            const S cja = pvA[cg + CG * s2], cjb = pvB[cg + CG * s2];
     #pragma unroll
                             for (int r = 0; r < HR; ++r) hv[r][s2] = fma(-wB[r], cjb, fma(-wA[r], cja, hv[r][s2]));
                         }
                         if ((unsigned)krow < (unsigned)HR) {  // the row group that holds the two pivot rows
     #pragma unroll
                             for (int s2 = 0; s2 < HC; ++s2) {
-                                const double cja = pvA[cg + CG * s2], cjb = pvB[cg + CG * s2];
-                                const double ra = fma(e00, cja, e01 * cjb), rb = fma(e01, cja, e11 * cjb);
+                                const S cja = pvA[cg + CG * s2], cjb = pvB[cg + CG * s2];
+                                const S ra = fma(e00, cja, e01 * cjb), rb = fma(e01, cja, e11 * cjb);
     #pragma unroll
                                 for (int r = 0; r < HR; ++r) hv[r][s2] = (r == krow) ? ra : ((r == krow + 1) ? rb : hv[r][s2]);
                             }
@@ -551,43 +568,43 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
     #pragma unroll 1
                     for (int cgk = 0; cgk < CG; ++cgk) {
                         const int k = cgk + CG * s;
-                        double *pv = piv + (k & 1) * (NP + 2);
+                        S *pv = piv + (k & 1) * (NP + 2);
                         const int krow = k - i0;  // row of this lane's tile that is the pivot row (if 0 <= krow < HR)
                         if (cg == cgk) {
     #pragma unroll
-                            for (int r = 0; r < HR; r += 2) *reinterpret_cast<double2 *>(pv + i0 + r) = make_double2(hv[r][s], hv[r + 1][s]);
+                            for (int r = 0; r < HR; r += 2) *reinterpret_cast<V2 *>(pv + i0 + r) = mk2(hv[r][s], hv[r + 1][s]);
                             if ((unsigned)krow < (unsigned)HR) {  // the one lane that owns the pivot publishes d and 1/d
-                                double d = hv[0][s];
+                                S d = hv[0][s];
     #pragma unroll
                                 for (int r = 1; r < HR; ++r) d = (r == krow) ? hv[r][s] : d;
-                                pv[NP] = 1.0 / d;
+                                pv[NP] = S(1.0) / d;
                                 pv[NP + 1] = d;
                             }
                         }
                         cta_sync<NW>();
-                        const double2 dd = *reinterpret_cast<const double2 *>(pv + NP);
-                        const double inv_d = dd.x;
-                        if (!(fabs(dd.y) > 0.0)) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
+                        const V2 dd = *reinterpret_cast<const V2 *>(pv + NP);
+                        const S inv_d = dd.x;
+                        if (!(fabs(dd.y) > S(0.0))) {  // zero or NaN pivot: Eigen::LDLT::info() != Success
                             ok = false;
                             break;
                         }
-                        double t[HR];
+                        S t[HR];
     #pragma unroll
                         for (int r = 0; r < HR; r += 2) {
-                            const double2 ci = *reinterpret_cast<const double2 *>(pv + i0 + r);
+                            const V2 ci = *reinterpret_cast<const V2 *>(pv + i0 + r);
                             t[r] = ci.x * inv_d;
                             t[r + 1] = ci.y * inv_d;
                         }
     #pragma unroll
                         for (int s2 = 0; s2 < HC; ++s2) {
-                            const double cj = pv[cg + CG * s2];
+                            const S cj = pv[cg + CG * s2];
     #pragma unroll
                             for (int r = 0; r < HR; ++r) hv[r][s2] = fma(-t[r], cj, hv[r][s2]);
                         }
                         if ((unsigned)krow < (unsigned)HR) {  // the row group holding pivot row k: that row becomes c_j / d
     #pragma unroll
                             for (int s2 = 0; s2 < HC; ++s2) {
-                                const double rowv = pv[cg + CG * s2] * inv_d;
+                                const S rowv = pv[cg + CG * s2] * inv_d;
     #pragma unroll
                                 for (int r = 0; r < HR; ++r) hv[r][s2] = (r == krow) ? rowv : hv[r][s2];
                             }
@@ -615,11 +632,11 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         cta_sync<NW>();
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) {
-            const double *colp = sA + row0 + LS * TL::colA(lc, kk);
+            const S *colp = sA + row0 + LS * TL::colA(lc, kk);
             if constexpr (R >= 2) {
 #pragma unroll
                 for (int kr = 0; kr < R; kr += 2) {
-                    const double2 t2 = *reinterpret_cast<const double2 *>(colp + kr);
+                    const V2 t2 = *reinterpret_cast<const V2 *>(colp + kr);
                     a[kr][kk] = t2.x;
                     a[kr + 1][kk] = t2.y;
                 }
@@ -645,7 +662,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #pragma unroll
                 for (int r = 0; r < HR; ++r) {
                     const int i = i0 + r;
-                    hv[r][s] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? 1.0 : 0.0);
+                    hv[r][s] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? S(1.0) : S(0.0));
                 }
             }
             cta_sync<NW>();  // tiles are in registers; the staging area may be overwritten
@@ -712,7 +729,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 cta_sync<NW>();
                 // P2: b = sigma x - q + A^T w   (rhs of qp.cpp:272-276 pushed through the (2,2) block)
                 if (tid < NP) {
-                    double pw[NW];
+                    S pw[NW];
 #pragma unroll
                     for (int w2 = 0; w2 < NW; ++w2) pw[w2] = part[w2 * NP + tid];
 #pragma unroll
@@ -726,22 +743,22 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 {
                     int row;
                     bool prim;
-                    const double xt = TL::mv_sym_reg(hv, sb, rg, cg, lane, row, prim);
+                    const S xt = TL::mv_sym_reg(hv, sb, rg, cg, lane, row, prim);
                     if (prim) {
                         sxt[row] = xt;
-                        sx[row] = alpha * xt + (1.0 - alpha) * sx[row];
+                        sx[row] = alpha * xt + (S(1.0) - alpha) * sx[row];
                     }
                 }
                 cta_sync<NW>();
                 // P4: z~ = A x~ ; z, y updates in the owner lanes (qp.cpp:93-103)
                 {
-                    double zt[RO];
+                    S zt[RO];
                     TL::mv_A(a, sxt, lc, lane, zt);
 #pragma unroll
                     for (int t = 0; t < RO; ++t) {
-                        const double zh = alpha * zt[t] + (1.0 - alpha) * zr[t];
-                        const double2 bd = *reinterpret_cast<const double2 *>(sbnd + 2 * (own0 + t));
-                        const double zn = box_project(zh + rinv[t] * yr[t], bd.x, bd.y);
+                        const S zh = alpha * zt[t] + (S(1.0) - alpha) * zr[t];
+                        const V2 bd = *reinterpret_cast<const V2 *>(sbnd + 2 * (own0 + t));
+                        const S zn = box_project(zh + rinv[t] * yr[t], bd.x, bd.y);
                         yr[t] = yr[t] + rhor[t] * (zh - zn);
                         zr[t] = zn;
                     }
@@ -752,9 +769,9 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 if (adapt) to_adapt = st.adaptive_rho_interval;
                 if (chk || adapt) {
                     // update_state, qp.cpp:316-331
-                    double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
+                    S mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
                     {
-                        double ax[RO];  // A x (x, not x~: they differ when alpha != 1), qp.cpp:319
+                        S ax[RO];  // A x (x, not x~: they differ when alpha != 1), qp.cpp:319
                         TL::mv_A(a, sx, lc, lane, ax);
 #pragma unroll
                         for (int t = 0; t < RO; ++t) {
@@ -772,15 +789,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     {
                         int row;
                         bool prim;
-                        const double px = TL::mv_sym_smem(sP, sx, rg, cg, lane, row, prim);
+                        const S px = TL::mv_sym_smem(sP, sx, rg, cg, lane, row, prim);
                         if (prim) spx[row] = px;
                     }
                     cta_sync<NW>();
                     if (tid < NP) {
-                        double aty = part[tid];
+                        S aty = part[tid];
 #pragma unroll
                         for (int w2 = 1; w2 < NW; ++w2) aty += part[w2 * NP + tid];
-                        const double px = spx[tid], qv = sq[tid];
+                        const S px = spx[tid], qv = sq[tid];
                         mx[2] = absmax(mx[2], px);
                         mx[3] = absmax(mx[3], aty);
                         mx[4] = absmax(mx[4], qv);
@@ -788,21 +805,21 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     }
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
-                        const double v = warp_max(mx[k]);
+                        const S v = warp_max(mx[k]);
                         if (lane == 0) red[k * NW + warp] = v;
                     }
-                    const double rho = s_info[3];  // read before the barrier: thread 0 rewrites it after the decision below
+                    const S rho = s_info[3];  // read before the barrier: thread 0 rewrites it after the decision below
                     cta_sync<NW>();
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
-                        double v = red[k * NW];
+                        S v = red[k * NW];
 #pragma unroll
                         for (int w2 = 1; w2 < NW; ++w2) v = red[k * NW + w2] > v ? red[k * NW + w2] : v;
                         mx[k] = v;
                     }
-                    const double sc_p = fmax(mx[0], mx[1]);
-                    const double sc_d = fmax(mx[2], fmax(mx[3], mx[4]));
-                    const double res_prim = mx[5], res_dual = mx[6];
+                    const S sc_p = fmax(mx[0], mx[1]);
+                    const S sc_d = fmax(mx[2], fmax(mx[3], mx[4]));
+                    const S res_prim = mx[5], res_dual = mx[6];
                     if (tid == 0) {
                         s_info[1] = res_prim;
                         s_info[2] = res_dual;
@@ -814,7 +831,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         }
                     }
                     if (adapt) {  // qp.cpp:125-144
-                        const double new_rho = rho_estimate_clamped(rho, res_prim, res_dual, sc_p, sc_d);
+                        const S new_rho = rho_estimate_clamped_t<S>(rho, res_prim, res_dual, sc_p, sc_d);
                         if (tid == 0) s_info[0] = new_rho;
                         if (new_rho < rho / st.adaptive_rho_tolerance || new_rho > rho * st.adaptive_rho_tolerance) {
                             if (tid == 0) {
@@ -825,8 +842,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                             for (int t = 0; t < RO; ++t) {
                                 const int i = own0 + t;  // constraint classes were fixed by setup (qp.cpp:31): read them back
                                 const int typ = i < m ? p.ctype[b * m + i] : SQPB200_LOOSE_BOUNDS;
-                                rhor[t] = rho_of(typ, new_rho);
-                                rinv[t] = 1.0 / rhor[t];
+                                rhor[t] = rho_of_t<S>(typ, new_rho);
+                                rinv[t] = S(1.0) / rhor[t];
                             }
                             refactor = true;
                             break;
@@ -895,6 +912,11 @@ using Cfg32x64 = TileCfg<32, 64, 2, 4, 2, 8>;      // two warps per QP
 using Cfg32x64w1 = TileCfg<32, 64, 1, 4, 4, 8>;    // ONE warp per QP: no CTA barrier anywhere (BASELINE config 2's mapping)
 using Cfg16x32 = TileCfg<16, 32, 1, 4, 2, 16>;
 using Cfg8x16 = TileCfg<8, 16, 1, 4, 2, 16>;
+// fp32 compute (QPSolver<float>): half the registers and shared memory per QP, so more resident CTAs per SM
+using Cfg64x128w4f = TileCfg<64, 128, 4, 8, 4, 4, float>;
+using Cfg32x64w1f = TileCfg<32, 64, 1, 4, 4, 16, float>;
+using Cfg16x32f = TileCfg<16, 32, 1, 4, 2, 16, float>;
+using Cfg8x16f = TileCfg<8, 16, 1, 4, 2, 16, float>;
 
 bool tile_supported(int n, int m) { return n >= 1 && m >= 0 && n <= 64 && m <= 128; }
 
@@ -910,13 +932,19 @@ static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_
     if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
     long long grid = (long long)sm_count * occ;  // persistent: a multiple of the SM count
     if (grid > p.count) grid = p.count;
-    if (name) snprintf(name, name_len, "tile<%d,%d,%d>x%d", Cfg::NP, Cfg::MP, Cfg::NW, occ);  // (the sweep variant is not part of the name)
+    if (name) snprintf(name, name_len, "tile<%d,%d,%d%s>x%d", Cfg::NP, Cfg::MP, Cfg::NW, Cfg::F64 ? "" : ",f32", occ);  // (the sweep variant is not part of the name)
     kernel<<<(int)grid, Cfg::T, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, int tile_warps, cudaStream_t stream, char *name,
+cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, int tile_warps, int f32, cudaStream_t stream, char *name,
                         size_t name_len) {
+    if (f32) {  // fp32 compute: one configuration per size class
+        if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16f>(p, sm_count, ctas_per_sm, stream, name, name_len);
+        if (p.n <= 16 && p.m <= 32) return launch_cfg<Cfg16x32f>(p, sm_count, ctas_per_sm, stream, name, name_len);
+        if (p.n <= 32 && p.m <= 64) return launch_cfg<Cfg32x64w1f>(p, sm_count, ctas_per_sm, stream, name, name_len);
+        return launch_cfg<Cfg64x128w4f>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    }
     if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16>(p, sm_count, ctas_per_sm, stream, name, name_len);
     if (p.n <= 16 && p.m <= 32) return launch_cfg<Cfg16x32>(p, sm_count, ctas_per_sm, stream, name, name_len);
     if (p.n <= 32 && p.m <= 64) {

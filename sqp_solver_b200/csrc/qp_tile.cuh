@@ -4,7 +4,8 @@
 
 namespace sqpb200 {
 bool tile_supported(int n, int m);
-// tile_warps: 0 = default, 4 or 8 selects the warps-per-QP variant of the 64x128 configuration
-cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, int tile_warps, cudaStream_t stream, char *name,
+// tile_warps: 0 = default, 4 or 8 selects the warps-per-QP variant of the 64x128 configuration; f32: compute in fp32
+// (QPSolver<float>; the arrays in HBM stay fp64)
+cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, int tile_warps, int f32, cudaStream_t stream, char *name,
                         size_t name_len);
 }  // namespace sqpb200

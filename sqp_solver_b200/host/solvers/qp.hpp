@@ -142,6 +142,9 @@ class BatchQPSolver {
     BatchQPSolver(const BatchQPSolver &) = delete;
     BatchQPSolver &operator=(const BatchQPSolver &) = delete;
 
+    // compute in fp32 (the reference's QPSolver<float>, qp.cpp:386) instead of fp64; the arrays of the interface stay double
+    void set_precision_fp32(bool fp32) { dev_->check(sqpb200_qp_batch_set_precision(h_, fp32 ? 1 : 0), "set_precision"); }
+
     int batch() const { return batch_; }
     int num_var() const { return n_; }
     int num_constr() const { return m_; }
@@ -257,6 +260,7 @@ class QPSolver {
             // a new batch object is a default-constructed solver; carry the cumulative counter over (qp.cpp:313)
             int carried = info_.rho_updates;
             batch_.reset(new BatchQPSolver(1, (int)n, (int)m));
+            batch_->set_precision_fp32(sizeof(Scalar) == 4);  // QPSolver<float> computes in fp32 on the device too
             carry_rho_updates_ = carried;
         }
         x.resize(n);

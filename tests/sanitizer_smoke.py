@@ -28,13 +28,31 @@ for kernel, warps, n, m, batch in () if os.environ.get("SANITIZER_ONLY") else ((
     assert np.array_equal(out["iter"], out2["iter"]) and np.allclose(out["x"], out2["x"], rtol=0, atol=0), ctx.last_kernel
     print(ctx.last_kernel, n, m, out["iter"].tolist())
     b.close()
+# fp32 instantiation of the register-tiled kernel (QPSolver<float>)
+if not os.environ.get("SANITIZER_ONLY") or os.environ.get("SANITIZER_ONLY") == "fp32":
+    ctx.set_option(api.OPT_KERNEL, api.KERNEL_TILE)
+    ctx.set_option(api.OPT_TILE_WARPS, 0)
+    for n, m, batch in ((64, 128, 4), (32, 64, 4), (50, 100, 3), (5, 7, 3)):
+        d = make_batch(batch, n, m, seed0=99)
+        b = api.QPBatch(ctx, batch, n, m)
+        b.set_precision(True)
+        b.settings = api.default_settings(alpha=1.6, adaptive_rho=1, max_iter=120)
+        b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"])
+        out = b.get()
+        b.setup(d["P"], d["q"], d["A"], d["l"], d["u"])
+        b.solve(d["P"], d["q"], d["A"], d["l"], d["u"])
+        out2 = b.get()
+        assert np.array_equal(out["iter"], out2["iter"]) and np.array_equal(out["x"], out2["x"]), ctx.last_kernel
+        print(ctx.last_kernel, n, m, out["iter"].tolist())
+        b.close()
+
 # blocked kernel (dense and sparse A) and the thread-block-cluster kernel (sparse A): fused launches with adaptive rho
 from sqp_solver_b200.synth import make_sparse_batch
 
 only = os.environ.get("SANITIZER_ONLY", "")
 for kernel, n, m, batch, dens in ((api.KERNEL_BLOCK, 96, 160, 3, 0.0), (api.KERNEL_BLOCK, 100, 150, 3, 0.08),
                                   (api.KERNEL_CLUSTER, 100, 150, 3, 0.08), (api.KERNEL_CLUSTER, 200, 301, 2, 0.03)):
-    if only and only != {api.KERNEL_BLOCK: "block", api.KERNEL_CLUSTER: "cluster"}[kernel]:
+    if only and only != {api.KERNEL_BLOCK: "block", api.KERNEL_CLUSTER: "cluster"}[kernel]:  # (SANITIZER_ONLY=fp32 skips them all)
         continue
     ctx.set_option(api.OPT_KERNEL, kernel)
     st = api.default_settings(alpha=1.6, adaptive_rho=1, max_iter=60)
