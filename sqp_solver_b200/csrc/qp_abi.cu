@@ -56,6 +56,8 @@ struct sqpb200_qp_batch {
     int *sp2_outer = nullptr, *sp2_inner = nullptr, *sp2_perm = nullptr;  // the other compressed view of the pattern
     unsigned long long sp_hash = 0;  // hash of the pattern whose derived views (sp2_*, sp_pack) are on the device; 0 = none
     int sp_col_slice_cap = 0;
+    double *cl_scratch = nullptr;  // cluster kernel: per-cluster exchange buffers (owned by the batch object: launches of different
+    size_t cl_scratch_bytes = 0;   // batch objects may overlap on different streams)
     unsigned *sp_pack = nullptr;  // [2][cap]: packed (index | value position << 10) entries of the CSC and the CSR view (cluster kernel)
 };
 
@@ -203,7 +205,7 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
-                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm, b->sp_pack};
+                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm, b->sp_pack, b->cl_scratch};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete b;
@@ -371,9 +373,17 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     cudaError_t e;
     if (want_cluster) {
         if (clusters > count) clusters = count;
-        int rc = ensure_scratch(c, cluster_scratch_bytes(clusters));
-        if (rc) return rc;
-        e = launch_cluster(p, clusters, (double *)c->scratch, stream, c->last_kernel, sizeof c->last_kernel);
+        const size_t need = cluster_scratch_bytes(cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap));
+        if (need > b->cl_scratch_bytes) {
+            CK(c, cudaDeviceSynchronize());
+            if (b->cl_scratch) cudaFree(b->cl_scratch);
+            b->cl_scratch = nullptr;
+            b->cl_scratch_bytes = 0;
+            cudaError_t ea = cudaMalloc(&b->cl_scratch, need);
+            if (ea != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "cluster scratch cudaMalloc", ea);
+            b->cl_scratch_bytes = need;
+        }
+        e = launch_cluster(p, clusters, b->cl_scratch, stream, c->last_kernel, sizeof c->last_kernel);
     } else if (want_tile) {
         e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, c->opt_tile_warps, b->f32, stream, c->last_kernel, sizeof c->last_kernel);
     } else if (want_block) {

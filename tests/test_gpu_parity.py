@@ -784,3 +784,37 @@ def test_fp32_reference_float_test_and_fallback(api, ctx, golden):
     b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"])
     assert "f32" not in ctx.last_kernel and ctx.last_kernel.startswith("block")
     b.close()
+
+
+def test_cluster_kernel_concurrent_batches_on_streams(api, ctx):
+    """Two batch objects solved by the cluster kernel at the same time on two CUDA streams (device pointers, asynchronous calls):
+    each owns its exchange scratch, so the overlapped launches give the same results as running them one after the other."""
+    import torch
+
+    n, m, batch = 130, 260, 40
+    ds = [_sparse_batch(batch, n, m, 0.04, 18000 + 100 * k, "csr") for k in range(2)]
+    s = api.default_settings(alpha=1.6, adaptive_rho=1, max_iter=200)
+    ctx.set_option(api.OPT_KERNEL, api.KERNEL_CLUSTER)
+    dev = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in
+            dict(P=d["P"], q=d["q"], l=d["l"], u=d["u"], vals=vals, outer=outer, inner=inner).items()} for d, vals, outer, inner in ds]
+    serial = []
+    for k in range(2):
+        b = api.QPBatch(ctx, batch, n, m)
+        b.settings = s
+        b.setup_solve_sparse(dev[k]["P"], dev[k]["q"], dev[k]["vals"], dev[k]["outer"], dev[k]["inner"], dev[k]["l"], dev[k]["u"], layout=api.SPARSE_CSR)
+        torch.cuda.synchronize()
+        serial.append(b.get())
+        b.close()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    bs = [api.QPBatch(ctx, batch, n, m) for _ in range(2)]
+    for rep in range(3):
+        for k in range(2):
+            bs[k].settings = s
+            bs[k].setup_solve_sparse(dev[k]["P"], dev[k]["q"], dev[k]["vals"], dev[k]["outer"], dev[k]["inner"], dev[k]["l"], dev[k]["u"],
+                                     layout=api.SPARSE_CSR, stream=streams[k].cuda_stream)
+    torch.cuda.synchronize()
+    for k in range(2):
+        got = bs[k].get()
+        np.testing.assert_array_equal(got["iter"], serial[k]["iter"])
+        np.testing.assert_array_equal(got["x"], serial[k]["x"])
+        bs[k].close()
