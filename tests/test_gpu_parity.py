@@ -818,3 +818,36 @@ def test_cluster_kernel_concurrent_batches_on_streams(api, ctx):
         np.testing.assert_array_equal(got["iter"], serial[k]["iter"])
         np.testing.assert_array_equal(got["x"], serial[k]["x"])
         bs[k].close()
+
+
+def test_cluster_and_fp32_against_committed_golden_outputs(api, ctx):
+    """The cluster kernel (sparse A) and the fp32 instantiation against the COMMITTED oracle outputs of
+    tests/golden/oracle_sparse_f32.json (no oracle run involved)."""
+    import json
+    import os
+
+    from sqp_solver_b200.synth import make_batch, make_sparse_batch
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_sparse_f32.json")) as f:
+        gold = json.load(f)
+    for c in gold["sparse"]:
+        d = make_sparse_batch(c["batch"], c["n"], c["m"], density=c["density"], seed0=c["seed0"])
+        b = api.QPBatch(ctx, c["batch"], c["n"], c["m"])
+        b.settings = api.default_settings(**c["settings"])
+        b.setup_solve_sparse(d["P"], d["q"], d["vals"], d["outer"], d["inner"], d["l"], d["u"], layout=api.SPARSE_CSR)
+        assert ctx.last_kernel.startswith("cluster"), ctx.last_kernel
+        out = b.get()
+        ref = dict(status=np.array(c["status"]), iter=np.array(c["iter"]), x=np.array(c["x"]), y=np.array(c["y"]))
+        assert_parity({k: out[k] for k in ("status", "iter", "x", "y")}, ref, what="golden " + c["name"])
+        b.close()
+    for c in gold["f32"]:
+        d = make_batch(c["batch"], c["n"], c["m"], seed0=c["seed0"])
+        b = api.QPBatch(ctx, c["batch"], c["n"], c["m"])
+        b.settings = api.default_settings(**c["settings"])
+        b.set_precision(True)
+        b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"])
+        out = b.get()
+        assert out["status"].tolist() == c["status"] and out["iter"].tolist() == c["iter"], c["name"]
+        rel = np.linalg.norm(out["x"] - np.array(c["x"]), axis=1) / np.linalg.norm(np.array(c["x"]), axis=1)
+        assert rel.max() < 1e-4, (c["name"], rel)
+        b.close()

@@ -240,3 +240,31 @@ def test_oracle_reproduces_committed_golden_outputs(oracle):
         assert r["rho_updates"].tolist() == c["rho_updates"], c["name"]
         np.testing.assert_allclose(r["x"], np.array(c["x"]), rtol=0, atol=1e-9, err_msg=c["name"])
         np.testing.assert_allclose(r["y"], np.array(c["y"]), rtol=0, atol=1e-8, err_msg=c["name"])
+
+
+def test_oracle_reproduces_committed_sparse_and_f32_golden(oracle):
+    """tests/golden/oracle_sparse_f32.json: the densified sparse-A cases (BASELINE config 5's path) and the float instantiation."""
+    import json
+    import os
+
+    from sqp_solver_b200.synth import densify, make_batch, make_sparse_batch
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_sparse_f32.json")) as f:
+        gold = json.load(f)
+    for c in gold["sparse"][:2]:  # (the third case repeats the 256x512 shape with more iterations: left to the GPU test)
+        d = make_sparse_batch(c["batch"], c["n"], c["m"], density=c["density"], seed0=c["seed0"])
+        assert d["nnz"] == c["nnz"]
+        r = oracle.solve_batch(d["P"], d["q"], densify(d), d["l"], d["u"], oracle.default_settings(**c["settings"]), nthreads=2)
+        assert r["status"].tolist() == c["status"] and r["iter"].tolist() == c["iter"], c["name"]
+        np.testing.assert_allclose(r["x"], np.array(c["x"]), rtol=0, atol=1e-9, err_msg=c["name"])
+    for c in gold["f32"]:
+        d = make_batch(c["batch"], c["n"], c["m"], seed0=c["seed0"])
+        n, m = c["n"], c["m"]
+        for i in range(c["batch"]):
+            qp = oracle.QuadraticProblem(d["P"][i].reshape(n, n, order="F"), d["q"][i], d["A"][i].reshape(m, n, order="F"), d["l"][i],
+                                         d["u"][i], dtype=np.float32)
+            s = oracle.QPSolver(dtype=np.float32)
+            s.setup(qp)
+            s.solve(qp)
+            assert int(s.info().status) == c["status"][i] and int(s.info().iter) == c["iter"][i], c["name"]
+            np.testing.assert_allclose(s.primal_solution(), np.array(c["x"][i]), rtol=0, atol=2e-6, err_msg=c["name"])
