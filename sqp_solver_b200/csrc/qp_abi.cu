@@ -356,9 +356,13 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     const bool want_tile = !sp && c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
     // sparse A: a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
     int clusters = 0;
-    if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && cluster_sparse_supported(b->n, b->m, sp->nnz, sp->col_slice_cap, optin) &&
-        mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE))
-        clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap);
+    if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && sp->cluster_size > 0 && mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE))
+        clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap, sp->cluster_size);
+    // Eight CTAs per QP buy latency, not throughput (measured at n = 256, nnz = 8.9 k: 0.84 ms per QP on 8 SMs against 7.7 ms on one SM
+    // with the blocked kernel, i.e. the same QPs per SM-second): keep them for batches that cannot fill the SMs one QP each
+    if (clusters >= 1 && sp->cluster_size == 8 && c->opt_kernel == 0 && count > c->prop.multiProcessorCount &&
+        block_sparse_supported(b->n, b->m, sp->nnz, optin))
+        clusters = 0;
     if (c->opt_kernel == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
     const bool want_cluster = clusters >= 1;
     const bool want_block = !want_cluster && (sp || (!want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin)));
@@ -373,7 +377,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     cudaError_t e;
     if (want_cluster) {
         if (clusters > count) clusters = count;
-        const size_t need = cluster_scratch_bytes(cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap));
+        const size_t need = cluster_scratch_bytes(cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap, sp->cluster_size));
         if (need > b->cl_scratch_bytes) {
             CK(c, cudaDeviceSynchronize());
             if (b->cl_scratch) cudaFree(b->cl_scratch);
@@ -575,22 +579,16 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
 
     // Shapes the register-tiled kernel covers keep A in registers anyway: densify. Larger ones run the blocked kernel with the
     // values of one instance staged in shared memory and both compressed views of the pattern.
-    // cluster kernel: the most stored entries in the n/4-column slice one CTA owns (sizes its shared-memory copy of them)
-    int col_slice_cap = 0;
+    // cluster kernel: how many CTAs per QP (0 = does not fit on chip) and the most stored entries in the column slice one CTA owns
+    int col_slice_cap = 0, cluster_size = 0;
     if (b->n > 64 && b->n <= 256) {
         std::vector<int> colcount(b->n, 0);
         if (csr) for (int e = 0; e < nnz; ++e) colcount[h_inner[e]]++;
         else for (int j = 0; j < b->n; ++j) colcount[j] = h_outer[j + 1] - h_outer[j];
-        const int rs = cluster_rows_per_cta(b->n);
-        for (int j0 = 0; j0 < b->n; j0 += rs) {
-            int cnt = 0;
-            for (int j = j0; j < j0 + rs && j < b->n; ++j) cnt += colcount[j];
-            if (cnt > col_slice_cap) col_slice_cap = cnt;
-        }
+        cluster_size = cluster_plan(b->n, b->m, nnz, colcount.data(), c->prop.sharedMemPerBlockOptin, &col_slice_cap);
     }
     const bool sparse_kernel = (c->opt_kernel == 0 || c->opt_kernel == 3 || c->opt_kernel == 4) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
-                               m > 0 && (block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin) ||
-                                         cluster_sparse_supported(b->n, b->m, nnz, col_slice_cap, c->prop.sharedMemPerBlockOptin));
+                               m > 0 && (block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin) || cluster_size > 0);
     auto copy_instances = [&](cudaStream_t cs, size_t lo, size_t cnt) -> cudaError_t {
         cudaError_t e = cudaSuccess;
         if (nnz > 0) e = cudaMemcpyAsync(b->sp_vals + lo * nnz, A_values + lo * nnz, sizeof(double) * cnt * nnz, cudaMemcpyHostToDevice, cs);
@@ -649,6 +647,7 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         }
         SparseA sp{};
         sp.col_slice_cap = col_slice_cap;
+        sp.cluster_size = cluster_size;
         sp.col_pack = b->sp_pack;
         sp.row_pack = b->sp_pack + nnz;
         sp.vals = d_vals;

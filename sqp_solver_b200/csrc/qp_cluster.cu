@@ -1,7 +1,7 @@
 // Thread-block-cluster batched ADMM QP kernel for sparse constraint matrices with 64 < n <= 256 -- BASELINE.json config 5
 // (n = 256, m = 512, one sparsity pattern shared by the batch).
 //
-// One CLUSTER of CS = 4 CTAs (4 SMs) per QP, persistent clusters on the atomic work queue. H^-1 (n x n fp64, 512 KB at
+// One CLUSTER of CS = 4 CTAs (4 SMs) per QP (8 when the pattern is too dense for four at n > 128), persistent clusters on the atomic work queue. H^-1 (n x n fp64, 512 KB at
 // n = 256) does not fit in one SM's shared memory, but it fits in the cluster's: CTA r keeps rows [r n/4, (r+1) n/4) of it
 // (all columns) in its own shared memory for the whole solve, so the per-iteration KKT solve (reference qp.cpp:90) is ONE
 // dense mat-vec out of shared memory -- no substitution chain, no L2 traffic. Per iteration the CTAs exchange only vectors
@@ -33,7 +33,6 @@ namespace sqpb200 {
 #define TCK(i)
 #endif
 
-constexpr int CS = 4;    // CTAs per cluster
 constexpr int CT = 256;  // threads per CTA
 constexpr int CNW = CT / 32;
 constexpr int KB = 32;   // pivot block
@@ -53,7 +52,7 @@ struct ClusterSmem {
     double *red;   // CS * 8
 };
 // ccap = the largest number of stored entries in the n/CS columns one CTA owns
-__host__ __device__ inline size_t cluster_x_doubles(int np, int m, int nnz, int ccap) {
+__host__ __device__ inline size_t cluster_x_doubles(int np, int m, int nnz, int ccap, int CS) {
     const size_t RS = np / CS;
     const size_t sweep = 2 * (size_t)LDR * RCH + (RS + 4) * KB + 2 * (size_t)LDE * KB;
     // sparse data of the instance: values | packed CSC entries of the own columns | packed CSR entries | own column pointers | row pointers
@@ -61,16 +60,16 @@ __host__ __device__ inline size_t cluster_x_doubles(int np, int m, int nnz, int 
     v += v & 1;  // keeps every region behind it 16-byte aligned
     return v > sweep ? v : sweep;
 }
-__host__ __device__ inline size_t cluster_smem_doubles(int np, int m, int nnz, int ccap) {
+__host__ __device__ inline size_t cluster_smem_doubles(int np, int m, int nnz, int ccap, int CS) {
     const size_t RS = np / CS;
-    return (RS + 2) * np + cluster_x_doubles(np, m, nnz, ccap) + (size_t)(m + (m & 1)) + 4 * (size_t)np + (size_t)CS * np + CS * 8;
+    return (RS + 2) * np + cluster_x_doubles(np, m, nnz, ccap, CS) + (size_t)(m + (m & 1)) + 4 * (size_t)np + (size_t)CS * np + CS * 8;
 }
-__device__ __forceinline__ ClusterSmem carve_cluster(double *base, int np, int m, int nnz, int ccap) {
+__device__ __forceinline__ ClusterSmem carve_cluster(double *base, int np, int m, int nnz, int ccap, int CS) {
     ClusterSmem s;
     const int RS = np / CS;
     s.S = base;
     s.X = s.S + (size_t)(RS + 2) * np;
-    s.sw = s.X + cluster_x_doubles(np, m, nnz, ccap);
+    s.sw = s.X + cluster_x_doubles(np, m, nnz, ccap, CS);
     s.sb = s.sw + (m + (m & 1));
     s.sxt = s.sb + np;
     s.sx = s.sxt + np;
@@ -80,11 +79,28 @@ __device__ __forceinline__ ClusterSmem carve_cluster(double *base, int np, int m
     return s;
 }
 
-bool cluster_sparse_supported(int n, int m, int nnz, int ccap, size_t smem_optin) {
-    return n > 64 && n <= 256 && m >= 1 && m <= CS * CT && nnz >= 0 &&
-           sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz, ccap) + 1024 <= smem_optin;
+// Cluster size for a sparse problem: 4 CTAs when the instance fits their shared memory, else 8 (n > 128 only: a pivot block must
+// not straddle two CTAs), else 0 (the blocked kernel takes it). colcount[j] = stored entries of column j; *ccap = the most entries
+// in the columns one CTA owns.
+int cluster_plan(int n, int m, int nnz, const int *colcount, size_t smem_optin, int *ccap) {
+    if (!(n > 64 && n <= 256 && m >= 1 && nnz >= 0)) return 0;
+    const int np = cluster_np(n);
+    for (int cs = 4; cs <= 8; cs *= 2) {
+        const int rs = np / cs;
+        if (rs < KB || m > cs * CT) continue;
+        int cap = 0;
+        for (int j0 = 0; j0 < n; j0 += rs) {
+            int cnt = 0;
+            for (int j = j0; j < j0 + rs && j < n; ++j) cnt += colcount[j];
+            if (cnt > cap) cap = cnt;
+        }
+        if (sizeof(double) * cluster_smem_doubles(np, m, nnz, cap, cs) + 1024 <= smem_optin) {
+            *ccap = cap;
+            return cs;
+        }
+    }
+    return 0;
 }
-int cluster_rows_per_cta(int n) { return cluster_np(n) / CS; }
 
 __device__ __forceinline__ double ldcg(const double *p) { return __ldcg(p); }
 // branch-free reciprocal (MUFU.RCP64H seed + two Newton steps; ~1 ulp): keeps the pivot chain of the sweep free of the
@@ -118,6 +134,7 @@ __device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p
     return (a0 + a1) + (a2 + a3);
 }
 
+template <int CS>
 __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, double *scratch) {
     extern __shared__ __align__(16) double smem_raw[];
     __shared__ int s_qp;
@@ -132,7 +149,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
     const SparseA sp = p.sp;
     const int nnz = sp.nnz;
     const int ccap = sp.col_slice_cap;
-    ClusterSmem s = carve_cluster(smem_raw, np, m, nnz, ccap);
+    ClusterSmem s = carve_cluster(smem_raw, np, m, nnz, ccap, CS);
     double *vals = s.X;
     unsigned *cpack = reinterpret_cast<unsigned *>(s.X + (nnz + 2 - (nnz & 1)));  // vals has one extra slot holding 0.0
     const unsigned dummy = (unsigned)nnz << 10;
@@ -754,11 +771,12 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
     cluster.sync();  // no CTA exits while a peer may still touch its shared memory
 }
 
+template <int CS>
 static cudaError_t cluster_config(size_t smem, int *max_clusters) {
-    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CS * 64, 1, 1);
+    cfg.gridDim = dim3(CS * 16, 1, 1);
     cfg.blockDim = dim3(CT, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
@@ -768,13 +786,13 @@ static cudaError_t cluster_config(size_t smem, int *max_clusters) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(max_clusters, qp_cluster_kernel, &cfg);
+    return cudaOccupancyMaxActiveClusters(max_clusters, qp_cluster_kernel<CS>, &cfg);
 }
 
-int cluster_max_clusters(int n, int m, int nnz, int ccap) {
+int cluster_max_clusters(int n, int m, int nnz, int ccap, int cs) {
     int mc = 0;
-    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz, ccap);
-    if (cluster_config(smem, &mc) != cudaSuccess) {
+    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(n), m, nnz, ccap, cs);
+    if ((cs == 8 ? cluster_config<8>(smem, &mc) : cluster_config<4>(smem, &mc)) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -782,9 +800,10 @@ int cluster_max_clusters(int n, int m, int nnz, int ccap) {
 }
 size_t cluster_scratch_bytes(int clusters) { return sizeof(double) * cluster_scratch_doubles() * (size_t)clusters; }
 
-cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len) {
-    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(p.n), p.m, p.sp.nnz, p.sp.col_slice_cap);
-    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int CS>
+static cudaError_t launch_cluster_cs(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len) {
+    const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(p.n), p.m, p.sp.nnz, p.sp.col_slice_cap, CS);
+    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (clusters > p.count) clusters = p.count;
     if (clusters < 1) return cudaErrorLaunchOutOfResources;
@@ -801,7 +820,12 @@ cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (name) snprintf(name, name_len, "cluster<%d>/sparse x%d", CS, clusters);
-    return cudaLaunchKernelEx(&cfg, qp_cluster_kernel, p, scratch);
+    return cudaLaunchKernelEx(&cfg, qp_cluster_kernel<CS>, p, scratch);
+}
+
+cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len) {
+    return p.sp.cluster_size == 8 ? launch_cluster_cs<8>(p, clusters, scratch, stream, name, name_len)
+                                  : launch_cluster_cs<4>(p, clusters, scratch, stream, name, name_len);
 }
 
 }  // namespace sqpb200

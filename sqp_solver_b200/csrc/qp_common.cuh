@@ -50,6 +50,7 @@ struct SparseA {
     const unsigned *col_pack, *row_pack;          // per stored entry of the CSC / CSR view: inner index | (position in vals << 10)
     int nnz;
     int col_slice_cap;  // cluster kernel: most stored entries in the columns one CTA owns
+    int cluster_size;   // cluster kernel: CTAs per QP (4 or 8); 0 = not planned for the cluster kernel
 };
 
 struct KernelParams {
@@ -176,9 +177,8 @@ bool block_sparse_supported(int n, int m, int nnz, size_t smem_optin);
 size_t block_fact_doubles(int n);
 cudaError_t launch_block(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, char *name, size_t name_len);
 // cluster kernel for sparse A, 64 < n <= 256 (qp_cluster.cu)
-bool cluster_sparse_supported(int n, int m, int nnz, int col_slice_cap, size_t smem_optin);
-int cluster_rows_per_cta(int n);
-int cluster_max_clusters(int n, int m, int nnz, int col_slice_cap);
+int cluster_plan(int n, int m, int nnz, const int *colcount, size_t smem_optin, int *col_slice_cap);
+int cluster_max_clusters(int n, int m, int nnz, int col_slice_cap, int cluster_size);
 size_t cluster_scratch_bytes(int clusters);
 cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len);
 cudaError_t launch_densify(const double *vals, const int *outer, const int *inner, int nnz, int m, int n, int csr, int count,
