@@ -552,9 +552,10 @@ def main():
                              "DRAM traffic is far below this and frac can exceed 1 (see DESIGN.md)"},
         # the honest binding resource: fp64 FMA work against the chip's nominal fp64 vector rate
         "compute": {"flops_per_iteration": 4 * m * n + 2 * n * n, "achieved_tflops": (4 * m * n + 2 * n * n) * total_iters / sec_per_launch / 1e12,
-                    "peak_tflops": 148 * 64 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s fp64",
-                    "peak_source": "nominal: 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp64 entry)",
-                    "frac": (4 * m * n + 2 * n * n) * total_iters / sec_per_launch / (148 * 64 * 2 * 1.965e9)},
+                    "peak_tflops": 148 * 58.98 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s fp64",
+                    "peak_source": "measured: 58.98 DFMA/clk/SM x 148 SMs x 2 x 1.965 GHz (tools/proto/proto_lat.cu on this pool's B200; "
+                                   "nominal 64/clk; MEASURED_PEAKS.json has no fp64 entry)",
+                    "frac": (4 * m * n + 2 * n * n) * total_iters / sec_per_launch / (148 * 58.98 * 2 * 1.965e9)},
         "clocks": clocks,
     }
     if e2e is not None:
