@@ -125,6 +125,22 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b);
  * fp64. Meets the reference's own 1e-2 float test, not the 1e-6 parity bar of the fp64 path. */
 int sqpb200_qp_batch_set_precision(sqpb200_qp_batch *b, int fp32);
 
+/* ---- peer memory (multi-GPU, one process per GPU) --------------------------------------------------------------------------
+ * The batch axis shards with no exchange during the solve. For the strong-scaling flow of the north star (one batch
+ * owned by one rank, split over the GPUs, results gathered back) these helpers let every rank's solve kernel READ its slice of the
+ * inputs straight out of the owner's memory over NVLink (the kernel's TMA bulk copies and loads take the peer address) and WRITE its
+ * results straight into the owner's arrays (sqpb200_qp_batch_get with device pointers into the imported mapping): no separate split
+ * or gather step, the transfer overlaps the solve QP by QP. Buffers come from sqpb200_dev_alloc (so that a handle maps the whole
+ * allocation), are exported as 64-byte CUDA IPC handles, and imported by the other processes of the node. */
+#define SQPB200_IPC_HANDLE_BYTES 64
+int sqpb200_dev_alloc(sqpb200_ctx *ctx, size_t bytes, void **dev_ptr);
+int sqpb200_dev_free(sqpb200_ctx *ctx, void *dev_ptr);
+/* copy between any two of: host memory, this device's memory, imported peer memory (cudaMemcpyDefault), asynchronous on `stream` */
+int sqpb200_dev_copy(sqpb200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+int sqpb200_ipc_export(sqpb200_ctx *ctx, const void *dev_ptr, unsigned char handle[SQPB200_IPC_HANDLE_BYTES]);
+int sqpb200_ipc_import(sqpb200_ctx *ctx, const unsigned char handle[SQPB200_IPC_HANDLE_BYTES], void **dev_ptr);
+int sqpb200_ipc_release(sqpb200_ctx *ctx, void *dev_ptr);
+
 /* setup: zero x,z,y; classify constraints; rho vector from settings->rho (rho_updates += 1);
  * build and factor the KKT system; status = UNSOLVED or NUMERICAL_ISSUES. qp.cpp:11-44 */
 int sqpb200_qp_batch_setup(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,

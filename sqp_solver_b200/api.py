@@ -32,7 +32,8 @@ ABI_SYMBOLS = [
     "sqpb200_device_query", "sqpb200_launch_count", "sqpb200_last_kernel", "sqpb200_qp_default_settings",
     "sqpb200_constr_type_init", "sqpb200_qp_batch_create", "sqpb200_qp_batch_destroy", "sqpb200_qp_batch_setup",
     "sqpb200_qp_batch_update_qp", "sqpb200_qp_batch_solve", "sqpb200_qp_batch_setup_solve",
-    "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_set_precision", "sqpb200_qp_batch_get",
+    "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_set_precision", "sqpb200_dev_alloc", "sqpb200_dev_free", "sqpb200_dev_copy",
+    "sqpb200_ipc_export", "sqpb200_ipc_import", "sqpb200_ipc_release", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
     "sqpb200_qp_solve_batch",
 ]
@@ -91,6 +92,12 @@ def load_library(path=None):
     L.sqpb200_qp_batch_setup_solve_sparse.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, ip, ip, C.c_int, C.c_int, dp, dp,
                                                       C.c_uint, vp]
     L.sqpb200_qp_batch_set_precision.argtypes = [vp, C.c_int]
+    L.sqpb200_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.sqpb200_dev_free.argtypes = [vp, vp]
+    L.sqpb200_dev_copy.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.sqpb200_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.sqpb200_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.sqpb200_ipc_release.argtypes = [vp, vp]
     L.sqpb200_qp_batch_get.argtypes = [vp, C.c_int, dp, dp, dp, ip, ip, ip, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_set_iterates.argtypes = [vp, C.c_int, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_device_view.argtypes = [vp, C.POINTER(DeviceView)]
@@ -133,10 +140,25 @@ def _is_torch(a):
     return type(a).__module__.startswith("torch")
 
 
+class DevPtr:
+    """A raw device address (this GPU's memory from Context.dev_alloc, or a peer GPU's memory imported with Context.ipc_import)
+    usable wherever the API takes a CUDA tensor. `offset(elements)` advances by whole elements of `dtype`."""
+
+    def __init__(self, ptr, dtype=np.float64):
+        self.ptr, self.dtype = int(ptr), np.dtype(dtype)
+
+    def offset(self, elements):
+        return DevPtr(self.ptr + int(elements) * self.dtype.itemsize, self.dtype)
+
+
 def _ptr_and_space(a, dtype, what):
     """(address, DEVICE_PTRS|HOST_PTRS) of a contiguous numpy array or torch tensor."""
     if a is None:
         return None, None
+    if isinstance(a, DevPtr):
+        if a.dtype != np.dtype(dtype):
+            raise SolverError("%s: DevPtr of dtype %s, need %s" % (what, a.dtype, np.dtype(dtype)))
+        return a.ptr, DEVICE_PTRS
     if _is_torch(a):
         import torch
 
@@ -178,6 +200,36 @@ class Context:
 
     def set_option(self, option, value):
         self._check(self._L.sqpb200_ctx_set_option(self._h, option, value), "set_option")
+
+    # ---- raw device buffers and CUDA IPC (peer memory over NVLink; see include/sqp_b200_qp.h) ----
+    def dev_alloc(self, nbytes, dtype=np.float64):
+        p = C.c_void_p()
+        self._check(self._L.sqpb200_dev_alloc(self._h, int(nbytes), C.byref(p)), "dev_alloc")
+        return DevPtr(p.value, dtype)
+
+    def dev_free(self, dp):
+        self._check(self._L.sqpb200_dev_free(self._h, C.c_void_p(dp.ptr)), "dev_free")
+
+    def dev_copy(self, dst, src, nbytes, stream=None):
+        """dst/src: DevPtr, CUDA tensor or contiguous numpy array; asynchronous on `stream`."""
+        def addr(a):
+            if isinstance(a, DevPtr):
+                return a.ptr
+            return a.data_ptr() if _is_torch(a) else a.ctypes.data
+        self._check(self._L.sqpb200_dev_copy(self._h, C.c_void_p(addr(dst)), C.c_void_p(addr(src)), int(nbytes), C.c_void_p(stream or 0)), "dev_copy")
+
+    def ipc_export(self, dp):
+        buf = C.create_string_buffer(64)
+        self._check(self._L.sqpb200_ipc_export(self._h, C.c_void_p(dp.ptr), buf), "ipc_export")
+        return buf.raw
+
+    def ipc_import(self, handle, dtype=np.float64):
+        p = C.c_void_p()
+        self._check(self._L.sqpb200_ipc_import(self._h, handle, C.byref(p)), "ipc_import")
+        return DevPtr(p.value, dtype)
+
+    def ipc_release(self, dp):
+        self._check(self._L.sqpb200_ipc_release(self._h, C.c_void_p(dp.ptr)), "ipc_release")
 
     def device_query(self):
         dev, sm, ma, mi, sz = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_size_t()

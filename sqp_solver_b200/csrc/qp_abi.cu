@@ -192,6 +192,51 @@ int sqpb200_device_query(const sqpb200_ctx *c, int *device, int *sm_count, int *
 long long sqpb200_launch_count(const sqpb200_ctx *c) { return c ? c->launches : 0; }
 const char *sqpb200_last_kernel(const sqpb200_ctx *c) { return c ? c->last_kernel : "none"; }
 
+int sqpb200_dev_alloc(sqpb200_ctx *c, size_t bytes, void **dev_ptr) {
+    if (!c || !dev_ptr) return SQPB200_ERR_INVALID;
+    *dev_ptr = nullptr;
+    CK(c, cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(dev_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "sqpb200_dev_alloc", e);
+    return SQPB200_OK;
+}
+int sqpb200_dev_free(sqpb200_ctx *c, void *dev_ptr) {
+    if (!c) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (dev_ptr) CK(c, cudaFree(dev_ptr));
+    return SQPB200_OK;
+}
+int sqpb200_dev_copy(sqpb200_ctx *c, void *dst, const void *src, size_t bytes, void *stream) {
+    if (!c || (bytes && (!dst || !src))) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (bytes) CK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return SQPB200_OK;
+}
+int sqpb200_ipc_export(sqpb200_ctx *c, const void *dev_ptr, unsigned char handle[SQPB200_IPC_HANDLE_BYTES]) {
+    if (!c || !dev_ptr || !handle) return SQPB200_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == SQPB200_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    CK(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, sizeof h);
+    return SQPB200_OK;
+}
+int sqpb200_ipc_import(sqpb200_ctx *c, const unsigned char handle[SQPB200_IPC_HANDLE_BYTES], void **dev_ptr) {
+    if (!c || !handle || !dev_ptr) return SQPB200_ERR_INVALID;
+    *dev_ptr = nullptr;
+    CK(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CK(c, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SQPB200_OK;
+}
+int sqpb200_ipc_release(sqpb200_ctx *c, void *dev_ptr) {
+    if (!c) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (dev_ptr) CK(c, cudaIpcCloseMemHandle(dev_ptr));
+    return SQPB200_OK;
+}
+
 int sqpb200_qp_batch_set_precision(sqpb200_qp_batch *b, int fp32) {
     if (!b) return SQPB200_ERR_INVALID;
     if (fp32 != 0 && fp32 != 1) return fail(b->ctx, SQPB200_ERR_INVALID, "sqpb200_qp_batch_set_precision: 0 (fp64) or 1 (fp32)");

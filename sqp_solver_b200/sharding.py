@@ -112,3 +112,88 @@ def gpu_solve_local(qbatch):
             qbatch.get_into(count=cnt, **res)
         return res
     return run
+
+
+# ---- strong scaling without a split/gather step: peer memory over NVLink -------------------------------------------------
+class PeerBatch:
+    """One batch owned by rank `root`, solved by all the GPUs of the node with NO data-path collective and no staging copy:
+    the owner's input arrays and result arrays are shared with the other processes as CUDA IPC mappings, every rank's solve kernel
+    reads its slice of P, q, A, l, u straight out of the owner's HBM over NVLink (the kernel's TMA bulk copies take the peer
+    address, so the transfer overlaps the solve QP by QP) and its results go straight into the owner's arrays (device-to-peer
+    copies issued by sqpb200_qp_batch_get). torch.distributed is used for the handle exchange and the closing barrier only.
+
+        pb = PeerBatch(ctx, n, m, batch, root=0)      # collective: allocates on root, exchanges handles
+        pb.load(problem)                              # root: dict of CUDA tensors P,q,A,l,u -> the shared input arrays
+        pb.solve(qbatch, stream)                      # every rank: solve its slice (asynchronous on `stream`)
+        out = pb.results()                            # root: dict of CUDA tensors (after a barrier)
+    """
+
+    IN_WIDTH = lambda self, k: dict(P=self.n * self.n, q=self.n, A=self.m * self.n, l=self.m, u=self.m)[k]
+
+    def __init__(self, ctx, n, m, batch, root=0):
+        import numpy as np
+
+        from . import api
+
+        self.ctx, self.n, self.m, self.batch, self.root = ctx, n, m, batch, root
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.lo, self.hi = shard_range(batch, self.rank, self.world)
+        self._np = {torch.float64: np.float64, torch.int32: np.int32}
+        self.out_width = dict(x=n, y=m, z=m, status=1, iter=1, rho_updates=1, rho_estimate=1, res_prim=1, res_dual=1)
+        names = [("in", k) for k in PROBLEM_KEYS] + [("out", k) for k in RESULT_DTYPES]
+        self.buf = {}
+        handles = [None]
+        if self.rank == root:
+            hs = {}
+            for kind, k in names:
+                dt = np.float64 if kind == "in" else self._np[RESULT_DTYPES[k]]
+                width = self.IN_WIDTH(k) if kind == "in" else self.out_width[k]
+                self.buf[(kind, k)] = ctx.dev_alloc(batch * width * np.dtype(dt).itemsize, dt)
+                hs[(kind, k)] = ctx.ipc_export(self.buf[(kind, k)])
+            handles = [hs]
+        dist.broadcast_object_list(handles, src=root)
+        if self.rank != root:
+            for kind, k in names:
+                dt = np.float64 if kind == "in" else self._np[RESULT_DTYPES[k]]
+                self.buf[(kind, k)] = ctx.ipc_import(handles[0][(kind, k)], dt)
+        self._api = api
+
+    def load(self, problem, stream=None):
+        if self.rank == self.root:
+            for k in PROBLEM_KEYS:
+                t = problem[k].contiguous()
+                self.ctx.dev_copy(self.buf[("in", k)], t, t.numel() * 8, stream)
+
+    def solve(self, qbatch, stream=None):
+        cnt = self.hi - self.lo
+        if cnt <= 0:
+            return
+        ins = [self.buf[("in", k)].offset(self.lo * self.IN_WIDTH(k)) for k in PROBLEM_KEYS]
+        qbatch.setup_solve(*ins, count=cnt, stream=stream)
+        outs = {k: self.buf[("out", k)].offset(self.lo * self.out_width[k]) for k in RESULT_DTYPES}
+        qbatch.get_into(count=cnt, stream=stream, **outs)
+
+    def results(self):
+        """Barrier, then (root) the whole-batch results as CUDA tensors."""
+        torch.cuda.synchronize()
+        dist.barrier()
+        if self.rank != self.root:
+            return None
+        out = {}
+        for k, dt in RESULT_DTYPES.items():
+            w = self.out_width[k]
+            t = torch.empty((self.batch, w) if k in ("x", "y", "z") else (self.batch,), dtype=dt, device="cuda")
+            self.ctx.dev_copy(t, self.buf[("out", k)], t.numel() * t.element_size())
+            out[k] = t
+        torch.cuda.synchronize()
+        return out
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier()
+        for key, dp in self.buf.items():
+            if self.rank == self.root:
+                self.ctx.dev_free(dp)
+            else:
+                self.ctx.ipc_release(dp)
+        self.buf = {}
