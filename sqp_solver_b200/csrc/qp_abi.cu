@@ -398,7 +398,10 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
 
     // kernel choice: register-tiled (n <= 64, m <= 128) > blocked (n <= 256, m <= 1024) > generic (anything that fits)
     const size_t optin = c->prop.sharedMemPerBlockOptin;
-    const bool want_tile = !sp && c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
+    // settings.verbose (the reference's per-check status line, qp.cpp:114-118 / :375-382) is a debugging aid: such calls take the generic
+    // kernel, the one that prints it, so the fast kernels carry no printf in their loops
+    const bool verbose_generic = st->verbose && !sp && c->opt_kernel == 0 && generic_supported(b->n, b->m, optin);
+    const bool want_tile = !sp && !verbose_generic && c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
     // sparse A: a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
     int clusters = 0;
     if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && sp->cluster_size > 0 && mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE))
@@ -410,7 +413,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
         clusters = 0;
     if (c->opt_kernel == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
     const bool want_cluster = clusters >= 1;
-    const bool want_block = !want_cluster && (sp || (!want_tile && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin)));
+    const bool want_block = !want_cluster && (sp || (!want_tile && !verbose_generic && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin)));
     if (c->opt_kernel == 2 && !want_tile) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
     if (c->opt_kernel == 3 && !want_block) return fail(c, SQPB200_ERR_UNSUPPORTED, "blocked kernel forced but (n, m) is outside its range");
     const bool needs_fact = !want_cluster && (!want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE)));
@@ -632,7 +635,7 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         else for (int j = 0; j < b->n; ++j) colcount[j] = h_outer[j + 1] - h_outer[j];
         cluster_size = cluster_plan(b->n, b->m, nnz, colcount.data(), c->prop.sharedMemPerBlockOptin, &col_slice_cap);
     }
-    const bool sparse_kernel = (c->opt_kernel == 0 || c->opt_kernel == 3 || c->opt_kernel == 4) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
+    const bool sparse_kernel = !(s->verbose && c->opt_kernel == 0) && (c->opt_kernel == 0 || c->opt_kernel == 3 || c->opt_kernel == 4) && !(c->opt_kernel == 0 && tile_supported(b->n, b->m)) &&
                                m > 0 && (block_sparse_supported(b->n, b->m, nnz, c->prop.sharedMemPerBlockOptin) || cluster_size > 0);
     auto copy_instances = [&](cudaStream_t cs, size_t lo, size_t cnt) -> cudaError_t {
         cudaError_t e = cudaSuccess;

@@ -8,6 +8,8 @@
 // form_KKT_rhs :272-276, box_projection :278-281, constr_type_init :283-294,
 // rho_vec_update :296-314, update_state :316-331, rho_estimate :333-341,
 // eps_prim/eps_dual :343-351, residual_prim/dual :353-361, termination_criteria :363-371.
+#include <cstdio>
+
 #include "qp_common.cuh"
 
 namespace sqpb200 {
@@ -255,6 +257,18 @@ __global__ void __launch_bounds__(GT) qp_generic_kernel(KernelParams p) {
                     const double sc_d = fmax(mx[2], fmax(mx[3], mx[4]));
                     res_prim = mx[5];
                     res_dual = mx[6];
+                    if (chk && st.verbose && local == 0) {  // print_status, qp.cpp:114-118 and :375-382 (first instance of the launch only)
+                        if (tid == 0) {
+                            double obj = 0.0;
+                            for (int j = 0; j < n; ++j) {
+                                double pxj = 0.0;
+                                for (int k = 0; k < n; ++k) pxj += P[j + (size_t)n * k] * s.x[k];
+                                obj += s.x[j] * (0.5 * pxj + s.q[j]);
+                            }
+                            if (iter == st.check_termination) printf("iter   obj       rp        rd\n");
+                            printf("%4d  %.2e  %.2e  %.2e\n", iter, obj, res_prim, res_dual);
+                        }
+                    }
                     if (chk) {  // termination_criteria, qp.cpp:363-371
                         if (res_prim <= st.eps_abs + st.eps_rel * sc_p && res_dual <= st.eps_abs + st.eps_rel * sc_d) {
                             status = SQPB200_SOLVED;

@@ -854,3 +854,31 @@ def test_cluster_and_fp32_against_committed_golden_outputs(api, ctx):
         rel = np.linalg.norm(out["x"] - np.array(c["x"]), axis=1) / np.linalg.norm(np.array(c["x"]), axis=1)
         assert rel.max() < 1e-4, (c["name"], rel)
         b.close()
+
+
+def test_verbose_prints_the_reference_status_lines():
+    """settings.verbose: the per-check status line of the reference (print_status, qp.cpp:375-382: a header at the first check, then
+    `iter obj rp rd` with "%4d  %.2e  %.2e  %.2e") comes from the device; SimpleQP with default settings checks at 25, 50, ..., 125."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np\n"
+        "from sqp_solver_b200 import api\n"
+        "ctx = api.Context(0)\n"
+        "b = api.QPBatch(ctx, 1, 2, 3)\n"
+        "b.settings = api.default_settings(verbose=1)\n"
+        "P = np.array([[4., 1., 1., 2.]]); q = np.array([[1., 1.]]); A = np.array([[1., 1., 0., 1., 0., 1.]])\n"
+        "b.setup_solve(P, q, A, np.array([[1., 0., 0.]]), np.array([[1., .7, .7]]))\n"
+        "o = b.get(); print('KERNEL', ctx.last_kernel, int(o['iter'][0]), int(o['status'][0]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "iter   obj       rp        rd"
+    rows = [ln for ln in lines[1:] if not ln.startswith("KERNEL")]
+    assert [int(ln.split()[0]) for ln in rows] == [25, 50, 75, 100, 125]
+    assert all(len(ln.split()) == 4 and "e" in ln.split()[1] for ln in rows)
+    assert abs(float(rows[-1].split()[1]) - 1.88) < 0.02  # objective of SimpleQP at [0.3, 0.7]: 0.5 x'Px + q'x = 1.88
+    assert "KERNEL generic 125 0" in lines[-1]
