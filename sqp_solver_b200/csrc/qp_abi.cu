@@ -55,7 +55,6 @@ struct sqpb200_qp_batch {
     int sp_nnz_cap = 0;
     int *sp2_outer = nullptr, *sp2_inner = nullptr, *sp2_perm = nullptr;  // the other compressed view of the pattern
     unsigned long long sp_hash = 0;  // hash of the pattern whose derived views (sp2_*, sp_pack) are on the device; 0 = none
-    int sp_col_slice_cap = 0;
     double *cl_scratch = nullptr;  // cluster kernel: per-cluster exchange buffers (owned by the batch object: launches of different
     size_t cl_scratch_bytes = 0;   // batch objects may overlap on different streams)
     unsigned *sp_pack = nullptr;  // [2][cap]: packed (index | value position << 10) entries of the CSC and the CSR view (cluster kernel)

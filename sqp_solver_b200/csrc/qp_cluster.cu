@@ -659,9 +659,10 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                         mx[0] = fabs(ax);
                         mx[1] = fabs(zr);
                         mx[5] = fabs(ax - zr);
+                        if (row_half == 0) {
 #pragma unroll
-                        if (row_half == 0)
                             for (int r = 0; r < CS; ++r) peer_sw[r][my_row] = yr;  // all-gather y (w is rebuilt next iteration)
+                        }
                     }
                     // P x for the rows of the own slice: partial sums over CT / RS column groups
                     {
