@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 const int k0l = kb * KB - (kb * KB / RS) * RS;
                 double *scrR = scr_base + (size_t)(kb & 1) * SCR1;
                 for (int e = t; e < KB * np; e += nthr) scrR[e] = s.S[(k0l + (e % KB)) + LD * (e / KB)];
-                // (no fence: the cluster barrier that ends the step is a release/acquire at cluster scope for these global writes)
+                __threadfence();  // belt and braces: the cluster barrier that ends the step is already a release/acquire at cluster scope
             };
             // Symmetric sweep of the 32 x 32 pivot block of block kb by ONE warp, a row per lane in registers (the 32 pivots are a
             // serial chain: a CTA-wide version pays a barrier per pivot), published as E^-1 with the failure flag. Per pivot the lanes
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
 #pragma unroll
                 for (int j = 0; j < KB; ++j) scrE[lane + KB * j] = bad ? 0.0 : -row[j];
                 if (lane == 0) scrF[0] = bad ? 1.0 : 0.0;
+                __threadfence();
             };
             // rank-32 update S[rows of block rb, j] <- S - T R[:, j] on the fp64 tensor cores for the column groups g0, g0 + gstep, ...
             // (a group = four 8-column tiles = four independent DMMA chains); the pivot rows R of step kb are staged chunk by chunk
