@@ -883,3 +883,23 @@ def test_verbose_prints_the_reference_status_lines():
     assert all(len(ln.split()) == 4 and "e" in ln.split()[1] for ln in rows)
     assert abs(float(rows[-1].split()[1]) - 1.88) < 0.02  # objective of SimpleQP at [0.3, 0.7]: 0.5 x'Px + q'x = 1.88
     assert "KERNEL generic 125 0" in lines[-1]
+
+
+@pytest.mark.parametrize("kernel,n", [("tile", 5), ("tile", 64), ("generic", 12), ("block", 80), ("auto", 130)])
+def test_unconstrained_qp_m_zero(api, ctx, oracle, kernel, n):
+    """m = 0 (no constraint rows: Eigen handles the 0 x n matrices of the reference transparently): every kernel returns the
+    oracle's result -- SOLVED at the first check with x = -P^-1 q."""
+    rng = np.random.default_rng(50 + n)
+    B = 3
+    M = rng.standard_normal((B, n, n)) / np.sqrt(n)
+    P = np.einsum("bij,bkj->bik", M, M) + 0.1 * np.eye(n)
+    d = dict(P=np.ascontiguousarray(P.transpose(0, 2, 1).reshape(B, n * n)), q=rng.standard_normal((B, n)), A=np.zeros((B, 0)),
+             l=np.zeros((B, 0)), u=np.zeros((B, 0)), n=n, m=0, batch=B)
+    out = run_fused(api, ctx, d, api.default_settings(), kernel)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"])
+    assert (ref["status"] == api.SOLVED).all() and (ref["iter"] == 25).all()
+    np.testing.assert_array_equal(out["status"], ref["status"])
+    np.testing.assert_array_equal(out["iter"], ref["iter"])
+    xs = np.stack([-np.linalg.solve(P[i], d["q"][i]) for i in range(B)])
+    assert np.abs(out["x"] - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
+    assert np.abs(out["x"] - xs).max() <= 1e-4 * np.abs(xs).max()
