@@ -903,3 +903,44 @@ def test_unconstrained_qp_m_zero(api, ctx, oracle, kernel, n):
     xs = np.stack([-np.linalg.solve(P[i], d["q"][i]) for i in range(B)])
     assert np.abs(out["x"] - ref["x"]).max() <= 1e-9 * np.abs(ref["x"]).max()
     assert np.abs(out["x"] - xs).max() <= 1e-4 * np.abs(xs).max()
+
+
+def test_full_size_properties_config5(api, ctx, oracle):
+    """BASELINE config 5 at full size (batch 2048 sparse-A QPs, n=256, m=512, one CSR pattern, SQP settings) through the cluster
+    kernel: size-independent properties on every instance (the termination test recomputed independently in torch fp64 from the
+    returned x, z, y; z inside the box; iteration counts on the check grid) plus oracle parity on a seeded sample."""
+    import torch
+    from sqp_solver_b200.synth import densify, make_sparse_batch
+
+    B, n, m = 2048, 256, 512
+    d = make_sparse_batch(B, n, m, density=0.03, seed0=0)
+    s = api.default_settings(alpha=1.6, adaptive_rho=1)
+    b = api.QPBatch(ctx, B, n, m)
+    b.settings = s
+    b.setup_solve_sparse(d["P"], d["q"], d["vals"], d["outer"], d["inner"], d["l"], d["u"], layout=api.SPARSE_CSR)
+    out = b.get()
+    assert ctx.last_kernel.startswith("cluster<4>"), ctx.last_kernel
+    assert (out["status"] == api.SOLVED).all()
+    assert (out["iter"] % 25 == 0).all() and out["iter"].max() <= 1000
+    P = torch.from_numpy(d["P"]).cuda().view(B, n, n).transpose(1, 2)
+    A = torch.zeros(B, m, n, dtype=torch.float64, device="cuda")
+    A[:, torch.from_numpy(d["rows"]).cuda(), torch.from_numpy(d["cols"]).cuda()] = torch.from_numpy(d["vals"]).cuda()
+    q = torch.from_numpy(d["q"]).cuda()
+    x, y, z = (torch.from_numpy(out[k]).cuda() for k in ("x", "y", "z"))
+    Ax = torch.bmm(A, x.unsqueeze(2)).squeeze(2)
+    Px = torch.bmm(P, x.unsqueeze(2)).squeeze(2)
+    Aty = torch.bmm(A.transpose(1, 2), y.unsqueeze(2)).squeeze(2)
+    rp, rd = (Ax - z).abs().amax(1), (Px + q + Aty).abs().amax(1)
+    ep = s.eps_abs + s.eps_rel * torch.maximum(Ax.abs().amax(1), z.abs().amax(1))
+    ed = s.eps_abs + s.eps_rel * torch.maximum(torch.maximum(Px.abs().amax(1), Aty.abs().amax(1)), q.abs().amax(1))
+    assert bool(((rp <= ep * (1 + 1e-9)) & (rd <= ed * (1 + 1e-9))).all())
+    np.testing.assert_allclose(out["res_prim"], rp.cpu().numpy(), rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(out["res_dual"], rd.cpu().numpy(), rtol=1e-6, atol=1e-10)
+    l, u = torch.from_numpy(d["l"]).cuda(), torch.from_numpy(d["u"]).cuda()
+    assert bool(((z >= l) & (z <= u)).all())
+    idx = np.random.default_rng(321).choice(B, 6, replace=False)
+    sub_d = dict(d, vals=d["vals"][idx], batch=len(idx))
+    ref = oracle.solve_batch(d["P"][idx], d["q"][idx], densify(sub_d), d["l"][idx], d["u"][idx], oracle_settings_from(oracle, s))
+    sub = {k: v[idx] for k, v in out.items() if isinstance(v, np.ndarray)}
+    assert_parity({k: sub[k] for k in ("status", "iter", "x", "y")}, {k: ref[k] for k in ("status", "iter", "x", "y")}, what="config 5 sample")
+    b.close()
