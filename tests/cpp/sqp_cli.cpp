@@ -80,5 +80,9 @@ int main(int argc, char **argv) {
         SimpleNLP2 p; SQP<double> s;
         s.solve(p, v2(1.2, 0.1), zeros(1)); report("SimpleNLP2", s);
     }
+    {
+        RosenbrockBox p(2); SQP<double> s; s.settings().max_iter = 100;
+        s.solve(p, zeros(2), zeros(2)); report("RosenbrockBox2", s);
+    }
     return 0;
 }

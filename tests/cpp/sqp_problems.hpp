@@ -87,6 +87,34 @@ struct SimpleNLP2 : public NonLinearProblem<double> {  // N&W example 12.1, test
     }
 };
 
+struct RosenbrockBox : public NonLinearProblem<double> {  // `Rosenbrock`, tests/sqp_test_autodiff.cpp:61-71 and :122-144: 0 <= x <= 1
+    explicit RosenbrockBox(int n) { num_var = n; num_constr = n; }
+    void objective(const Vec &x, double &obj) override {
+        obj = 0;
+        for (int i = 0; i < num_var - 1; ++i) {
+            const double a = 1 - x(i), b = x(i + 1) - x(i) * x(i);
+            obj += a * a + 100 * b * b;
+        }
+    }
+    void objective_linearized(const Vec &x, Vec &grad, double &obj) override {
+        objective(x, obj);
+        for (int i = 0; i < num_var; ++i) grad(i) = 0;
+        for (int i = 0; i < num_var - 1; ++i) {
+            const double b = x(i + 1) - x(i) * x(i);
+            grad(i) += -2 * (1 - x(i)) - 400 * x(i) * b;
+            grad(i + 1) += 200 * b;
+        }
+    }
+    void constraint(const Vec &x, Vec &c, Vec &l, Vec &u) override {
+        for (int i = 0; i < num_var; ++i) { c(i) = x(i); l(i) = 0; u(i) = 1; }
+    }
+    void constraint_linearized(const Vec &x, Mat &Jc, Vec &c, Vec &l, Vec &u) override {
+        constraint(x, c, l, u);
+        for (int j = 0; j < num_var; ++j)
+            for (int i = 0; i < num_var; ++i) Jc(i, j) = i == j ? 1.0 : 0.0;
+    }
+};
+
 static Vec v2(double a, double b) { Vec v(2); v(0) = a; v(1) = b; return v; }
 static Vec zeros(int n) { Vec v(n); v.setZero(); return v; }
 
