@@ -44,6 +44,16 @@ def test_all_cpp_tests_compile():
         compile_cpp(name)
 
 
+def test_host_mirror_is_cxx11_like_the_reference():
+    """The reference builds with CMAKE_CXX_STANDARD 11 (CMakeLists.txt): the header-only mirror of its interface
+    (solvers/qp.hpp, sqp.hpp, bfgs.hpp) and every C++ test must compile in that mode, warning-free, so that src/sqp.cpp can include it."""
+    libdir = os.path.join(ROOT, "sqp_solver_b200")
+    for name in ("test_qp_solver", "test_sqp", "test_bfgs", "sqp_cli"):
+        r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-Wall", "-Wextra", "-fsyntax-only", "-I" + os.path.join(libdir, "host"),
+                            os.path.join(CPP, name + ".cpp")], capture_output=True, text=True)
+        assert r.returncode == 0 and "warning" not in r.stderr, name + "\n" + r.stderr
+
+
 def test_bfgs_oracle_keeps_posdef(oracle):
     """Oracle restatement of bfgs.hpp:15-41 keeps B positive definite under arbitrary curvature pairs."""
     from oracle import sqp_oracle
