@@ -177,8 +177,20 @@ def run_reference(args, rank, world):
 
     O.build()
     cores = O.num_procs()
-    sample = args.cpu_sample or min(args.batch, 64 * cores)
-    d = make_batch(sample, args.n, args.m, seed0=0)
+    metric, wl = METRIC, "configs[%d]: batch=%d dense QPs n=%d m=%d fp64" % (1 if args.workload == "config2" else 2, args.batch, args.n, args.m)
+    if args.workload == "config5":  # sparse A, densified for the CPU path (the reference's sparse variant is dead code)
+        from sqp_solver_b200.synth import densify, make_sparse_batch
+
+        sample = args.cpu_sample or min(args.batch, 2 * cores)
+        d = make_sparse_batch(sample, args.n, args.m, density=args.density, seed0=0)
+        d["A"] = densify(d)
+        metric = "QP-subproblems/sec (batch=%d, n=%d, m=%d, sparse A nnz=%d)" % (args.batch, args.n, args.m, d["nnz"])
+        wl = "configs[4]: batch=%d sparse-A QPs n=%d m=%d fp64 (densified for the CPU path)" % (args.batch, args.n, args.m)
+    else:
+        sample = args.cpu_sample or min(args.batch, 64 * cores)
+        d = make_batch(sample, args.n, args.m, seed0=0)
+        if (args.batch, args.n, args.m) != WORKLOADS["config3"]:
+            metric = "QP-subproblems/sec (batch=%d, n=%d, m=%d)" % (args.batch, args.n, args.m)
     st = O.default_settings(**settings_kwargs(args.settings))
     for _ in range(max(1, min(args.warmup, 1))):
         O.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], st, nthreads=cores)
@@ -189,11 +201,10 @@ def run_reference(args, rank, world):
         its += int(np.minimum(out["iter"], st.max_iter).sum())
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[2]: batch=8192 dense QPs n=%d m=%d fp64, settings %s; each step is a bounded "
-                                   "sample of %d QPs of that batch on host cores" % (args.n, args.m, args.settings, sample)},
+            "config": {"workload": "%s, settings %s; each step is a bounded sample of %d QPs of that batch on host cores" % (wl, args.settings, sample)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d QPs per step, gcc -O2 oracle restatement of src/qp.cpp (Eigen absent from the image, "
                                        "so the reference cannot be compiled), OpenMP over %d threads" % (sample, out["threads"])},
