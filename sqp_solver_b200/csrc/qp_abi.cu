@@ -239,7 +239,12 @@ int sqpb200_ipc_release(sqpb200_ctx *c, void *dev_ptr) {
 int sqpb200_qp_batch_set_precision(sqpb200_qp_batch *b, int fp32) {
     if (!b) return SQPB200_ERR_INVALID;
     if (fp32 != 0 && fp32 != 1) return fail(b->ctx, SQPB200_ERR_INVALID, "sqpb200_qp_batch_set_precision: 0 (fp64) or 1 (fp32)");
-    if (b->f32 != fp32) b->fact_valid = false;  // a factor stored by the other instantiation is not this one's
+    if (b->f32 != fp32) {  // a factor stored by the other instantiation is not this one's: forget it (separate solve() and REUSE_FACTOR)
+        b->fact_valid = false;
+        CK(b->ctx, cudaSetDevice(b->ctx->device));
+        CK(b->ctx, cudaDeviceSynchronize());
+        CK(b->ctx, cudaMemset(b->fact_rho, 0xff, (size_t)b->batch * sizeof(double)));  // all-ones bit pattern is a NaN: no factor stored
+    }
     b->f32 = fp32;
     return SQPB200_OK;
 }
