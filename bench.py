@@ -6,8 +6,12 @@
 
 A "step" is one pass of the hot path (fresh setup + ADMM solve, reference src/sqp.cpp:221-222)
 over one batch of synthetic QPs: BASELINE.json configs[2], batch=8192 dense QPs n=64 m=128 fp64,
-reference default settings. One process per GPU (torchrun for N>1); the batch axis is sharded
-with no data-path collective (weak scaling: every rank solves its own 8192 QPs).
+reference default settings. One process per GPU (torchrun for N>1).
+  N = 1: the batch is resident in HBM; `extra` carries the other regimes and configs (S2, config 2, config 5) measured in the same run.
+  N > 1: the north star's flow -- ONE batch of 8192 owned by rank 0 is solved by all N GPUs (strong scaling): every rank's solve
+         kernel pulls its slice out of rank 0's HBM over NVLink and writes its results into rank 0's arrays (no split/gather step;
+         `--transport nccl` runs the literal NCCL split -> solve -> NCCL gather instead). The weak-scaling figure (every rank its
+         own 8192 QPs, no data-path traffic at all) rides along under `extra.weak`.
 
 Prints ONE JSON line (rank 0). Keys follow the driver's contract; see DESIGN.md section
 "Measurement" for how `roofline.achieved` is formed from the algorithmic bytes of SURVEY.md 8(d).
@@ -47,10 +51,11 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tile"])
     ap.add_argument("--tile-warps", type=int, default=0, choices=[0, 1, 2, 4, 8])
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default, the driver's contract): every rank solves its own batch. strong: ONE batch on rank 0 "
-                         "is split over the ranks with NCCL send/recv, solved, and gathered back (north star's split/gather)")
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"],
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="auto (default): strong when N > 1 -- ONE batch on rank 0 solved by all ranks, the north star's split/gather "
+                         "flow -- with the weak figure under extra.weak. weak: every rank solves its own batch and nothing else")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (S2, config 2, config 5, weak) of the default line")
+    ap.add_argument("--transport", default="p2p", choices=["nccl", "p2p"],
                     help="--scaling strong only. nccl: split with NCCL send/recv, solve, gather with NCCL. p2p: no split/gather step at all -- "
                          "every rank's solve kernel reads its slice out of rank 0's HBM over NVLink (CUDA IPC mapping, TMA from peer "
                          "memory) and writes its results into rank 0's arrays")
@@ -213,73 +218,40 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def run_strong(args, rank, world, ctx, api, d, settings):
-    """Strong scaling: rank 0 owns the whole batch; NCCL send/recv splits it, each rank solves its slice,
-    NCCL gathers x, y, z and the info arrays back to rank 0. The split and gather are inside the timed region."""
-    import torch
-    import torch.distributed as dist
-
-    from sqp_solver_b200 import sharding
-
-    B, n, m = args.batch, args.n, args.m
-    lo, hi = sharding.shard_range(B, rank, world)
-    qb = api.QPBatch(ctx, max(hi - lo, 1), n, m)
-    qb.settings = settings
-    prob = {k: torch.from_numpy(d[k]).cuda() for k in sharding.PROBLEM_KEYS} if rank == 0 else None
-    solve_local = sharding.gpu_solve_local(qb)
-    stream = torch.cuda.current_stream()
-    pb = None
-    if args.transport == "p2p":
-        pb = sharding.PeerBatch(ctx, n, m, B, root=0)
-        pb.load(prob, stream=stream.cuda_stream)  # the batch is resident in rank 0's HBM before the timed region, as in the nccl flow
-        torch.cuda.synchronize()
-        dist.barrier()
-
-    def step():
-        if pb is None:
-            return sharding.solve_sharded(prob, n, m, B, solve_local, root=0)
-        pb.solve(qb, stream=stream.cuda_stream)
-        return None
-
-    for _ in range(args.warmup):
-        out = step()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        out = step()
-    ev1.record(stream)
-    dist.barrier()
-    torch.cuda.synchronize()
-    if pb is not None:
-        out = pb.results()
-        if rank == 0:  # same answers as a plain single-GPU solve of the first shard
-            chk = api.QPBatch(ctx, hi - lo, n, m)
-            chk.settings = settings
-            chk.setup_solve(*[prob[k][lo:hi].contiguous() for k in sharding.PROBLEM_KEYS])
-            ref = chk.get(fields=("x", "iter"))
-            assert (out["iter"][lo:hi].cpu().numpy() == ref["iter"]).all() and (out["x"][lo:hi].cpu().numpy() == ref["x"]).all()
-            chk.close()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        ms = float(t.item())
-        its = int(torch.clamp(out["iter"], max=settings.max_iter).sum().item())
-        print(json.dumps({"metric": METRIC, "value": B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": ("configs[2]: ONE batch=%d n=%d m=%d on rank 0, NCCL split -> solve -> NCCL gather (both inside the "
-                                                  "timed region)" if pb is None else "configs[2]: ONE batch=%d n=%d m=%d in rank 0's HBM; every rank's solve "
-                                                  "kernel reads its slice over NVLink (CUDA IPC peer mapping, TMA from peer memory) and writes its "
-                                                  "results into rank 0's arrays: no split/gather step, no collective") % (B, n, m),
-                                     "kernel": ctx.last_kernel, "transport": args.transport},
-                          "admm_iters_per_s": its / (ms / 1e3 / args.steps)}))
-    if pb is not None:
-        pb.close()
-
-
 WORKLOADS = {"config3": (8192, 64, 128), "config2": (1024, 32, 64), "config5": (2048, 256, 512)}
+
+
+def csrc_hash():
+    """Short hash of the kernel sources: ncu-derived constants under profiles/ (DRAM traffic per launch) are only quoted while the
+    sources they were captured from are unchanged."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "sqp_solver_b200", "csrc", "*.cu*"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def traffic_for(key):
+    """(bytes per launch or None, note). profiles/traffic.json maps a workload key to {"bytes": dram bytes of one launch from an
+    `ncu --set full` capture, "csrc": hash of the sources it was captured from}."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
+    except Exception:
+        e = None
+    if not isinstance(e, dict):
+        return None, "no ncu capture recorded for this workload"
+    if e.get("csrc") != csrc_hash():
+        return None, "stale: the ncu capture (%s) predates the current kernel sources" % e.get("capture", "?")
+    return float(e["bytes"]), "ncu --set full capture %s (dram__bytes_read.sum + dram__bytes_write.sum of the solve kernel, one launch)" % e.get("capture", "?")
+
+
+def algorithmic_flops(n, m, iters_executed, checks, factorizations):
+    """Least-work exact formulation ('flops per iteration: canonical 4mn + 2n^2'): per ADMM iteration A twice and the
+    n x n solve; per check A x, A^T y, P x; per (re)factorisation the SYRK A^T diag(rho) A (n^2 m) and chol(H) (n^3 / 3)."""
+    return (iters_executed + checks) * (4 * m * n + 2 * n * n) + factorizations * (n * n * m + n * n * n // 3)
 
 
 def sparse_algorithmic_bytes(n, m, nnz, iters_executed, checks, factorizations, count):
@@ -293,23 +265,295 @@ def sparse_algorithmic_bytes(n, m, nnz, iters_executed, checks, factorizations, 
     return count * b_io + iters_executed * b_iter + checks * b_check + factorizations * b_fact
 
 
-def run_config5(args, rank, world, local_rank):
-    """BASELINE.json configs[4]: sparse-A QPs (one CSR pattern for the batch) through sqpb200_qp_batch_setup_solve_sparse.
-    Same JSON keys as the headline line; weak scaling (every rank its own batch)."""
-    import torch
-    import torch.distributed as dist
+def fp64_peak(ctx):
+    """fp64 FMA peak of this GPU measured now (MEASURED_PEAKS.json carries HBM and bf16 only), with the SM clock it ran at."""
+    sampler = ClockSampler(ctx.device)
+    tf, sec, cnt = 0.0, 0.0, 0.0
+    for _ in range(6):  # ~60 ms of load so that nvidia-smi sees the clock
+        tf, sec, cnt = ctx.measure_fp64_peak()
+    clk = sampler.stop()
+    sms = ctx.device_query()["sm_count"]
+    out = {"peak_tflops": tf, "unit": "TFLOP/s fp64", "how": "sqpb200_measure_fp64_peak: saturating DFMA kernel (8 independent chains per "
+           "thread, 8 warps per scheduler), best of 4 launches, CUDA events", "sm_count": sms, "clocks": clk}
+    if clk.get("sm_mhz"):
+        out["dfma_per_clk_per_sm"] = cnt / sec / (clk["sm_mhz"] * 1e6) / sms
+    return out
 
-    from sqp_solver_b200 import api
+
+def counts_from_info(info, settings, api):
+    executed = np.minimum(info["iter"], settings.max_iter).astype(np.int64)
+    executed[info["status"] == api.NUMERICAL_ISSUES] = 0
+    ct = settings.check_termination
+    checks = int((executed // ct).sum()) if ct > 0 else 0
+    return int(executed.sum()), checks
+
+
+def rooflines(n, m, B, iters, checks, facts, sec, peak64, kernel, settings_name):
+    """(roofline bound by what binds -- the fp64 pipe --, the SURVEY 8(d) algorithmic-HBM figure beside it)."""
+    hbm_peak, hbm_src = peaks()
+    bytes_per_launch = algorithmic_bytes(n, m, iters, checks, facts, B)
+    flops = algorithmic_flops(n, m, iters, checks, facts)
+    traffic, traffic_note = traffic_for("%s_%dx%d_b%d_%s" % (kernel, n, m, B, settings_name))
+    ach = flops / sec / 1e12
+    roof = {"bound": "fp64", "achieved": ach, "peak": peak64["peak_tflops"], "unit": "TFLOP/s", "frac": ach / peak64["peak_tflops"],
+            "traffic": traffic, "traffic_note": traffic_note, "kernel_ms": 1e3 * sec, "algorithmic_flops_per_launch": flops,
+            "units_per_launch": {"qps": B, "admm_iterations": iters, "checks": checks, "factorisations": facts},
+            "peak_source": "measured in this run: " + peak64["how"],
+            "note": "the working set (A, H^-1, P) is register/shared-memory resident for the whole solve, so HBM carries the compulsory "
+                    "I/O only; the kernel is bound by the fp64 pipe and the shuffle/barrier latencies around it (DESIGN.md 4.1)"}
+    if traffic:
+        roof["dram_gbs"] = traffic / sec / 1e9
+        roof["dram_frac_of_hbm_peak"] = traffic / sec / 1e9 / hbm_peak
+        roof["traffic_over_compulsory_io"] = traffic / (B * (8 * (n * n + n + m * n + 2 * m) + 8 * (n + 2 * m) + 40))
+    hbm = {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+           "frac": bytes_per_launch / sec / 1e9 / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+           "note": "SURVEY.md 8(d) canonical bytes (B_iter = 16mn + 8n(n+1), B_check = 8(n^2+mn), B_io, 8(n^2+mn) per factorisation) x the "
+                   "units of one launch / kernel time: what an implementation streaming A and the factor from HBM every iteration would "
+                   "need; > 1 because nothing is streamed"}
+    return roof, hbm
+
+
+def time_device(qb, dev, stream, steps, warmup, barrier, torch):
+    """W untimed + K timed device-resident fused setup+solve launches. Returns (ms of the K steps on this rank, launches, last info,
+    factorisations per launch, ADMM iterations of the last launch)."""
+    def step():
+        qb.setup_solve(dev["P"], dev["q"], dev["A"], dev["l"], dev["u"], stream=stream.cuda_stream)
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    ru0 = int(qb.get(fields=("rho_updates",))["rho_updates"].astype(np.int64).sum())
+    l0 = qb.ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = qb.ctx.launch_count - l0
+    total_iters = qb.total_iters()
+    info = qb.get(fields=("status", "iter", "rho_updates"))
+    # rho_updates is cumulative over the calls on a batch object (qp.cpp:313): per launch = the timed region's increase / K
+    facts = (int(info["rho_updates"].astype(np.int64).sum()) - ru0) // max(steps, 1)
+    return ms, launches, info, facts, total_iters
+
+
+def time_e2e(qb, d, B, n, m, steps, warmup, barrier, torch, info=None):
+    """The same step through the reference-facing C-ABI call with HOST buffers: pinned host arrays -> sqpb200_qp_batch_setup_solve
+    (HOST_PTRS: one persistent launch gated on the chunk-by-chunk H2D staging) -> sqpb200_qp_batch_get to pinned host. Wall clock."""
+    pin = {k: torch.from_numpy(d[k][:B]).pin_memory() for k in ("P", "q", "A", "l", "u")}
+    hp = {k: v.numpy() for k, v in pin.items()}
+    ox = torch.empty(B, n, dtype=torch.float64).pin_memory()
+    oy = torch.empty(B, max(m, 1), dtype=torch.float64).pin_memory()[:, :m]
+    ost = torch.empty(B, dtype=torch.int32).pin_memory()
+    oit = torch.empty(B, dtype=torch.int32).pin_memory()
+    oy_np = np.ascontiguousarray(oy.numpy()) if m == 0 else oy.numpy()
+
+    def step():
+        qb.setup_solve(hp["P"], hp["q"], hp["A"], hp["l"], hp["u"], count=B)
+        qb.get_into(count=B, x=ox.numpy(), y=oy_np, status=ost.numpy(), iter=oit.numpy())
+
+    for _ in range(min(warmup, 2)):
+        step()
+    barrier()
+    l0 = qb.ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if info is not None:
+        assert (ost.numpy() == info["status"][:B]).all() and (oit.numpy() == info["iter"][:B]).all()
+    h2d = 8 * B * (n * n + n + m * n + 2 * m)
+    return dt, {"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * (8 * (n + m) + 8), "launches": qb.ctx.launch_count - l0,
+                "h2d_gbs_this_rank": h2d * steps / dt / 1e9}
+
+
+E2E_HOW = ("pinned host buffers -> sqpb200_qp_batch_setup_solve(HOST_PTRS): one persistent launch whose work queue is gated on the "
+           "chunk-by-chunk H2D staging -> sqpb200_qp_batch_get to pinned host; wall clock between device synchronisations, max over ranks")
+
+
+def dense_record(ctx, api, torch, B, n, m, settings_name, steps, warmup, peak64, seed0=0, d=None, cpu=True, cpu_sample=0, e2e=True):
+    """One single-GPU record of a dense workload (used for the headline at N = 1 and for the `extra` records)."""
+    from sqp_solver_b200.synth import make_batch
+
+    d = d if d is not None else make_batch(B, n, m, seed0=seed0)
+    settings = api.default_settings(**settings_kwargs(settings_name))
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")}
+    qb = api.QPBatch(ctx, B, n, m)
+    qb.settings = settings
+    stream = torch.cuda.current_stream()
+    barrier = torch.cuda.synchronize
+    sampler = ClockSampler(ctx.device)
+    ms, launches, info, facts, total_iters = time_device(qb, dev, stream, steps, warmup, barrier, torch)
+    kernel = ctx.last_kernel
+    sec = ms / 1e3 / steps
+    iters, checks = counts_from_info(info, settings, api)
+    roof, hbm = rooflines(n, m, B, iters, checks, facts, sec, peak64, kernel, settings_name)
+    rec = {"value": B / sec, "unit": UNIT, "ms_per_step": 1e3 * sec, "steps": steps, "warmup": warmup, "kernel": kernel,
+           "workload": "batch=%d dense QPs n=%d m=%d fp64, settings %s, fresh setup+solve per step, inputs resident in HBM (%.0f MB per step: %s)"
+                       % (B, n, m, settings_name, 8 * B * (n * n + n + m * n + 2 * m) / 1e6,
+                          "larger than the 126 MB L2" if 8 * B * (n * n + n + m * n + 2 * m) > 126e6 else "L2-resident across steps"),
+           "admm_iters_per_s": total_iters / sec, "admm_iters_per_step": total_iters, "factorisations_per_step": facts,
+           "status_histogram": {api.STATUS_NAMES[k]: int((info["status"] == k).sum()) for k in np.unique(info["status"])},
+           "gpu_launches": int(launches), "roofline": roof, "roofline_hbm_algorithmic": hbm}
+    if e2e:
+        dt, ex = time_e2e(qb, d, B, n, m, steps, warmup, barrier, torch, info)
+        rec["e2e"] = dict({"value": B * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps, "how": E2E_HOW}, **ex)
+    rec["clocks"] = sampler.stop()
+    if cpu:
+        rec["cpu_baseline"] = cpu_baseline(d, settings_name, cpu_sample)
+    qb.close()
+    return rec, d
+
+
+def run_strong(args, rank, world, local_rank, ctx, api, torch, dist):
+    """N > 1, the north star's flow: ONE batch (8192 QPs) owned by rank 0 is solved by all N GPUs.
+    p2p (default): every rank's solve kernel reads its slice from rank 0's HBM over NVLink (CUDA IPC peer mapping, TMA from peer
+    memory) and its epilogue writes the results into rank 0's arrays -- ONE kernel per rank per step, no split/gather step.
+    nccl: NCCL send/recv split -> local solve -> NCCL gather, all inside the timed region."""
+    from sqp_solver_b200 import sharding
+    from sqp_solver_b200.synth import make_batch
+
+    B, n, m = args.batch, args.n, args.m
+    settings = api.default_settings(**settings_kwargs(args.settings))
+    lo, hi = sharding.shard_range(B, rank, world)
+    # every rank generates its own full batch (weak extra); rank 0's (seed0 = 0) is THE batch of the strong flow
+    want_weak = not args.no_extras
+    d = make_batch(B, n, m, seed0=rank * B) if (rank == 0 or want_weak) else None
+    qb = api.QPBatch(ctx, max(hi - lo, 1) if not want_weak else B, n, m)
+    qb.settings = settings
+    prob = {k: torch.from_numpy(d[k]).cuda() for k in sharding.PROBLEM_KEYS} if rank == 0 else None
+    solve_local = sharding.gpu_solve_local(qb)
+    stream = torch.cuda.current_stream()
+    pb = None
+    if args.transport == "p2p":
+        pb = sharding.PeerBatch(ctx, n, m, B, root=0)
+        pb.load(prob, stream=stream.cuda_stream)  # the batch is resident in rank 0's HBM before the timed region, as in the nccl flow
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if pb is None:
+            return sharding.solve_sharded(prob, n, m, B, solve_local, root=0)
+        pb.solve(qb, stream=stream.cuda_stream)
+        return None
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        out = step()
+    ev1.record(stream)
+    barrier()
+    launches = ctx.launch_count - l0
+    kernel = ctx.last_kernel
+    if pb is not None:
+        out = pb.results()
+        if rank == 0:  # same answers as a plain single-GPU solve of the first shard
+            chk = api.QPBatch(ctx, hi - lo, n, m)
+            chk.settings = settings
+            chk.setup_solve(*[prob[k][lo:hi].contiguous() for k in sharding.PROBLEM_KEYS])
+            ref = chk.get(fields=("x", "iter"))
+            assert (out["iter"][lo:hi].cpu().numpy() == ref["iter"]).all() and (out["x"][lo:hi].cpu().numpy() == ref["x"]).all()
+            chk.close()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    nl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+
+    # ---- end to end: the batch arrives SHARDED in host memory (each rank holds its slice in its own pinned buffers, the way a
+    # data-parallel loader delivers it) -> every rank's C-ABI call with HOST pointers -> results back in pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        cnt = hi - lo
+        dsl = make_batch(cnt, n, m, seed0=lo) if rank != 0 else {k: d[k][lo:hi] for k in ("P", "q", "A", "l", "u")}
+        dt, ex = time_e2e(qb, dsl, cnt, n, m, args.steps, args.warmup, barrier, torch)
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        agg = torch.tensor([float(ex["h2d_bytes_per_step"]), float(ex["d2h_bytes_per_step"]), float(ex["launches"])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dt = float(tt.item())
+        e2e = {"value": B * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(agg[0].item()), "d2h_bytes_per_step": int(agg[1].item()),
+               "ms_per_step": 1e3 * dt / args.steps, "launches": int(agg[2].item()), "h2d_gbs_rank0": ex["h2d_gbs_this_rank"],
+               "how": "the 8192-QP batch sharded over the ranks' own pinned host buffers (%d QPs each) -> " % cnt + E2E_HOW}
+
+    # ---- weak scaling beside it: every rank its own 8192 QPs, nothing on the data path
+    weak = None
+    if want_weak:
+        dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")} if rank != 0 else prob
+        wms, wl, winfo, wfacts, wit = time_device(qb, dev, stream, args.steps, args.warmup, barrier, torch)
+        wt = torch.tensor([wms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        wagg = torch.tensor([float(wit)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(wagg, op=dist.ReduceOp.SUM)
+        wms = float(wt.item())
+        weak = {"scaling": "weak", "value": world * B * args.steps / (wms / 1e3), "unit": UNIT, "ms_per_step": wms / args.steps,
+                "admm_iters_per_s": float(wagg.item()) / (wms / 1e3 / args.steps), "batch_per_gpu": B,
+                "workload": "every rank solves its own batch of %d QPs (seed0 = rank x %d), no data-path traffic; device time, max over ranks" % (B, B)}
+        if not args.no_e2e:
+            dt, ex = time_e2e(qb, d, B, n, m, args.steps, args.warmup, barrier, torch, winfo)
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            weak["e2e"] = {"value": world * B * args.steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / args.steps,
+                           "h2d_bytes_per_step": world * ex["h2d_bytes_per_step"], "d2h_bytes_per_step": world * ex["d2h_bytes_per_step"],
+                           "h2d_gbs_rank0": ex["h2d_gbs_this_rank"]}
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        its = int(torch.clamp(out["iter"], max=settings.max_iter).sum().item())
+        info = {"iter": out["iter"].cpu().numpy(), "status": out["status"].cpu().numpy()}
+        iters, checks = counts_from_info(info, settings, api)
+        # p2p: fresh instances every step (setup_solve_to), so rho_updates is per launch; nccl: cumulative over the calls on the object
+        facts = int(out["rho_updates"].sum().item()) // (1 if pb is not None else args.warmup + args.steps)
+        peak64 = fp64_peak(ctx)
+        sec = ms / 1e3 / args.steps
+        # the whole job's work over the whole job's time against N GPUs' peak
+        roof, hbm = rooflines(n, m, B, iters, checks, facts, sec, dict(peak64, peak_tflops=world * peak64["peak_tflops"]), kernel, args.settings)
+        roof["peak_source"] += " x %d GPUs" % world
+        hbm["peak"] *= world
+        hbm["frac"] /= world
+        line = {"metric": METRIC, "value": B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": ("configs[2]: ONE batch=%d n=%d m=%d fp64 (settings %s) on rank 0, NCCL split -> solve -> NCCL gather (both inside "
+                                        "the timed region)" if pb is None else "configs[2]: ONE batch=%d n=%d m=%d fp64 (settings %s) resident in rank "
+                                        "0's HBM (826 MB, larger than L2); every rank's solve kernel reads its slice over NVLink (CUDA IPC peer mapping, "
+                                        "TMA from peer memory) and its epilogue writes the results into rank 0's arrays: one kernel per rank per "
+                                        "step, no split/gather step, no collective") % (B, n, m, args.settings),
+                           "kernel": kernel, "transport": args.transport, "n": n, "m": m, "batch": B,
+                           "parallelism": "batch-sharded x%d (strong: %d QPs per GPU)" % (world, hi - lo)},
+                "admm_iters_per_s": its / (ms / 1e3 / args.steps), "admm_iters_per_step": its,
+                "gpu_launches": int(nl.item()), "roofline": roof, "roofline_hbm_algorithmic": hbm, "compute_peak": peak64, "clocks": clocks}
+        if e2e is not None:
+            line["e2e"] = e2e
+        extra = {}
+        if weak is not None:
+            extra["weak"] = weak
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line))
+    if pb is not None:
+        pb.close()
+    qb.close()
+
+
+def config5_record(args, rank, world, local_rank, ctx, api, torch, dist, B, n, m, settings_name, steps, warmup, no_e2e, no_cpu, cpu_sample):
+    """BASELINE.json configs[4]: sparse-A QPs (one CSR pattern for the batch) through sqpb200_qp_batch_setup_solve_sparse.
+    Same JSON keys as the headline line; weak scaling (every rank its own batch). Returns the record on rank 0 (None elsewhere)."""
     from sqp_solver_b200.synth import densify, make_sparse_batch
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = api.Context(local_rank)
-    B, n, m = args.batch, args.n, args.m
     d = make_sparse_batch(B, n, m, density=args.density, seed0=rank * B)
     nnz = d["nnz"]
-    settings = api.default_settings(**settings_kwargs(args.settings))
+    settings = api.default_settings(**settings_kwargs(settings_name))
     dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "vals", "outer", "inner", "l", "u")}
     qb = api.QPBatch(ctx, B, n, m)
     qb.settings = settings
@@ -324,14 +568,15 @@ def run_config5(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    ru0 = int(qb.get(fields=("rho_updates",))["rho_updates"].astype(np.int64).sum())
     launches0 = ctx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     ev1.record(stream)
     barrier()
@@ -339,6 +584,7 @@ def run_config5(args, rank, world, local_rank):
     launches = ctx.launch_count - launches0
     total_iters = qb.total_iters()
     info0 = qb.get(fields=("status", "iter", "rho_updates"))
+    facts = (int(info0["rho_updates"].astype(np.int64).sum()) - ru0) // max(steps, 1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(total_iters), float(B)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -347,7 +593,7 @@ def run_config5(args, rank, world, local_rank):
     ms_max, all_iters, all_qps = float(t.item()), float(agg[0].item()), float(agg[1].item())
 
     e2e = None
-    if not args.no_e2e:
+    if not no_e2e:
         pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ("P", "q", "vals", "l", "u")}
         hp = {k: v.numpy() for k, v in pin.items()}
         ox = torch.empty(B, n, dtype=torch.float64).pin_memory()
@@ -359,11 +605,11 @@ def run_config5(args, rank, world, local_rank):
             qb.setup_solve_sparse(hp["P"], hp["q"], hp["vals"], d["outer"], d["inner"], hp["l"], hp["u"], layout=api.SPARSE_CSR)
             qb.get_into(x=ox.numpy(), y=oy.numpy(), status=ost.numpy(), iter=oit.numpy())
 
-        for _ in range(min(args.warmup, 2)):
+        for _ in range(min(warmup, 2)):
             step_host()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_host()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -372,46 +618,36 @@ def run_config5(args, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         assert (ost.numpy() == info0["status"]).all() and (oit.numpy() == info0["iter"]).all()
-        e2e = {"value": all_qps * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": B * (8 * (n * n + n + 2 * m + nnz)) + 4 * (m + 1 + nnz),
-               "d2h_bytes_per_step": B * (8 * (n + m) + 8), "ms_per_step": 1e3 * dt / args.steps,
+        e2e = {"value": all_qps * steps / dt, "unit": UNIT, "h2d_bytes_per_step": B * (8 * (n * n + n + 2 * m + nnz)) + 4 * (m + 1 + nnz),
+               "d2h_bytes_per_step": B * (8 * (n + m) + 8), "ms_per_step": 1e3 * dt / steps,
                "how": "pinned host buffers -> sqpb200_qp_batch_setup_solve_sparse(HOST_PTRS): one persistent launch whose work queue is gated "
                       "on the chunk-by-chunk H2D staging -> sqpb200_qp_batch_get to pinned host; wall clock, max over ranks"}
     clocks = sampler.stop() if sampler else None
+    kernel = ctx.last_kernel
+    qb.close()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    executed = np.minimum(info0["iter"], settings.max_iter).astype(np.int64)
-    executed[info0["status"] == api.NUMERICAL_ISSUES] = 0
-    ct = settings.check_termination
-    checks = int((executed // ct).sum()) if ct > 0 else 0
-    # rho_updates is cumulative over the calls on this batch object (qp.cpp:313): per launch = total / launches so far
-    calls = args.warmup + args.steps + (0 if args.no_e2e else min(args.warmup, 2) + args.steps)
-    facts = int(info0["rho_updates"].sum()) // max(calls, 1)
-    bytes_per_launch = sparse_algorithmic_bytes(n, m, nnz, int(executed.sum()), checks, facts, B)
-    sec = ms / 1e3 / args.steps
+        return None
+    iters, checks = counts_from_info(info0, settings, api)
+    bytes_per_launch = sparse_algorithmic_bytes(n, m, nnz, iters, checks, facts, B)
+    sec = ms / 1e3 / steps
     peak, peak_src = peaks()
     achieved = bytes_per_launch / sec / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%dx%d_b%d_%s" % (ctx.last_kernel, n, m, B, args.settings))
-    except Exception:
-        traffic = None
+    traffic, traffic_note = traffic_for("%s_%dx%d_b%d_%s" % (kernel, n, m, B, settings_name))
     line = {
-        "metric": "QP-subproblems/sec (batch=%d, n=%d, m=%d, sparse A nnz=%d)" % (B, n, m, nnz), "value": all_qps * args.steps / (ms_max / 1e3),
-        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+        "metric": "QP-subproblems/sec (batch=%d, n=%d, m=%d, sparse A nnz=%d)" % (B, n, m, nnz), "value": all_qps * steps / (ms_max / 1e3),
+        "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[4]: batch=%d sparse-A QPs n=%d m=%d fp64 per GPU, one CSR pattern for the batch (density %.3g + one "
-                               "entry per row: nnz=%d), settings %s, fresh setup+solve per step" % (B, n, m, args.density, nnz, args.settings),
-                   "batch_per_gpu": B, "n": n, "m": m, "nnz": nnz, "kernel": ctx.last_kernel,
+                               "entry per row: nnz=%d), settings %s, fresh setup+solve per step" % (B, n, m, args.density, nnz, settings_name),
+                   "batch_per_gpu": B, "n": n, "m": m, "nnz": nnz, "kernel": kernel,
                    "parallelism": "batch-sharded x%d, no collective on the data path" % world,
                    "l2": "inputs are %.0f MB per step, larger than the 126 MB L2" % (8 * B * (n * n + n + 2 * m + nnz) / 1e6)},
-        "admm_iters_per_s": all_iters / (ms_max / 1e3 / args.steps), "admm_iters_per_step": all_iters,
+        "admm_iters_per_s": all_iters / (ms_max / 1e3 / steps), "admm_iters_per_step": all_iters,
         "factorisations_per_step": facts,
         "status_histogram": {api.STATUS_NAMES[k]: int((info0["status"] == k).sum()) for k in np.unique(info0["status"])},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": 1e3 * sec,
+                     "traffic_note": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": 1e3 * sec,
                      "note": "SURVEY.md 8(d) accounting with A compressed (12 B per stored entry). H^-1 lives in the shared memory of a "
                              "4-CTA cluster, so DRAM traffic is the compulsory I/O only; the kernel is bound by cluster barriers and the "
                              "serial pivot chain of the factorisation (DESIGN.md 4.4), not by HBM"},
@@ -419,25 +655,23 @@ def run_config5(args, rank, world, local_rank):
     }
     if e2e is not None:
         line["e2e"] = e2e
-    if not args.no_cpu_baseline:
+    if not no_cpu:
         from oracle import qp_oracle as O
 
         O.build()
         cores = O.num_procs()
-        sample = args.cpu_sample or min(B, 2 * cores)
+        sample = cpu_sample or min(B, 2 * cores)
         A = densify(d, 0, sample)
-        st = O.default_settings(**settings_kwargs(args.settings))
+        st = O.default_settings(**settings_kwargs(settings_name))
         t0 = time.perf_counter()
         out = O.solve_batch(d["P"][:sample], d["q"][:sample], A, d["l"][:sample], d["u"][:sample], st, nthreads=cores)
         dt = time.perf_counter() - t0
         assert (out["status"] == info0["status"][:sample]).all(), "GPU and oracle disagree on the status of the sampled QPs"
         line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "first %d QPs of the same batch (densified: the reference's sparse variant is dead code), %s, gcc -O2 "
-                                          "oracle restatement of src/qp.cpp, OpenMP over %d threads, %.2f s" % (sample, args.settings, out["threads"], dt),
+                                          "oracle restatement of src/qp.cpp, OpenMP over %d threads, %.2f s" % (sample, settings_name, out["threads"], dt),
                                 "admm_iters_per_s": int(np.minimum(out["iter"], st.max_iter).sum()) / dt}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -450,32 +684,42 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.workload == "config5":
-        run_config5(args, rank, world, local_rank)
-        return
 
     import torch
     import torch.distributed as dist
 
     from sqp_solver_b200 import api
-    from sqp_solver_b200.synth import make_batch
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = api.Context(local_rank)
-    ctx.set_option(api.OPT_KERNEL, {"auto": 0, "generic": 1, "tile": 2}[args.kernel])
-    ctx.set_option(api.OPT_TILE_WARPS, args.tile_warps)
-    ctx.set_option(api.OPT_CTAS_PER_SM, args.ctas_per_sm)
+    ctx = api.Context(local_rank)  # raises when the CUDA library or the device is missing: no fallback
+    try:
+        if args.workload == "config5":
+            line = config5_record(args, rank, world, local_rank, ctx, api, torch, dist, args.batch, args.n, args.m, args.settings,
+                                  args.steps, args.warmup, args.no_e2e, args.no_cpu_baseline, args.cpu_sample)
+            if rank == 0:
+                print(json.dumps(line))
+            return
+        ctx.set_option(api.OPT_KERNEL, {"auto": 0, "generic": 1, "tile": 2}[args.kernel])
+        ctx.set_option(api.OPT_TILE_WARPS, args.tile_warps)
+        ctx.set_option(api.OPT_CTAS_PER_SM, args.ctas_per_sm)
+        if world > 1 and args.scaling in ("auto", "strong"):
+            run_strong(args, rank, world, local_rank, ctx, api, torch, dist)
+            return
+        run_weak(args, rank, world, local_rank, ctx, api, torch, dist)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def run_weak(args, rank, world, local_rank, ctx, api, torch, dist):
+    """N = 1 (the driver's headline line) or --scaling weak: every rank solves its own batch, no data-path traffic."""
+    from sqp_solver_b200.synth import make_batch
+
     B, n, m = args.batch, args.n, args.m
-    strong = args.scaling == "strong" and world > 1
-    # weak: every rank owns a disjoint shard of the seed sequence; strong: only rank 0 builds the (single) batch
-    d = make_batch(B if (not strong or rank == 0) else 1, n, m, seed0=0 if strong else rank * B)
+    d = make_batch(B, n, m, seed0=rank * B)
     settings = api.default_settings(**settings_kwargs(args.settings))
-    if strong:
-        run_strong(args, rank, world, ctx, api, d, settings)
-        dist.destroy_process_group()
-        return
     dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")}
     qb = api.QPBatch(ctx, B, n, m)
     qb.settings = settings
@@ -484,29 +728,15 @@ def main():
         args.no_cpu_baseline = True
     stream = torch.cuda.current_stream()
 
-    def step_device():
-        qb.setup_solve(dev["P"], dev["q"], dev["A"], dev["l"], dev["u"], stream=stream.cuda_stream)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+    peak64 = fp64_peak(ctx) if rank == 0 else None
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count - launches0
-    total_iters = qb.total_iters()
-    info = qb.get(fields=("status", "iter", "rho_updates"))
+    ms, launches, info, facts, total_iters = time_device(qb, dev, stream, args.steps, args.warmup, barrier, torch)
+    kernel = ctx.last_kernel
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(total_iters), float(B)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -515,64 +745,25 @@ def main():
     ms_max = float(t.item())
     all_iters, all_qps = float(agg[0].item()), float(agg[1].item())
 
-    # ---- end to end: host (pinned) buffers through the C-ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ("P", "q", "A", "l", "u")}
-        hp = {k: v.numpy() for k, v in pin.items()}
-        ox = torch.empty(B, n, dtype=torch.float64).pin_memory()
-        oy = torch.empty(B, m, dtype=torch.float64).pin_memory()
-        ost = torch.empty(B, dtype=torch.int32).pin_memory()
-        oit = torch.empty(B, dtype=torch.int32).pin_memory()
-
-        def step_host():
-            qb.setup_solve(hp["P"], hp["q"], hp["A"], hp["l"], hp["u"])
-            qb.get_into(x=ox.numpy(), y=oy.numpy(), status=ost.numpy(), iter=oit.numpy())
-
-        for _ in range(min(args.warmup, 2)):
-            step_host()
-        barrier()
-        l0 = ctx.launch_count
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e_launches = ctx.launch_count - l0
+        dt, ex = time_e2e(qb, d, B, n, m, args.steps, args.warmup, barrier, torch, info)
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        assert (ost.numpy() == info["status"]).all() and (oit.numpy() == info["iter"]).all()
-        e2e = {"value": all_qps * args.steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": 8 * B * (n * n + n + m * n + 2 * m), "d2h_bytes_per_step": B * (8 * (n + m) + 8),
-               "ms_per_step": 1e3 * dt / args.steps, "launches": e2e_launches,
-               "how": "pinned host buffers -> sqpb200_qp_batch_setup_solve(HOST_PTRS): one persistent launch whose work queue is "
-                      "gated on the chunk-by-chunk H2D staging -> sqpb200_qp_batch_get to pinned host; wall clock between device "
-                      "synchronisations, max over ranks"}
+        e2e = {"value": all_qps * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": world * ex["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": world * ex["d2h_bytes_per_step"], "ms_per_step": 1e3 * dt / args.steps, "launches": ex["launches"],
+               "h2d_gbs_rank0": ex["h2d_gbs_this_rank"], "how": E2E_HOW}
     clocks = sampler.stop() if sampler else None
-
+    qb.close()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
-    executed = np.minimum(info["iter"], settings.max_iter).astype(np.int64)
-    executed[info["status"] == api.NUMERICAL_ISSUES] = 0
-    ct = settings.check_termination
-    checks = int((executed // ct).sum()) if ct > 0 else 0
-    facts = int(info["rho_updates"].sum())
-    bytes_per_launch = algorithmic_bytes(n, m, int(executed.sum()), checks, facts, B)
+    iters, checks = counts_from_info(info, settings, api)
     sec_per_launch = ms / 1e3 / args.steps  # rank 0's own kernel time
-    peak, peak_src = peaks()
-    achieved = bytes_per_launch / sec_per_launch / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("%s_%dx%d_b%d_%s" % (ctx.last_kernel, n, m, B, args.settings))
-        except Exception:
-            traffic = None
+    roof, hbm = rooflines(n, m, B, iters, checks, facts, sec_per_launch, peak64, kernel, args.settings)
+    in_bytes = 8 * B * (n * n + n + m * n + 2 * m)
     line = {
         "metric": METRIC if (B, n, m) == WORKLOADS["config3"] else "QP-subproblems/sec (batch=%d, n=%d, m=%d)" % (B, n, m),
         "value": all_qps * args.steps / (ms_max / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -581,32 +772,37 @@ def main():
         "config": {"workload": "configs[%d]: batch=%%d dense QPs n=%%d m=%%d fp64 per GPU, settings %%s (%%s), fresh setup+solve per step" % (1 if args.workload == "config2" else 2)
                                % (B, n, m, args.settings, "reference defaults qp.hpp:38-53" if args.settings == "S1" else
                                   "alpha=1.6 adaptive_rho"),
-                   "batch_per_gpu": B, "n": n, "m": m, "kernel": ctx.last_kernel, "parallelism": "batch-sharded x%d, no collective on the data path" % world,
-                   "l2": "inputs are %.0f MB per step, larger than the 126 MB L2" % (8 * B * (n * n + n + m * n + 2 * m) / 1e6)},
+                   "batch_per_gpu": B, "n": n, "m": m, "kernel": kernel, "parallelism": "batch-sharded x%d, no collective on the data path" % world,
+                   "l2": "inputs are %.0f MB per step, %s" % (in_bytes / 1e6, "larger than the 126 MB L2" if in_bytes > 126e6 else
+                                                             "SMALLER than the 126 MB L2: they stay L2-resident across steps (no flush between steps)")},
         "admm_iters_per_s": all_iters / (ms_max / 1e3 / args.steps),
-        "admm_iters_per_step": all_iters,
+        "admm_iters_per_step": all_iters, "factorisations_per_step": facts,
         "status_histogram": {api.STATUS_NAMES[k]: int((info["status"] == k).sum()) for k in np.unique(info["status"])},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                     "kernel_ms": 1e3 * sec_per_launch,
-                     "note": "algorithmic bytes of SURVEY.md 8(d); the working set is register/shared-memory resident, so measured "
-                             "DRAM traffic is far below this and frac can exceed 1 (see DESIGN.md)"},
-        # the honest binding resource: fp64 FMA work against the chip's nominal fp64 vector rate
-        "compute": {"flops_per_iteration": 4 * m * n + 2 * n * n, "achieved_tflops": (4 * m * n + 2 * n * n) * total_iters / sec_per_launch / 1e12,
-                    "peak_tflops": 148 * 58.98 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s fp64",
-                    "peak_source": "measured: 58.98 DFMA/clk/SM x 148 SMs x 2 x 1.965 GHz (tools/proto/proto_lat.cu on this pool's B200; "
-                                   "nominal 64/clk; MEASURED_PEAKS.json has no fp64 entry)",
-                    "frac": (4 * m * n + 2 * n * n) * total_iters / sec_per_launch / (148 * 58.98 * 2 * 1.965e9)},
+        "roofline": roof, "roofline_hbm_algorithmic": hbm, "compute_peak": peak64,
         "clocks": clocks,
     }
     if e2e is not None:
         line["e2e"] = e2e
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(d, args.settings, args.cpu_sample)
+    # ---- the other regimes and configs, measured in the same run (N = 1 only; each a few seconds)
+    if world == 1 and not args.no_extras and not args.fp32 and args.workload == "config3" and args.settings == "S1" and args.kernel == "auto":
+        extra = {}
+        xs, xw = min(args.steps, 10), 3
+        try:
+            extra["config3_S2"], _ = dense_record(ctx, api, torch, B, n, m, "S2", xs, xw, peak64, d=d, cpu=not args.no_cpu_baseline)
+            extra["config3_S2"]["note"] = "the regime the reference's own caller uses (SQP constructor: alpha 1.6 + adaptive rho)"
+            b2, n2, m2 = WORKLOADS["config2"]
+            extra["config2_S1"], _ = dense_record(ctx, api, torch, b2, n2, m2, "S1", xs, xw, peak64, cpu=not args.no_cpu_baseline)
+            extra["config2_S1"]["note"] = "BASELINE configs[1]: batch=1024 dense QPs n=32 m=64, one warp per QP"
+            b5, n5, m5 = WORKLOADS["config5"]
+            extra["config5_S2"] = config5_record(args, 0, 1, local_rank, ctx, api, torch, dist, b5, n5, m5, "S2", min(xs, 5), 2,
+                                                 args.no_e2e, args.no_cpu_baseline, 0)
+        except Exception as e:  # the extras never take the headline line down
+            extra["error"] = repr(e)
+        line["extra"] = extra
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -84,7 +84,8 @@ typedef enum sqpb200_error {
 
 /* context options for sqpb200_ctx_set_option */
 #define SQPB200_OPT_KERNEL 1       /* 0 = auto (default), 1 = force the generic kernel, 2 = force the register-tiled kernel,
-                                      3 = force the blocked kernel, 4 = force the cluster kernel (sparse A only) (tests / tuning) */
+                                      3 = force the blocked kernel, 4 = force the cluster kernel (sparse A only), 5 = force the
+                                      thread-per-QP literal KKT kernel (n + m <= 16) (tests / tuning) */
 #define SQPB200_OPT_H2D_CHUNKS 2   /* number of staging chunks for HOST_PTRS calls (default 16) */
 #define SQPB200_OPT_CTAS_PER_SM 3  /* 0 = auto */
 #define SQPB200_OPT_TILE_WARPS 4   /* warps per QP of the register-tiled kernel: 0 = default; 4 (default) or 8 for the 64x128 class, 1 (default) or 2 for the 32x64 class (tuning/tests) */
@@ -105,6 +106,10 @@ int sqpb200_device_query(const sqpb200_ctx *ctx, int *device, int *sm_count, int
 long long sqpb200_launch_count(const sqpb200_ctx *ctx);
 /* name of the kernel the last solve dispatched to ("generic", "tile<64,128,8>", ...) */
 const char *sqpb200_last_kernel(const sqpb200_ctx *ctx);
+
+/* fp64 FMA peak of this device, measured now with a saturating DFMA kernel (a few ms): *tflops = 2 x FMA / s. Used by bench.py for
+ * the roofline of the compute-bound kernels (the driver's MEASURED_PEAKS.json carries HBM and bf16 figures only). */
+int sqpb200_measure_fp64_peak(sqpb200_ctx *ctx, double *tflops, double *seconds, double *fma_count);
 
 void sqpb200_qp_default_settings(sqpb200_qp_settings *s);
 
@@ -162,6 +167,17 @@ int sqpb200_qp_batch_setup_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings 
                                  const double *q, const double *A, const double *l, const double *u, unsigned flags,
                                  void *stream);
 
+/* setup_solve of `count` FRESH solver instances (default-constructed: rho_updates starts at 0) whose results are written by the
+ * kernel's epilogue straight into caller-provided DEVICE arrays -- which may live in another GPU's memory (imported with
+ * sqpb200_ipc_import): with the inputs read from the owner's memory as well, a rank solves its slice of a batch another GPU owns
+ * with no split, no gather and no copy at all (SURVEY.md 8e "the gather can be folded into the solve kernel's epilogue").
+ * Device pointers only; asynchronous on `stream`. The object's own x, y, z and info are NOT advanced by this call. Shapes
+ * outside the register-tiled kernel fall back to a solve into the object followed by device-to-device copies. */
+int sqpb200_qp_batch_setup_solve_to(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                                    const double *q, const double *A, const double *l, const double *u, double *x, double *y,
+                                    double *z, int *status, int *iter, int *rho_updates, double *rho_estimate, double *res_prim,
+                                    double *res_dual, void *stream);
+
 /* setup_solve with factor bookkeeping for callers that re-solve the SAME P and A with new q, l, u -- the
  * second-order-correction QP of SQP<T>::second_order_correction (sqp.cpp:244-276, "TODO: only l and u change").
  *   SQPB200_KEEP_FACTOR   remember each instance's setup factor (one n*n store per QP)
@@ -177,8 +193,10 @@ int sqpb200_qp_batch_setup_solve_opts(sqpb200_qp_batch *b, const sqpb200_qp_sett
 /* setup + solve with a SPARSE constraint matrix: one sparsity pattern shared by the batch, per-instance values
  * A_values[B][nnz]. layout SQPB200_SPARSE_CSC is Eigen::SparseMatrix's compressed column storage (the reference's intended
  * sparse variant, qp.hpp:22-25; A_outer has n+1 entries, A_inner holds row indices); SQPB200_SPARSE_CSR has m+1 outer
- * entries and column indices. P stays dense. Round 1 densifies on the device and runs the dense kernels (results are
- * identical to the dense entry points); a sparsity-exploiting kernel is next-round work. */
+ * entries and column indices. P stays dense. Shapes of the thread-per-QP and register-tiled kernels (n <= 64, m <= 128) densify on
+ * the device (A lives in registers there anyway; results are identical to the dense entry points); 64 < n <= 256 run the
+ * thread-block-cluster kernel (A compressed in shared memory, H^-1 distributed over the cluster) or, when the instance does not
+ * fit on chip, the blocked kernel walking the compressed pattern. */
 #define SQPB200_SPARSE_CSC 0
 #define SQPB200_SPARSE_CSR 1
 int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,

@@ -22,7 +22,7 @@ INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = range(3)  # qp.hpp:13
 STATUS_NAMES = ["SOLVED", "MAX_ITER_EXCEEDED", "UNSOLVED", "NUMERICAL_ISSUES", "UNINITIALIZED"]
 HOST_PTRS, DEVICE_PTRS = 0, 1
 OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS = 1, 2, 3, 4
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE, KERNEL_BLOCK, KERNEL_CLUSTER = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE, KERNEL_BLOCK, KERNEL_CLUSTER, KERNEL_SMALL = 0, 1, 2, 3, 4, 5
 KEEP_FACTOR, REUSE_FACTOR = 1, 2
 SPARSE_CSC, SPARSE_CSR = 0, 1
 
@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_set_precision", "sqpb200_dev_alloc", "sqpb200_dev_free", "sqpb200_dev_copy",
     "sqpb200_ipc_export", "sqpb200_ipc_import", "sqpb200_ipc_release", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
-    "sqpb200_qp_solve_batch",
+    "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library(path=None):
     L.sqpb200_last_error.restype = C.c_char_p
     L.sqpb200_device_query.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                        C.POINTER(C.c_size_t)]
+    L.sqpb200_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sqpb200_launch_count.argtypes = [vp]
     L.sqpb200_launch_count.restype = C.c_longlong
     L.sqpb200_last_kernel.argtypes = [vp]
@@ -91,6 +92,7 @@ def load_library(path=None):
     L.sqpb200_qp_batch_setup_solve_opts.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp, C.c_uint]
     L.sqpb200_qp_batch_setup_solve_sparse.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, ip, ip, C.c_int, C.c_int, dp, dp,
                                                       C.c_uint, vp]
+    L.sqpb200_qp_batch_setup_solve_to.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip, ip, dp, dp, dp, vp]
     L.sqpb200_qp_batch_set_precision.argtypes = [vp, C.c_int]
     L.sqpb200_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
     L.sqpb200_dev_free.argtypes = [vp, vp]
@@ -237,6 +239,12 @@ class Context:
                     "device_query")
         return dict(device=dev.value, sm_count=sm.value, cc=(ma.value, mi.value), smem_per_block_optin=sz.value)
 
+    def measure_fp64_peak(self):
+        """(TFLOP/s, seconds, DFMA count) of a saturating fp64 FMA kernel on this device, measured now."""
+        t, s_, c = C.c_double(), C.c_double(), C.c_double()
+        self._check(self._L.sqpb200_measure_fp64_peak(self._h, C.byref(t), C.byref(s_), C.byref(c)), "measure_fp64_peak")
+        return t.value, s_.value, c.value
+
     @property
     def launch_count(self):
         return int(self._L.sqpb200_launch_count(self._h))
@@ -307,6 +315,31 @@ class QPBatch:
         else:
             self._call("setup_solve", P, q, A, l, u, count, stream)
 
+    def setup_solve_to(self, P, q, A, l, u, out, count=None, stream=None):
+        """Fused setup + solve of fresh instances; the kernel writes x, y, z, status, iter, rho_updates, rho_estimate, res_prim,
+        res_dual straight into the device arrays of `out` (CUDA tensors or DevPtr, possibly peer memory). Asynchronous on `stream`."""
+        count = self.batch if count is None else int(count)
+        ins = []
+        for nm, a in (("P", P), ("q", q), ("A", A), ("l", l), ("u", u)):
+            p_, sp = _ptr_and_space(a, np.float64, nm)
+            if sp != DEVICE_PTRS and p_ is not None:
+                raise SolverError("setup_solve_to takes device arrays only")
+            ins.append(p_)
+        order = ["x", "y", "z", "status", "iter", "rho_updates", "rho_estimate", "res_prim", "res_dual"]
+        ints = {"status", "iter", "rho_updates"}
+        outs = []
+        for k in order:
+            p_, sp = _ptr_and_space(out[k], np.int32 if k in ints else np.float64, k)
+            if sp != DEVICE_PTRS:
+                raise SolverError("setup_solve_to takes device arrays only")
+            outs.append(p_)
+        if stream is None:
+            import torch
+
+            stream = torch.cuda.current_stream().cuda_stream
+        self.ctx._check(self._L.sqpb200_qp_batch_setup_solve_to(self._h, C.byref(self.settings), count, *ins, *outs, C.c_void_p(stream or 0)),
+                        "setup_solve_to")
+
     def setup_solve_sparse(self, P, q, A_values, A_outer, A_inner, l, u, layout=SPARSE_CSC, count=None, stream=None):
         """setup + solve with A given as CSC (Eigen::SparseMatrix layout) or CSR: one pattern for the whole batch
         (A_outer, A_inner: int32), per-instance values A_values[B, nnz]."""
@@ -332,7 +365,7 @@ class QPBatch:
                         "setup_solve_sparse")
 
     def get(self, count=None, fields=("x", "y", "z", "status", "iter", "rho_updates", "rho_estimate", "res_prim", "res_dual")):
-        """Copy results to fresh host arrays (synchronises)."""
+        """Copy results to fresh host arrays (synchronises; ordered behind the last launch on this object whatever stream that used)."""
         count = self.batch if count is None else int(count)
         shapes = dict(x=((count, self.n), np.float64), y=((count, self.m), np.float64), z=((count, self.m), np.float64),
                       status=((count,), np.int32), iter=((count,), np.int32), rho_updates=((count,), np.int32),

@@ -16,6 +16,10 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-ccbin", "/usr/bin/g++"]
 
 
+# per-file flags: the thread-per-QP kernel restates the CPU path's arithmetic operation by operation, so no FMA contraction there
+PER_FILE = {"qp_small.cu": ["-fmad=false"]}
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -36,7 +40,7 @@ def build(force=False, verbose=False, extra=()):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
-        cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + PER_FILE.get(os.path.basename(src), []) + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, pr in procs:

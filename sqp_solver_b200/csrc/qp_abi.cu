@@ -25,8 +25,6 @@ struct sqpb200_ctx {
     int *ready_host = nullptr;           // pinned: chunk boundaries, source of the flag copies
     static constexpr int kCounters = 1024;
     long long launches = 0;
-    double *scratch = nullptr;
-    size_t scratch_bytes = 0;
     int opt_kernel = 0, opt_chunks = 16, opt_ctas_per_sm = 0, opt_tile_warps = 0;
     std::string err;
     char last_kernel[64] = "none";
@@ -46,6 +44,12 @@ struct sqpb200_qp_batch {
     bool fused_used = false;
     int f32 = 0;  // compute precision of the register-tiled kernel for this batch (QPSolver<float>)
     bool fact_valid = false;  // a setup()/update_qp()/solve() launch has stored H^-1, rho and classes
+    int fact_kernel = 0;      // which kernel family wrote the stored factor (its layout differs per kernel): KERNEL_* below, 0 = none
+    int keep_kernel = 0;      // which kernel family wrote the factor kept by SQPB200_KEEP_FACTOR
+    cudaStream_t last_stream = nullptr;  // stream of the last launch on this object, and an event recorded behind it:
+    cudaEvent_t last_event = nullptr;    // get / set_iterates / total_iters on ANOTHER stream wait for it first
+    double *gen_scratch = nullptr;  // generic kernel: per-CTA n*n factorisation workspace (owned by the batch object: launches of
+    size_t gen_scratch_bytes = 0;   // different batch objects may overlap on different streams)
     unsigned long long *total_iters = nullptr;
     // staging for HOST_PTRS calls (lazily allocated)
     double *dP = nullptr, *dq = nullptr, *dA = nullptr, *dl = nullptr, *du = nullptr;
@@ -57,7 +61,7 @@ struct sqpb200_qp_batch {
     unsigned long long sp_hash = 0;  // hash of the pattern whose derived views (sp2_*, sp_pack) are on the device; 0 = none
     double *cl_scratch = nullptr;  // cluster kernel: per-cluster exchange buffers (owned by the batch object: launches of different
     size_t cl_scratch_bytes = 0;   // batch objects may overlap on different streams)
-    unsigned *sp_pack = nullptr;  // [2][cap]: packed (index | value position << 10) entries of the CSC and the CSR view (cluster kernel)
+    unsigned *sp_pack = nullptr;  // [2][cap]: packed (index | value position << PACK_BITS) entries of the CSC and the CSR view (cluster kernel)
 };
 
 static int fail(sqpb200_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
@@ -141,7 +145,6 @@ int sqpb200_ctx_destroy(sqpb200_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &ev : c->chunk_events)
         if (ev) cudaEventDestroy(ev);
-    if (c->scratch) cudaFree(c->scratch);
     if (c->counters) cudaFree(c->counters);
     if (c->ready_dev) cudaFree(c->ready_dev);
     if (c->ready_host) cudaFreeHost(c->ready_host);
@@ -155,7 +158,7 @@ int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
     if (!c) return SQPB200_ERR_INVALID;
     switch (option) {
         case SQPB200_OPT_KERNEL:
-            if (value < 0 || value > 4) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_KERNEL: value must be 0..4");
+            if (value < 0 || value > 5) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_KERNEL: value must be 0..5");
             c->opt_kernel = value;
             return SQPB200_OK;
         case SQPB200_OPT_H2D_CHUNKS:
@@ -185,6 +188,18 @@ int sqpb200_device_query(const sqpb200_ctx *c, int *device, int *sm_count, int *
     if (cc_major) *cc_major = c->prop.major;
     if (cc_minor) *cc_minor = c->prop.minor;
     if (smem_per_block_optin) *smem_per_block_optin = c->prop.sharedMemPerBlockOptin;
+    return SQPB200_OK;
+}
+
+int sqpb200_measure_fp64_peak(sqpb200_ctx *c, double *tflops, double *seconds, double *fma_count) {
+    if (!c || !tflops) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    double sec = 0, cnt = 0;
+    CK(c, measure_dfma_peak(c->prop.multiProcessorCount, c->stream, &sec, &cnt));
+    c->launches += 5;
+    *tflops = 2.0 * cnt / sec / 1e12;
+    if (seconds) *seconds = sec;
+    if (fma_count) *fma_count = cnt;
     return SQPB200_OK;
 }
 
@@ -254,9 +269,10 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
-                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm, b->sp_pack, b->cl_scratch};
+                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm, b->sp_pack, b->cl_scratch, b->gen_scratch};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (b->last_event) cudaEventDestroy(b->last_event);
     delete b;
     return SQPB200_OK;
 }
@@ -271,6 +287,10 @@ int sqpb200_qp_batch_create(sqpb200_ctx *c, int batch, int n, int m, sqpb200_qp_
     sqpb200_qp_batch *b = new (std::nothrow) sqpb200_qp_batch();
     if (!b) return fail(c, SQPB200_ERR_NOMEM, "host allocation failed");
     b->ctx = c;
+    if (cudaEventCreateWithFlags(&b->last_event, cudaEventDisableTiming) != cudaSuccess) {
+        delete b;
+        return fail(c, SQPB200_ERR_CUDA, "sqpb200_qp_batch_create: cudaEventCreate");
+    }
     b->batch = batch;
     b->n = n;
     b->m = m;
@@ -337,15 +357,25 @@ int sqpb200_qp_batch_create(sqpb200_ctx *c, int batch, int n, int m, sqpb200_qp_
 
 // ---- launch plumbing -----------------------------------------------------------------------
 
-static int ensure_scratch(sqpb200_ctx *c, size_t bytes) {
-    if (bytes <= c->scratch_bytes) return SQPB200_OK;
+enum { KERNEL_NONE = 0, KERNEL_GENERIC, KERNEL_TILE, KERNEL_BLOCK, KERNEL_CLUSTER, KERNEL_SMALL };
+
+static int ensure_scratch(sqpb200_qp_batch *b, size_t bytes) {
+    sqpb200_ctx *c = b->ctx;
+    if (bytes <= b->gen_scratch_bytes) return SQPB200_OK;
     CK(c, cudaDeviceSynchronize());
-    if (c->scratch) cudaFree(c->scratch);
-    c->scratch = nullptr;
-    c->scratch_bytes = 0;
-    cudaError_t e = cudaMalloc(&c->scratch, bytes);
+    if (b->gen_scratch) cudaFree(b->gen_scratch);
+    b->gen_scratch = nullptr;
+    b->gen_scratch_bytes = 0;
+    cudaError_t e = cudaMalloc(&b->gen_scratch, bytes);
     if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "scratch cudaMalloc", e);
-    c->scratch_bytes = bytes;
+    b->gen_scratch_bytes = bytes;
+    return SQPB200_OK;
+}
+
+// Order `stream` behind the last launch on this object when that ran on another stream (a non-blocking stream does not
+// synchronise with the legacy default stream, so results read on stream 0 would otherwise be stale).
+static int order_after_last_launch(sqpb200_qp_batch *b, cudaStream_t stream) {
+    if (b->last_event && b->last_stream != stream) CK(b->ctx, cudaStreamWaitEvent(stream, b->last_event, 0));
     return SQPB200_OK;
 }
 
@@ -376,9 +406,17 @@ static int ensure_staging(sqpb200_qp_batch *b) {
 }
 
 // One kernel launch over QPs [first, first+count) of the batch arrays.
+// results written by the kernel straight into caller arrays instead of the object's state (sqpb200_qp_batch_setup_solve_to)
+struct OutOverride {
+    double *x, *y, *z;
+    int *status, *iter, *rho_updates;
+    double *rho_estimate, *res_prim, *res_dual;
+};
+
 static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode, int first, int count,
                         const double *P, const double *q, const double *A, const double *l, const double *u,
-                        cudaStream_t stream, const int *ready = nullptr, const SparseA *sp = nullptr) {
+                        cudaStream_t stream, const int *ready = nullptr, const SparseA *sp = nullptr, const OutOverride *ov = nullptr,
+                        bool *ov_used = nullptr) {
     sqpb200_ctx *c = b->ctx;
     KernelParams p{};
     p.first = first;
@@ -400,34 +438,77 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     p.work_counter = c->counters + slot;
     CK(c, cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
 
-    // kernel choice: register-tiled (n <= 64, m <= 128) > blocked (n <= 256, m <= 1024) > generic (anything that fits)
+    // kernel choice (dense A): thread-per-QP literal KKT kernel (n + m <= 16: the SQP regime) > register-tiled (n <= 64, m <= 128) >
+    // blocked (n <= 256, m <= 1024) > generic (anything that fits). Sparse A: cluster kernel when the instance fits on chip, else blocked.
     const size_t optin = c->prop.sharedMemPerBlockOptin;
-    // settings.verbose (the reference's per-check status line, qp.cpp:114-118 / :375-382) is a debugging aid: such calls take the generic
-    // kernel, the one that prints it, so the fast kernels carry no printf in their loops
-    const bool verbose_generic = st->verbose && !sp && c->opt_kernel == 0 && generic_supported(b->n, b->m, optin);
-    const bool want_tile = !sp && !verbose_generic && c->opt_kernel != 1 && c->opt_kernel != 3 && tile_supported(b->n, b->m);
-    // sparse A: a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
-    int clusters = 0;
-    if (sp && (c->opt_kernel == 0 || c->opt_kernel == 4) && sp->cluster_size > 0 && mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE))
-        clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap, sp->cluster_size);
-    // Eight CTAs per QP buy latency, not throughput (measured at n = 256, nnz = 8.9 k: 0.84 ms per QP on 8 SMs against 7.7 ms on one SM
-    // with the blocked kernel, i.e. the same QPs per SM-second): keep them for batches that cannot fill the SMs one QP each
-    if (clusters >= 1 && sp->cluster_size == 8 && c->opt_kernel == 0 && count > c->prop.multiProcessorCount &&
-        block_sparse_supported(b->n, b->m, sp->nnz, optin))
-        clusters = 0;
-    if (c->opt_kernel == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
-    const bool want_cluster = clusters >= 1;
-    const bool want_block = !want_cluster && (sp || (!want_tile && !verbose_generic && c->opt_kernel != 1 && c->opt_kernel != 2 && block_supported(b->n, b->m, optin)));
-    if (c->opt_kernel == 2 && !want_tile) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
-    if (c->opt_kernel == 3 && !want_block) return fail(c, SQPB200_ERR_UNSUPPORTED, "blocked kernel forced but (n, m) is outside its range");
-    const bool needs_fact = !want_cluster && (!want_tile || (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE)));
+    const int opt = c->opt_kernel;
+    int kind = KERNEL_NONE, clusters = 0;
+    if (sp) {
+        // a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
+        if ((opt == 0 || opt == 4) && sp->cluster_size > 0 && mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE))
+            clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap, sp->cluster_size);
+        // Eight CTAs per QP buy latency, not throughput (measured at n = 256, nnz = 8.9 k: 0.84 ms per QP on 8 SMs against 7.7 ms on one SM
+        // with the blocked kernel, i.e. the same QPs per SM-second): keep them for batches that cannot fill the SMs one QP each
+        if (clusters >= 1 && sp->cluster_size == 8 && opt == 0 && count > c->prop.multiProcessorCount &&
+            block_sparse_supported(b->n, b->m, sp->nnz, optin))
+            clusters = 0;
+        if (opt == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
+        kind = clusters >= 1 ? KERNEL_CLUSTER : KERNEL_BLOCK;
+    } else if (opt == 1) {
+        kind = KERNEL_GENERIC;
+    } else if (opt == 2) {
+        if (!tile_supported(b->n, b->m)) return fail(c, SQPB200_ERR_UNSUPPORTED, "register-tiled kernel forced but (n, m) is outside its range");
+        kind = KERNEL_TILE;
+    } else if (opt == 3) {
+        if (!block_supported(b->n, b->m, optin)) return fail(c, SQPB200_ERR_UNSUPPORTED, "blocked kernel forced but (n, m) is outside its range");
+        kind = KERNEL_BLOCK;
+    } else if (opt == 5) {
+        if (!small_supported(b->n, b->m)) return fail(c, SQPB200_ERR_UNSUPPORTED, "thread-per-QP kernel forced but n + m > 16");
+        kind = KERNEL_SMALL;
+    } else if (opt == 4) {
+        return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but A is dense");
+    } else if (st->verbose && generic_supported(b->n, b->m, optin)) {
+        // settings.verbose (the reference's per-check status line, qp.cpp:114-118 / :375-382) is a debugging aid: such calls take the
+        // generic kernel, the one that prints it, so the fast kernels carry no printf in their loops
+        kind = KERNEL_GENERIC;
+    } else if (small_supported(b->n, b->m)) {
+        kind = KERNEL_SMALL;
+    } else if (tile_supported(b->n, b->m)) {
+        kind = KERNEL_TILE;
+    } else if (block_supported(b->n, b->m, optin)) {
+        kind = KERNEL_BLOCK;
+    } else {
+        kind = KERNEL_GENERIC;
+    }
+    // The layout of a stored factor belongs to the kernel that wrote it (dense H^-1 for the tile and generic kernels, blocked
+    // LDL^T panels for the blocked kernel, nothing for the thread-per-QP kernel): solve() after setup()/update_qp() keeps that
+    // kernel even when the option or settings.verbose changed in between, and a REUSE of a factor another kernel kept is dropped.
+    if ((mode & MODE_LOAD_FACTOR) && b->fact_valid && b->fact_kernel != KERNEL_NONE && !sp) {
+        const bool compatible = (kind == b->fact_kernel) || (kind == KERNEL_TILE && b->fact_kernel == KERNEL_GENERIC) ||
+                                (kind == KERNEL_GENERIC && b->fact_kernel == KERNEL_TILE);  // both store the dense n x n inverse
+        if (!compatible) kind = b->fact_kernel;
+    }
+    if ((mode & MODE_REUSE) && b->keep_kernel != kind) mode &= ~MODE_REUSE;
+    if (ov_used) *ov_used = false;
+    if (ov && kind == KERNEL_TILE) {  // the register-tiled kernel honours MODE_FRESH: its epilogue writes the caller's arrays
+        mode |= MODE_FRESH;
+        p.x = ov->x; p.y = ov->y; p.z = ov->z;
+        p.status = ov->status; p.iter = ov->iter; p.rho_updates = ov->rho_updates;
+        p.rho_estimate = ov->rho_estimate; p.res_prim = ov->res_prim; p.res_dual = ov->res_dual;
+        if (ov_used) *ov_used = true;
+    }
+    p.mode = mode;
+    if (mode & MODE_KEEP_INITIAL) b->keep_kernel = kind;
+    if (mode & MODE_STORE_FACTOR) b->fact_kernel = kind;
+    const bool needs_fact = kind == KERNEL_BLOCK || kind == KERNEL_GENERIC ||
+                            (kind == KERNEL_TILE && (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE)));
     if (needs_fact) {
-        int rc = ensure_fact(b, want_block ? block_fact_doubles(b->n) : (size_t)b->n * b->n);
+        int rc = ensure_fact(b, kind == KERNEL_BLOCK ? block_fact_doubles(b->n) : (size_t)b->n * b->n);
         if (rc) return rc;
     }
     p.fact = b->fact;
     cudaError_t e;
-    if (want_cluster) {
+    if (kind == KERNEL_CLUSTER) {
         if (clusters > count) clusters = count;
         const size_t need = cluster_scratch_bytes(cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap, sp->cluster_size));
         if (need > b->cl_scratch_bytes) {
@@ -440,21 +521,25 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
             b->cl_scratch_bytes = need;
         }
         e = launch_cluster(p, clusters, b->cl_scratch, stream, c->last_kernel, sizeof c->last_kernel);
-    } else if (want_tile) {
+    } else if (kind == KERNEL_SMALL) {
+        e = launch_small(p, b->f32, stream, c->last_kernel, sizeof c->last_kernel);
+    } else if (kind == KERNEL_TILE) {
         e = launch_tile(p, c->prop.multiProcessorCount, c->opt_ctas_per_sm, c->opt_tile_warps, b->f32, stream, c->last_kernel, sizeof c->last_kernel);
-    } else if (want_block) {
+    } else if (kind == KERNEL_BLOCK) {
         e = launch_block(p, c->prop.multiProcessorCount, optin, stream, c->last_kernel, sizeof c->last_kernel);
     } else {
         if (!generic_supported(b->n, b->m, optin)) return fail(c, SQPB200_ERR_UNSUPPORTED, "(n, m) too large for the generic kernel");
         int grid = generic_grid(count, c->prop.multiProcessorCount);
-        int rc = ensure_scratch(c, generic_scratch_bytes(b->n, grid));
+        int rc = ensure_scratch(b, generic_scratch_bytes(b->n, grid));
         if (rc) return rc;
-        p.scratch = c->scratch;
+        p.scratch = b->gen_scratch;
         e = launch_generic(p, c->prop.multiProcessorCount, optin, stream, nullptr);
         snprintf(c->last_kernel, sizeof c->last_kernel, "generic");
     }
     if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "kernel launch", e);
     c->launches += 1;
+    b->last_stream = stream;
+    CK(c, cudaEventRecord(b->last_event, stream));
     return SQPB200_OK;
 }
 
@@ -539,6 +624,30 @@ int sqpb200_qp_batch_setup_solve(sqpb200_qp_batch *b, const sqpb200_qp_settings 
         b->fused_used = true;
     }
     return run(b, s, MODE_RESET | MODE_FACTOR | MODE_SOLVE, count, P, q, A, l, u, flags, stream);
+}
+
+int sqpb200_qp_batch_setup_solve_to(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P, const double *q,
+                                    const double *A, const double *l, const double *u, double *x, double *y, double *z, int *status,
+                                    int *iter, int *rho_updates, double *rho_estimate, double *res_prim, double *res_dual, void *stream_) {
+    if (!b) return SQPB200_ERR_INVALID;
+    sqpb200_ctx *c = b->ctx;
+    if (!s) return fail(c, SQPB200_ERR_INVALID, "settings is NULL");
+    if (count < 0 || count > b->batch) return fail(c, SQPB200_ERR_INVALID, "count outside [0, batch]");
+    if (!P || !q || !A || ((!l || !u) && b->m > 0)) return fail(c, SQPB200_ERR_INVALID, "NULL problem array");
+    if (!x || !y || !z || !status || !iter || !rho_updates || !rho_estimate || !res_prim || !res_dual)
+        return fail(c, SQPB200_ERR_INVALID, "sqpb200_qp_batch_setup_solve_to: every result array must be given");
+    if (count == 0) return SQPB200_OK;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CK(c, cudaMemsetAsync(b->total_iters, 0, sizeof(unsigned long long), stream));
+    b->fact_valid = false;
+    b->fused_used = true;
+    const OutOverride ov{x, y, z, status, iter, rho_updates, rho_estimate, res_prim, res_dual};
+    bool direct = false;
+    int rc = launch_range(b, s, MODE_RESET | MODE_FACTOR | MODE_SOLVE, 0, count, P, q, A, l, u, stream, nullptr, nullptr, &ov, &direct);
+    if (rc || direct) return rc;
+    // kernels without the direct epilogue: the object's state holds the results; copy them out behind the launch
+    return sqpb200_qp_batch_get(b, count, x, y, z, status, iter, rho_updates, rho_estimate, res_prim, res_dual, SQPB200_DEVICE_PTRS, stream_);
 }
 
 int sqpb200_qp_batch_setup_solve_opts(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P,
@@ -682,13 +791,13 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
             CK(c, cudaMemcpyAsync(b->sp2_inner, i2.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
             CK(c, cudaMemcpyAsync(b->sp2_perm, perm.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, stream));
         }
-        // packed entries for the cluster kernel: inner index (10 bits) | position of the value in the caller's order
+        // packed entries for the cluster kernel: inner index (PACK_BITS bits) | position of the value in the caller's order
         std::vector<unsigned> pack(2 * (size_t)(nnz > 0 ? nnz : 1));
         {
             unsigned *pc = pack.data(), *pr = pack.data() + nnz;  // CSC view, CSR view
             for (int e = 0; e < nnz; ++e) {
-                const unsigned given = (unsigned)h_inner[e] | ((unsigned)e << 10);
-                const unsigned other = (unsigned)i2[e] | ((unsigned)perm[e] << 10);
+                const unsigned given = (unsigned)h_inner[e] | ((unsigned)e << PACK_BITS);
+                const unsigned other = (unsigned)i2[e] | ((unsigned)perm[e] << PACK_BITS);
                 (csr ? pr : pc)[e] = given;
                 (csr ? pc : pr)[e] = other;
             }
@@ -745,6 +854,7 @@ int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, d
     CK(c, cudaSetDevice(c->device));
     cudaStream_t stream = (cudaStream_t)stream_;  // NULL is the CUDA legacy default stream
     const cudaMemcpyKind kind = (flags & SQPB200_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (int rc = order_after_last_launch(b, stream)) return rc;
     size_t B = count, n = b->n, m = b->m;
     if (x) CK(c, cudaMemcpyAsync(x, b->x, B * n * sizeof(double), kind, stream));
     if (y && m) CK(c, cudaMemcpyAsync(y, b->y, B * m * sizeof(double), kind, stream));
@@ -767,6 +877,7 @@ int sqpb200_qp_batch_set_iterates(sqpb200_qp_batch *b, int count, const double *
     CK(c, cudaSetDevice(c->device));
     cudaStream_t stream = (cudaStream_t)stream_;  // NULL is the CUDA legacy default stream
     const cudaMemcpyKind kind = (flags & SQPB200_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (int rc = order_after_last_launch(b, stream)) return rc;
     size_t B = count, n = b->n, m = b->m;
     if (x) CK(c, cudaMemcpyAsync(b->x, x, B * n * sizeof(double), kind, stream));
     if (y && m) CK(c, cudaMemcpyAsync(b->y, y, B * m * sizeof(double), kind, stream));
@@ -790,6 +901,7 @@ int sqpb200_qp_batch_total_iters(sqpb200_qp_batch *b, long long *total, void *st
     CK(c, cudaSetDevice(c->device));
     cudaStream_t stream = (cudaStream_t)stream_;  // NULL is the CUDA legacy default stream
     unsigned long long v = 0;
+    if (int rc = order_after_last_launch(b, stream)) return rc;
     CK(c, cudaMemcpyAsync(&v, b->total_iters, sizeof v, cudaMemcpyDeviceToHost, stream));
     CK(c, cudaStreamSynchronize(stream));
     *total = (long long)v;

@@ -84,6 +84,8 @@ __device__ __forceinline__ ClusterSmem carve_cluster(double *base, int np, int m
 // in the columns one CTA owns.
 int cluster_plan(int n, int m, int nnz, const int *colcount, size_t smem_optin, int *ccap) {
     if (!(n > 64 && n <= 256 && m >= 1 && nnz >= 0)) return 0;
+    // packed entries: a row index must fit PACK_BITS bits and a value position (nnz itself for the padding entry) the rest
+    if (m > (int)PACK_MASK + 1 || nnz >= PACK_MAX_NNZ - 1) return 0;
     const int np = cluster_np(n);
     for (int cs = 4; cs <= 8; cs *= 2) {
         const int rs = np / cs;
@@ -116,7 +118,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return fma(x, e, x);
 }
 
-// sparse dot product of one compressed row / column (entries [p0, p1) of a packed view: inner index | value position << 10)
+// sparse dot product of one compressed row / column (entries [p0, p1) of a packed view: inner index | value position << PACK_BITS)
 // with a shared-memory vector; everything it touches is in shared memory
 // `dummy` is a packed entry whose value slot holds 0.0: the last group of four is padded with it instead of a serial tail loop.
 __device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p1, const double *vals, const double *vec, unsigned dummy) {
@@ -126,10 +128,10 @@ __device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p
         const unsigned e1 = p + 1 < p1 ? pack[p + 1] : dummy;
         const unsigned e2 = p + 2 < p1 ? pack[p + 2] : dummy;
         const unsigned e3 = p + 3 < p1 ? pack[p + 3] : dummy;
-        a0 = fma(vals[e0 >> 10], vec[e0 & 1023u], a0);
-        a1 = fma(vals[e1 >> 10], vec[e1 & 1023u], a1);
-        a2 = fma(vals[e2 >> 10], vec[e2 & 1023u], a2);
-        a3 = fma(vals[e3 >> 10], vec[e3 & 1023u], a3);
+        a0 = fma(vals[e0 >> PACK_BITS], vec[e0 & PACK_MASK], a0);
+        a1 = fma(vals[e1 >> PACK_BITS], vec[e1 & PACK_MASK], a1);
+        a2 = fma(vals[e2 >> PACK_BITS], vec[e2 & PACK_MASK], a2);
+        a3 = fma(vals[e3 >> PACK_BITS], vec[e3 & PACK_MASK], a3);
     }
     return (a0 + a1) + (a2 + a3);
 }
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
     ClusterSmem s = carve_cluster(smem_raw, np, m, nnz, ccap, CS);
     double *vals = s.X;
     unsigned *cpack = reinterpret_cast<unsigned *>(s.X + (nnz + 2 - (nnz & 1)));  // vals has one extra slot holding 0.0
-    const unsigned dummy = (unsigned)nnz << 10;
+    const unsigned dummy = (unsigned)nnz << PACK_BITS;
     unsigned *rpack = cpack + ccap;
     int *couter = reinterpret_cast<int *>(rpack + nnz), *router = couter + RS + 1;  // couter: own columns, relative to the slice
     double *Rb = s.X, *Tm = s.X + 2 * LDR * RCH, *Eb = Tm + (size_t)LDT * KB;
@@ -283,8 +285,8 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                     int r0_l = 0, r1_l = 0;
                     if (lane < cnt) {
                         const unsigned ec = cpack[base + lane];
-                        const int k = (int)(ec & 1023u);
-                        f_l = s.sw[k] * vals[ec >> 10];
+                        const int k = (int)(ec & PACK_MASK);
+                        f_l = s.sw[k] * vals[ec >> PACK_BITS];
                         r0_l = router[k];
                         r1_l = router[k + 1];
                     }
@@ -293,8 +295,8 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                         const int r0 = __shfl_sync(0xffffffffu, r0_l, t), r1 = __shfl_sync(0xffffffffu, r1_l, t);
                         for (int pr = r0 + lane; pr < r1; pr += 32) {
                             const unsigned er = rpack[pr];
-                            double *dst = s.S + r + LD * (int)(er & 1023u);
-                            *dst = fma(f, vals[er >> 10], *dst);
+                            double *dst = s.S + r + LD * (int)(er & PACK_MASK);
+                            *dst = fma(f, vals[er >> PACK_BITS], *dst);
                         }
                         __syncwarp();
                     }

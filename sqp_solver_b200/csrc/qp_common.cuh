@@ -36,6 +36,8 @@ enum : unsigned {
     MODE_STORE_FACTOR = 8u,  // keep H^-1, rho, constraint classes for a later solve() launch
     MODE_LOAD_FACTOR = 16u,  // solve() after a separate setup()/update_qp()
     MODE_KEEP_INITIAL = 32u, // with FACTOR: remember the setup factor (for settings.rho) in the slab, tagged with its rho
+    MODE_FRESH = 128u,       // the instances are default-constructed solvers (status UNINITIALIZED, counters 0): do not read the
+                             // status / info arrays, only write them (they may be caller arrays in peer memory, never initialised)
     MODE_REUSE = 64u,        // with FACTOR: same P, A as the launch that kept the factor; skip the factorisation of every
                              // instance whose constraint classes and rho are unchanged (the TODO at reference sqp.cpp:273)
 };
@@ -43,11 +45,17 @@ enum : unsigned {
 // Sparse constraint matrix with one pattern shared by the batch (blocked kernel). Both a row-compressed and a
 // column-compressed view of the pattern are given; `vals` is stored in the order of ONE of them (perm == nullptr) and the
 // other view reaches it through its perm array. row_outer == nullptr means "A is dense".
+// packed sparse entries (cluster kernel): inner index in the low PACK_BITS bits, position of the value above them. The inner
+// index is a row (< 2048 = 8 CTAs x 256 rows) or a column (< 256); the value position must stay below 2^(32 - PACK_BITS).
+constexpr int PACK_BITS = 11;
+constexpr unsigned PACK_MASK = (1u << PACK_BITS) - 1u;
+constexpr int PACK_MAX_NNZ = 1 << (32 - PACK_BITS);
+
 struct SparseA {
     const int *row_outer, *row_inner, *row_perm;  // CSR view: row_outer[m+1], row_inner[nnz] = column indices
     const int *col_outer, *col_inner, *col_perm;  // CSC view: col_outer[n+1], col_inner[nnz] = row indices
     const double *vals;                           // [B][nnz]
-    const unsigned *col_pack, *row_pack;          // per stored entry of the CSC / CSR view: inner index | (position in vals << 10)
+    const unsigned *col_pack, *row_pack;          // per stored entry of the CSC / CSR view: inner index | (position in vals << PACK_BITS)
     int nnz;
     int col_slice_cap;  // cluster kernel: most stored entries in the columns one CTA owns
     int cluster_size;   // cluster kernel: CTAs per QP (4 or 8); 0 = not planned for the cluster kernel
@@ -171,6 +179,10 @@ cudaError_t launch_generic(const KernelParams &p, int sm_count, size_t smem_opti
 size_t generic_scratch_bytes(int n, int grid);
 int generic_grid(int count, int sm_count);
 bool generic_supported(int n, int m, size_t smem_optin);
+cudaError_t measure_dfma_peak(int sm_count, cudaStream_t stream, double *seconds, double *fma_count);  // peak_fp64.cu
+// thread-per-QP literal KKT kernel for n + m <= 16 (qp_small.cu)
+bool small_supported(int n, int m);
+cudaError_t launch_small(const KernelParams &p, int f32, cudaStream_t stream, char *name, size_t name_len);
 // blocked kernel for 64 < n <= 256 (qp_block.cu)
 bool block_supported(int n, int m, size_t smem_optin);
 bool block_sparse_supported(int n, int m, int nnz, size_t smem_optin);

@@ -336,14 +336,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #define gl (p.l + (size_t)bi * m)
 #define gu (p.u + (size_t)bi * m)
 
-        int status = p.status[b];
+        const bool fresh = (p.mode & MODE_FRESH) != 0;  // default-constructed solvers: the info arrays are write-only
+        int status = fresh ? (int)SQPB200_UNINITIALIZED : p.status[b];
         // rho_estimate / res_prim / res_dual (QPSolverInfo, qp.hpp:76-78) only change at checks: kept in shared memory
         if (tid == 0) {
-            s_info[0] = p.rho_estimate[b];
-            s_info[1] = p.res_prim[b];
-            s_info[2] = p.res_dual[b];
+            s_info[0] = fresh ? 0.0 : p.rho_estimate[b];
+            s_info[1] = fresh ? 0.0 : p.res_prim[b];
+            s_info[2] = fresh ? 0.0 : p.res_dual[b];
             s_info[3] = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
-            s_cnt[0] = p.rho_updates[b] + ((p.mode & MODE_FACTOR) ? 1 : 0);  // rho_vec_update, qp.cpp:313
+            s_cnt[0] = (fresh ? 0 : p.rho_updates[b]) + ((p.mode & MODE_FACTOR) ? 1 : 0);  // rho_vec_update, qp.cpp:313
         }
         const S rho0 = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
         const bool reset = (p.mode & MODE_RESET) != 0;
@@ -648,7 +649,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         if (do_factor && (p.mode & MODE_REUSE)) {
             // same P and A as the launch that kept the factor: reuse it where classes and rho are unchanged
             // (duplicate owner lanes read the old classes before the primary wrote the same row: benign, values equal or both differ)
-            const bool reuse = cta_all<NW>(same_classes && p.fact_rho[b] == st.rho);
+            // (compared in the compute scalar: the fp32 instantiation tags the slab with the rounded rho)
+            const bool reuse = cta_all<NW>(same_classes && (S)p.fact_rho[b] == (S)st.rho);
             if (reuse) {
                 do_factor = false;
                 status = SQPB200_UNSOLVED;
@@ -689,6 +691,9 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 do_factor = false;
                 if (!in_solve) {
                     status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+                    // A factorisation that is not written to the slab leaves an older kept factor behind whose classes were just
+                    // overwritten: forget it (also on failure), or a later REUSE would match the new classes against the old factor.
+                    if (tid == 0 && !(ok && (p.mode & MODE_KEEP_INITIAL))) p.fact_rho[b] = __longlong_as_double(0x7ff8000000000000LL);
                     if (ok && (p.mode & MODE_KEEP_INITIAL)) {
                         double *gF = p.fact + b * n * n;
 #pragma unroll
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                                 if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
                             }
                         }
-                        if (tid == 0) p.fact_rho[b] = s_info[3];
+                        if (tid == 0) p.fact_rho[b] = st.rho;
                     }
                 } else if (!ok) {
                     status = SQPB200_NUMERICAL_ISSUES;  // qp.cpp:139-142 (break before the loop increment)

@@ -159,19 +159,24 @@ class PeerBatch:
         self._api = api
 
     def load(self, problem, stream=None):
+        """Root copies the problem into the shared input arrays; returns on every rank once the data has landed (stream
+        synchronisation on the root + barrier), so a following solve() on any rank reads complete inputs."""
         if self.rank == self.root:
             for k in PROBLEM_KEYS:
                 t = problem[k].contiguous()
                 self.ctx.dev_copy(self.buf[("in", k)], t, t.numel() * 8, stream)
+            torch.cuda.synchronize()
+        dist.barrier()
 
     def solve(self, qbatch, stream=None):
         cnt = self.hi - self.lo
         if cnt <= 0:
             return
         ins = [self.buf[("in", k)].offset(self.lo * self.IN_WIDTH(k)) for k in PROBLEM_KEYS]
-        qbatch.setup_solve(*ins, count=cnt, stream=stream)
         outs = {k: self.buf[("out", k)].offset(self.lo * self.out_width[k]) for k in RESULT_DTYPES}
-        qbatch.get_into(count=cnt, stream=stream, **outs)
+        # ONE kernel per rank and nothing else: inputs pulled from the owner's HBM by the kernel's TMA loads, results written into
+        # the owner's arrays by the kernel's epilogue
+        qbatch.setup_solve_to(*ins, outs, count=cnt, stream=stream)
 
     def results(self):
         """Barrier, then (root) the whole-batch results as CUDA tensors."""

@@ -133,12 +133,9 @@ def test_sqp_trajectory_matches_oracle(oracle, golden):
         # the reference's own pin: isApprox(solution, 1e-2) and iter < max_iter
         assert np.sum((x - sol) ** 2) <= 1e-4 * min(np.sum(x * x), np.sum(np.square(sol))), name
         assert g["iter"] < 100, name
-        if name == "RosenbrockBox2":
-            # From a feasible start constraint_norm returns eps, mu is ~1e16 and the Armijo test is decided by ~1e-6 of ADMM
-            # infeasibility: the outer trajectory is noise-decided (35 outer iterations here, 40 in the CPU
-            # oracle, both within the reference's 1e-2 assertion), so only the reference's own pin is checked for this problem.
-            continue
-        # oracle parity
+        # oracle parity. (RosenbrockBox2: from a feasible start constraint_norm returns eps, mu is ~1e16 and the Armijo test is decided
+        # by ~1e-6 of ADMM infeasibility, SURVEY.md Appendix B.3 -- the trajectory only coincides because the QP subproblems are
+        # solved with the reference's own arithmetic.)
         assert (g["iter"], g["qp_solver_iter"], g["status"]) == (ref["iter"], ref["qp_solver_iter"], ref["status"]), (name, g, ref)
         assert np.linalg.norm(x - ref["x"]) <= 1e-6 * np.linalg.norm(ref["x"]), name
         assert np.abs(np.array(g["lambda"]) - ref["lam"]).max() <= 1e-5 * max(1.0, np.abs(ref["lam"]).max()), name
@@ -164,18 +161,12 @@ def test_sqp_generated_subproblems_match_oracle(oracle):
         out = b.get()
         ref = dict(x=tr["x"], y=tr["y"], status=tr["status"], iter=tr["iter"])
         out.pop("rho_updates")
-        # Late SQP iterations hand over BFGS Hessians with cond(P) up to 1e14 and steps 1e-5 small next to
-        # |q| ~ 60: there the 1e-6 bar is applied on the scale of the data (floor 1.0), not of the tiny step.
-        # An infeasible subproblem (zero Jacobian row with l = u != 0 at x0 = 0) never converges and its duals
-        # diverge: they are not compared.
-        # Subproblems that stop at max_iter (100) are unconverged iterates of a sensitive recursion with adaptive rho;
-        # there the explicit H^-1 mat-vec and the oracle's KKT substitution differ by up to ~1e-8 ABSOLUTE on O(1)
-        # data (the oracle itself is ~1e-9 from a long-double run, see DESIGN.md "Numerics"): the bar is 1e-7 absolute there.
-        condP = np.array([np.linalg.cond(tr["P"][i].reshape(nx, nx)) for i in range(k)])
-        floor = np.where(condP > 1e7, 1.0, np.where(tr["status"] == api.MAX_ITER_EXCEEDED, 1e-1, 0.0))
-        diverged = (tr["status"] == api.MAX_ITER_EXCEEDED) & (np.abs(tr["y"]).max(axis=1) > 1e3)
-        assert_parity(out, ref, what="SQP-generated QPs of problem %d" % pid, x_norm_floor=floor, skip_y=diverged)
-        assert (floor == 0).sum() >= k // 3  # the converged, well-conditioned subproblems are held to the strict relative bar
+        # These sizes (n + m <= 16) run the thread-per-QP literal KKT kernel, the reference's formulation operation by operation:
+        # strict 1e-6 relative on EVERY subproblem -- cond(P) up to 1e14, steps 1e-5 next to |q| ~ 60, subproblems that stop at
+        # max_iter, the infeasible one whose duals diverge -- with no floor and nothing skipped. (tests/test_small_kernel_gpu.py
+        # holds the same subproblems to bit identity.)
+        assert ctx.last_kernel.startswith("small<"), ctx.last_kernel
+        assert_parity(out, ref, what="SQP-generated QPs of problem %d" % pid)
         b.close()
     ctx.close()
 
@@ -199,10 +190,8 @@ def test_batch_sqp_config4_full_size(oracle):
         ref = S.solve(S.CONSTRAINED_ROSENBROCK_2D, inst["x0"], [0, 0], S.default_settings())
         same = (inst["iter"], inst["qp_solver_iter"], inst["status"]) == (ref["iter"], ref["qp_solver_iter"], ref["status"])
         if same:
-            # the outer loop stops on step norms <= 1e-4 (sqp.hpp:17-18); late subproblems carry cond(P) up to 1e14, so
-            # two fp64 runs of the same trajectory agree to the SQP tolerance, not to QP-level 1e-6
-            assert np.linalg.norm(np.array(inst["x"]) - ref["x"]) <= 1e-4 * max(np.linalg.norm(ref["x"]), 1e-3)
+            assert np.linalg.norm(np.array(inst["x"]) - ref["x"]) <= 1e-6 * np.linalg.norm(ref["x"])
         agree += same
-    # the reference's l1-merit line search is decided by ~1e-6 noise from feasible-side iterates,
-    # so a few trajectories may branch differently from the oracle's; the large majority must coincide
-    assert agree >= int(0.8 * len(d["instances"])), "only %d of %d trajectories match the oracle" % (agree, len(d["instances"]))
+    # the reference's l1-merit line search is decided by ~1e-6 noise from feasible-side iterates: the
+    # trajectories only coincide because the QP subproblems are solved with the reference's own arithmetic
+    assert agree >= len(d["instances"]) - 1, "only %d of %d trajectories match the oracle" % (agree, len(d["instances"]))

@@ -295,7 +295,7 @@ def test_fused_then_solve_is_rejected(api, ctx):
 
 def test_full_size_properties_config3(api, ctx, oracle):
     """BASELINE config 3 at full size (batch 8192, n=64, m=128): size-independent properties on every
-    instance plus oracle parity on a seeded sample of 64."""
+    instance plus oracle parity on EVERY instance (the CPU oracle needs ~10 s for the batch on the box's cores)."""
     import torch
     from sqp_solver_b200.synth import make_batch
 
@@ -326,10 +326,28 @@ def test_full_size_properties_config3(api, ctx, oracle):
     # z is inside the box, y obeys the sign pattern of an active-set multiplier
     l, u = torch.from_numpy(d["l"]).cuda(), torch.from_numpy(d["u"]).cuda()
     assert bool(((z >= l) & (z <= u)).all())
-    idx = np.random.default_rng(123).choice(B, 64, replace=False)
-    ref = oracle.solve_batch(d["P"][idx], d["q"][idx], d["A"][idx], d["l"][idx], d["u"][idx], oracle_settings_from(oracle, s))
-    sub = {k: v[idx] for k, v in out.items() if isinstance(v, np.ndarray)}
-    assert_parity(sub, ref, what="config 3 sample")
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    worst = assert_parity(out, ref, what="config 3, all 8192 instances, S1")
+    print("config 3 S1: all %d instances agree with the oracle (status, iter, rho_updates); worst x rel err %.2e" % (B, worst))
+
+
+@pytest.mark.parametrize("config,B,n,m", [("config2", 1024, 32, 64), ("config3", 8192, 64, 128)])
+@pytest.mark.parametrize("settings_name", ["S1", "S2"])
+def test_full_batch_oracle_parity(api, ctx, oracle, config, B, n, m, settings_name):
+    """BASELINE configs 2 and 3 at their full batch sizes, reference defaults (S1) and the SQP constructor's regime
+    (S2: alpha 1.6 + adaptive rho): EVERY instance against the CPU oracle -- status, iteration count, rho updates, x within 1e-6
+    relative, y within 1e-5. Failures are listed one by one (helpers.assert_parity), never sampled or averaged."""
+    from sqp_solver_b200.synth import make_batch
+
+    if config == "config3" and settings_name == "S1":
+        pytest.skip("covered by test_full_size_properties_config3")
+    d = make_batch(B, n, m, seed0=0)
+    s = api.default_settings(**({} if settings_name == "S1" else dict(alpha=1.6, adaptive_rho=1)))
+    out = run_fused(api, ctx, d, s, "auto")
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+    worst = assert_parity(out, ref, what="%s, all %d instances, %s" % (config, B, settings_name))
+    assert out["total_iters"] == int(np.minimum(ref["iter"], s.max_iter).sum())
+    print("%s %s (%s): all %d instances agree with the oracle; worst x rel err %.2e" % (config, settings_name, out["kernel"], B, worst))
 
 
 @pytest.mark.parametrize("kernel", ["auto", "generic"])
@@ -623,18 +641,20 @@ def test_randomised_shapes_and_settings(api, ctx, oracle, kernel):
         ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], os_)
         # Adaptive rho takes rho * sqrt(res_prim / res_dual) of NORMALISED residuals: when one of them sits at rounding level
         # (e.g. no active constraint: A x - z is pure solve noise, ~1e-13 through the KKT substitution and ~1e-16 through
-        # z~ = A x~) the new rho -- and everything after it -- is decided by that noise and no two implementations agree
-        # (found by this sweep: n=2, m=3, rho 5566 -> 1.5e-4 in the oracle vs the 1e-6 clamp here). The oracle records the
-        # smallest normalised residual it ever fed to rho_estimate; instances below 1e-9 are excluded from the comparison.
+        # z~ = A x~) the new rho -- and everything after it -- is decided by that noise and only the SAME arithmetic reproduces it
+        # (found by this sweep: n=2, m=3, rho 5566 -> 1.5e-4 in the oracle vs the 1e-6 clamp in the Schur-complement kernels).
+        # The thread-per-QP kernel (n + m <= 16 under "auto") is that arithmetic and is compared on every instance; for the other
+        # kernels the oracle records the smallest normalised residual it ever fed to rho_estimate and instances below 1e-9 are excluded.
         stable = ref["diag_min_norms"].min(axis=1) > 1e-9
+        if out["kernel"].startswith("small<"):
+            stable[:] = True
         n_total += batch
         n_stable += int(stable.sum())
         if not stable.any():
             continue
         sub = lambda o: {k: v[stable] for k, v in o.items() if isinstance(v, np.ndarray) and v.shape[:1] == (batch,)}
-        # unconverged adaptive-rho runs are sensitive recursions: 1e-6 is applied on a floor of 1e-2 there (Numerics)
-        floor = np.where(ref["status"][stable] == api.MAX_ITER_EXCEEDED, 1e-2, 0.0)
-        assert_parity(sub(out), sub(ref), what="fuzz case %d n=%d m=%d %s %s" % (case, n, m, out["kernel"], kw), x_norm_floor=floor)
+        # strict bar everywhere: converged or not, 1e-6 relative on x with no floor
+        assert_parity(sub(out), sub(ref), what="fuzz case %d n=%d m=%d %s %s" % (case, n, m, out["kernel"], kw))
     assert n_stable >= 0.9 * n_total, "only %d of %d fuzz instances are numerically stable in the oracle" % (n_stable, n_total)
 
 
@@ -908,7 +928,8 @@ def test_unconstrained_qp_m_zero(api, ctx, oracle, kernel, n):
 def test_full_size_properties_config5(api, ctx, oracle):
     """BASELINE config 5 at full size (batch 2048 sparse-A QPs, n=256, m=512, one CSR pattern, SQP settings) through the cluster
     kernel: size-independent properties on every instance (the termination test recomputed independently in torch fp64 from the
-    returned x, z, y; z inside the box; iteration counts on the check grid) plus oracle parity on a seeded sample."""
+    returned x, z, y; z inside the box; iteration counts on the check grid) plus oracle parity on a seeded sample of 192 instances
+    (the densified CPU oracle runs ~100 of these per second on 16 cores)."""
     import torch
     from sqp_solver_b200.synth import densify, make_sparse_batch
 
@@ -938,7 +959,7 @@ def test_full_size_properties_config5(api, ctx, oracle):
     np.testing.assert_allclose(out["res_dual"], rd.cpu().numpy(), rtol=1e-6, atol=1e-10)
     l, u = torch.from_numpy(d["l"]).cuda(), torch.from_numpy(d["u"]).cuda()
     assert bool(((z >= l) & (z <= u)).all())
-    idx = np.random.default_rng(321).choice(B, 6, replace=False)
+    idx = np.sort(np.random.default_rng(321).choice(B, 192, replace=False))
     sub_d = dict(d, vals=d["vals"][idx], batch=len(idx))
     ref = oracle.solve_batch(d["P"][idx], d["q"][idx], densify(sub_d), d["l"][idx], d["u"][idx], oracle_settings_from(oracle, s))
     sub = {k: v[idx] for k, v in out.items() if isinstance(v, np.ndarray)}
