@@ -23,7 +23,7 @@ enum { ORC_INEQUALITY_CONSTRAINT = 0, ORC_EQUALITY_CONSTRAINT = 1, ORC_LOOSE_BOU
 #define ORC_FABS fabs
 #define ORC_FMAX fmax
 #define ORC_FMIN fmin
-#define ORC_SQRT sqrt
+#define ORC_RHO_EST(rho0, arg) ((rho0) * sqrt(arg)) /* qp.cpp:338 */
 #define ORC_EPS DBL_EPSILON /* DIV_BY_ZERO_REGUL, qp.hpp:141 */
 #define ORC_MINPOS DBL_MIN
 #include "qp_oracle_impl.h"
@@ -32,7 +32,7 @@ enum { ORC_INEQUALITY_CONSTRAINT = 0, ORC_EQUALITY_CONSTRAINT = 1, ORC_LOOSE_BOU
 #undef ORC_FABS
 #undef ORC_FMAX
 #undef ORC_FMIN
-#undef ORC_SQRT
+#undef ORC_RHO_EST
 #undef ORC_EPS
 #undef ORC_MINPOS
 
@@ -42,7 +42,9 @@ enum { ORC_INEQUALITY_CONSTRAINT = 0, ORC_EQUALITY_CONSTRAINT = 1, ORC_LOOSE_BOU
 /* the reference calls the double overloads fmax/fmin/sqrt on float arguments (src/qp.cpp:131, :338) */
 #define ORC_FMAX(a, b) ((float)fmax((double)(a), (double)(b)))
 #define ORC_FMIN(a, b) ((float)fmin((double)(a), (double)(b)))
-#define ORC_SQRT(a) ((float)sqrt((double)(a)))
+/* qp.cpp:338 `Scalar rho_new = rho0 * sqrt(...)`: with <cmath> only, unqualified sqrt(float) is ::sqrt(double) and returns a double, so
+ * the PRODUCT is formed in double and rounded to float once, on assignment (verified against oracle/_ref, the reference's own code) */
+#define ORC_RHO_EST(rho0, arg) ((float)((double)(rho0) * sqrt((double)(arg))))
 #define ORC_EPS FLT_EPSILON
 #define ORC_MINPOS FLT_MIN
 #include "qp_oracle_impl.h"

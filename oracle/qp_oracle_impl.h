@@ -426,7 +426,7 @@ static SCALAR FN(orc_rho_estimate)(FN(oracle_solver) * s, SCALAR rho0) {
     SCALAR rd_norm = s->info.res_dual / (s->max_Px_ATy_q_norm + ORC_EPS);
     if ((double)rp_norm < s->diag_min_rp_norm) s->diag_min_rp_norm = (double)rp_norm;
     if ((double)rd_norm < s->diag_min_rd_norm) s->diag_min_rd_norm = (double)rd_norm;
-    return rho0 * ORC_SQRT(rp_norm / (rd_norm + ORC_EPS));
+    return ORC_RHO_EST(rho0, rp_norm / (rd_norm + ORC_EPS));
 }
 
 /* src/qp.cpp:363-371 with eps_prim / eps_dual :343-351 */

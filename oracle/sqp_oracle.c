@@ -180,6 +180,7 @@ int oracle_sqp_make_problem(int id, int n, sqp_problem *p) {
     return 1;
 }
 
+#ifndef SQP_ORACLE_PROBLEMS_ONLY /* oracle/_ref links only the problem definitions above (oracle/ref_shim.cpp) */
 /* ---- SQP --------------------------------------------------------------------------------------- */
 typedef struct { /* sqp_settings_t, sqp.hpp:13-31 */
     double tau, eta, rho, eps_prim, eps_dual;
@@ -460,3 +461,4 @@ int oracle_is_posdef(const double *H, int n) {
     free(w);
     return r;
 }
+#endif /* SQP_ORACLE_PROBLEMS_ONLY */

@@ -168,7 +168,9 @@ __device__ __forceinline__ S rho_estimate_clamped_t(S rho, S rp, S rd, S sc_p, S
     const S eps = sizeof(S) == 8 ? S(DIV_BY_ZERO_REGUL) : S(1.1920928955078125e-7);  // numeric_limits<Scalar>::epsilon()
     S rp_norm = rp / (sc_p + eps);
     S rd_norm = rd / (sc_d + eps);
-    S r = rho * sqrt(rp_norm / (rd_norm + eps));
+    // `Scalar rho_new = rho0 * sqrt(...)` (qp.cpp:338): sqrt is the double overload for a float argument too, so the product is
+    // formed in double and rounded to Scalar once (the CPU path's exact semantics; matters for the float instantiation only)
+    S r = (S)((double)rho * sqrt((double)(rp_norm / (rd_norm + eps))));
     return fmax(S(RHO_MIN), fmin(r, S(RHO_MAX)));
 }
 

@@ -16,8 +16,8 @@
 #include <limits>
 #include <vector>
 
+#include "../../overlay/solvers/qp.hpp"
 #include "bfgs.hpp"
-#include "qp.hpp"
 
 namespace sqp {
 
@@ -132,6 +132,7 @@ struct Instance {
     Scalar dual_step_norm_ = 0, primal_step_norm_ = 0;
     Info info_;
     bool active = true;
+    int last_qp_iter = 0;  // info().iter of this instance's own QPSolver: a setup that fails leaves it stale (qp.cpp:68-71, sqp.cpp:224)
 
     void init(Problem &prob) {  // src/sqp.cpp:48-66
         const int nx = prob.num_var, nc = prob.num_constr;
@@ -152,6 +153,7 @@ struct Instance {
         info_.iter = 0;
         info_.status = MAX_ITER_EXCEEDED;
         active = true;
+        last_qp_iter = 0;
     }
 
     // Linearise and build the QP  min 0.5 p'Hp + g'p  s.t.  l - c <= J p <= u - c   (src/sqp.cpp:139-197)
@@ -467,7 +469,10 @@ class BatchSQP {
         for (int k = 0; k < na; ++k) {
             auto &I = inst_[slot_[k]];
             const auto qi = qp_.info(k);
-            I.info_.qp_solver_iter += qi.iter;
+            // A QP whose setup fails is not solved (qp.cpp:68-71), so the reference adds its solver's STALE info().iter (sqp.cpp:224):
+            // the count of this instance's previous subproblem -- not whatever instance last occupied batch slot k.
+            if (qi.status != qp_solver::NUMERICAL_ISSUES) I.last_qp_iter = qi.iter;
+            I.info_.qp_solver_iter += I.last_qp_iter;
             if (qi.status == qp_solver::NUMERICAL_ISSUES) continue;  // keep the stale step, like the reference
             const double *xs = qp_.primal_solution(k), *ys = qp_.dual_solution(k);
             for (int i = 0; i < nx_; ++i) I.p(i) = xs[i];

@@ -8,10 +8,12 @@
 //   qp_solver::BatchQPSolver              NEW: B independent QPSolver<double> instances in one object
 //                                         (the data-parallel axis; reference call site src/sqp.cpp:221-222)
 //
-// Same names, fields, defaults, enum values and call order as the reference, so src/sqp.cpp-style
-// code compiles against this header. Everything numeric happens on the GPU through the C-ABI of
-// include/sqp_b200_qp.h; there is no CPU fallback (constructing a solver without a B200 throws).
-// QPSolver<float> converts to double at the boundary and computes in fp64 on the device.
+// Same names, fields, defaults, enum values and call order as the reference: this directory (host/overlay) holds ONLY
+// solvers/qp.hpp (+ its dense.hpp), so putting it BEFORE the reference's include/ on the include path replaces exactly that
+// header -- the reference's own src/sqp.cpp, include/solvers/sqp.hpp and bfgs.hpp then compile unmodified against it
+// (tests/test_dropin.py builds the reference's src/sqp.cpp and its gtest files that way). Everything numeric happens on the GPU
+// through the C-ABI of include/sqp_b200_qp.h; there is no CPU fallback (constructing a solver without a B200 throws).
+// QPSolver<float> is the fp32 instantiation on the device too (sqpb200_qp_batch_set_precision); the ABI's arrays stay double.
 #pragma once
 #include <cstdio>
 #include <limits>
@@ -20,7 +22,7 @@
 #include <string>
 #include <vector>
 
-#include "../../../include/sqp_b200_qp.h"
+#include "../../../../include/sqp_b200_qp.h"
 #include "dense.hpp"
 
 #define QP_SOLVER_PRINTING

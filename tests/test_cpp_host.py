@@ -1,5 +1,5 @@
 """Builds and runs the C++ tests of the host-side mirror of the reference interface
-(sqp_solver_b200/host/solvers/*.hpp). They read like the reference's own GoogleTest files."""
+(sqp_solver_b200/host/overlay/solvers/qp.hpp, host/batch/solvers/{sqp,bfgs}.hpp). They read like the reference's own GoogleTest files."""
 import json
 import os
 import subprocess
@@ -19,7 +19,8 @@ def compile_cpp(name):
     os.makedirs(OUT, exist_ok=True)
     exe = os.path.join(OUT, name)
     libdir = os.path.join(ROOT, "sqp_solver_b200")
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(libdir, "host"), os.path.join(CPP, name + ".cpp"),
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(libdir, "host", "overlay"), "-I" + os.path.join(libdir, "host", "batch"),
+           os.path.join(CPP, name + ".cpp"),
            "-fopenmp", "-o", exe, "-L" + libdir, "-lsqp_b200", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64",
            "-Wl,-rpath,/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
@@ -49,8 +50,8 @@ def test_host_mirror_is_cxx11_like_the_reference():
     (solvers/qp.hpp, sqp.hpp, bfgs.hpp) and every C++ test must compile in that mode, warning-free, so that src/sqp.cpp can include it."""
     libdir = os.path.join(ROOT, "sqp_solver_b200")
     for name in ("test_qp_solver", "test_sqp", "test_bfgs", "sqp_cli"):
-        r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-Wall", "-Wextra", "-fsyntax-only", "-I" + os.path.join(libdir, "host"),
-                            os.path.join(CPP, name + ".cpp")], capture_output=True, text=True)
+        r = subprocess.run(["/usr/bin/g++", "-std=c++11", "-Wall", "-Wextra", "-fsyntax-only", "-I" + os.path.join(libdir, "host", "overlay"),
+                            "-I" + os.path.join(libdir, "host", "batch"), os.path.join(CPP, name + ".cpp")], capture_output=True, text=True)
         assert r.returncode == 0 and "warning" not in r.stderr, name + "\n" + r.stderr
 
 
