@@ -137,6 +137,10 @@ int sqpb200_qp_batch_set_precision(sqpb200_qp_batch *b, int fp32);
  * results straight into the owner's arrays (sqpb200_qp_batch_get with device pointers into the imported mapping): no separate split
  * or gather step, the transfer overlaps the solve QP by QP. Buffers come from sqpb200_dev_alloc (so that a handle maps the whole
  * allocation), are exported as 64-byte CUDA IPC handles, and imported by the other processes of the node. */
+/* page-locked host buffers for HOST_PTRS callers that call every few hundred microseconds (the SQP outer loop, src/sqp.cpp:210-242):
+ * copies from pinned memory are asynchronous and need no intermediate staging by the driver */
+int sqpb200_host_alloc(sqpb200_ctx *ctx, size_t bytes, void **host_ptr);
+int sqpb200_host_free(sqpb200_ctx *ctx, void *host_ptr);
 #define SQPB200_IPC_HANDLE_BYTES 64
 int sqpb200_dev_alloc(sqpb200_ctx *ctx, size_t bytes, void **dev_ptr);
 int sqpb200_dev_free(sqpb200_ctx *ctx, void *dev_ptr);

@@ -21,6 +21,9 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* ---- QP oracle (qp_oracle.c) ---------------------------------------------------------------- */
 typedef struct {
@@ -447,6 +450,25 @@ int oracle_sqp_solve_builtin(int prob_id, int n, const sqp_settings *settings, c
     sqp_problem p;
     if (oracle_sqp_make_problem(prob_id, n, &p)) return 1;
     return oracle_sqp_solve(&p, settings, x0, lambda0, x_out, lambda_out, info_out, trace);
+}
+
+/* B independent SQP solves of one built-in problem from B starting points, OpenMP dynamic schedule over the host cores: the CPU
+ * side of BASELINE config 4 (bench.py's cpu_baseline for the batched-SQP record). */
+int oracle_sqp_solve_batch(int prob_id, int n, const sqp_settings *settings, int batch, const double *x0, const double *lambda0,
+                           double *x_out, double *lambda_out, sqp_info *info_out, int nthreads) {
+    sqp_problem p;
+    if (oracle_sqp_make_problem(prob_id, n, &p)) return -1;
+    const int nx = p.num_var, nc = p.num_constr;
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    used = nthreads;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(nthreads)
+#endif
+    for (int b = 0; b < batch; ++b)
+        oracle_sqp_solve(&p, settings, x0 + (size_t)b * nx, lambda0 + (size_t)b * nc, x_out + (size_t)b * nx, lambda_out + (size_t)b * nc,
+                         info_out + b, NULL);
+    return used;
 }
 
 /* standalone BFGS entry for tests/bfgs_test.cpp-style checks */

@@ -87,3 +87,23 @@ def is_posdef(H):
     f = qp_oracle.lib().oracle_is_posdef
     f.restype = C.c_int
     return bool(f(H.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(H.shape[0])))
+
+
+def solve_batch(prob_id, x0, lambda0, settings=None, nthreads=0):
+    """B independent SQP<double>::solve runs (one built-in problem, B starts) over the host cores. x0: [B, nx], lambda0: [B, nc].
+    Returns dict(x, lam, iter, qp_solver_iter, status, threads)."""
+    L = qp_oracle.lib()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    lambda0 = np.ascontiguousarray(lambda0, dtype=np.float64)
+    B, nx = x0.shape
+    nc = lambda0.shape[1]
+    s = settings or default_settings()
+    x, lam = np.zeros((B, nx)), np.zeros((B, nc))
+    info = (Info * B)()
+    dp = C.POINTER(C.c_double)
+    L.oracle_sqp_solve_batch.restype = C.c_int
+    used = L.oracle_sqp_solve_batch(C.c_int(prob_id), C.c_int(nx), C.byref(s), C.c_int(B), x0.ctypes.data_as(dp), lambda0.ctypes.data_as(dp),
+                                    x.ctypes.data_as(dp), lam.ctypes.data_as(dp), info, C.c_int(nthreads))
+    assert used >= 1
+    return dict(x=x, lam=lam, iter=np.array([i.iter for i in info]), qp_solver_iter=np.array([i.qp_solver_iter for i in info]),
+                status=np.array([i.status for i in info]), threads=used)

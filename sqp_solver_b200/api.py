@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_set_precision", "sqpb200_dev_alloc", "sqpb200_dev_free", "sqpb200_dev_copy",
     "sqpb200_ipc_export", "sqpb200_ipc_import", "sqpb200_ipc_release", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
-    "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to",
+    "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to", "sqpb200_host_alloc", "sqpb200_host_free",
 ]
 
 
@@ -96,6 +96,8 @@ def load_library(path=None):
     L.sqpb200_qp_batch_set_precision.argtypes = [vp, C.c_int]
     L.sqpb200_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
     L.sqpb200_dev_free.argtypes = [vp, vp]
+    L.sqpb200_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.sqpb200_host_free.argtypes = [vp, vp]
     L.sqpb200_dev_copy.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.sqpb200_ipc_export.argtypes = [vp, vp, C.c_char_p]
     L.sqpb200_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p)]

@@ -11,6 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsqp_b200.so")
+TOOL = os.path.join(HERE, "build", "batch_sqp_bench")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-ccbin", "/usr/bin/g++"]
@@ -28,7 +29,10 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    if not os.path.exists(TOOL):
+        return True
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h")) + \
+        glob.glob(os.path.join(HERE, "host", "*", "*.*pp")) + glob.glob(os.path.join(HERE, "host", "*", "*", "*.*pp"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -51,7 +55,17 @@ def build(force=False, verbose=False, extra=()):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++", "-Wno-deprecated-gpu-targets"]
     subprocess.check_call(cmd)
+    build_tools()
     return LIB
+
+
+def build_tools():
+    """Host-side tools on top of the library: the batched-SQP benchmark driver (BASELINE config 4; bench.py runs it)."""
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-O2", "-Wall", "-fopenmp", os.path.join(HERE, "host", "tools", "batch_sqp_bench.cpp"),
+                           "-o", TOOL, "-L" + HERE, "-lsqp_b200", "-Wl,-rpath,$ORIGIN/..", "-L/usr/local/cuda/lib64",
+                           "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return TOOL
 
 
 if __name__ == "__main__":

@@ -226,6 +226,20 @@ int sqpb200_dev_copy(sqpb200_ctx *c, void *dst, const void *src, size_t bytes, v
     if (bytes) CK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return SQPB200_OK;
 }
+int sqpb200_host_alloc(sqpb200_ctx *c, size_t bytes, void **host_ptr) {
+    if (!c || !host_ptr) return SQPB200_ERR_INVALID;
+    *host_ptr = nullptr;
+    CK(c, cudaSetDevice(c->device));
+    cudaError_t e = cudaMallocHost(host_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "sqpb200_host_alloc", e);
+    return SQPB200_OK;
+}
+int sqpb200_host_free(sqpb200_ctx *c, void *host_ptr) {
+    if (!c) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (host_ptr) CK(c, cudaFreeHost(host_ptr));
+    return SQPB200_OK;
+}
 int sqpb200_ipc_export(sqpb200_ctx *c, const void *dev_ptr, unsigned char handle[SQPB200_IPC_HANDLE_BYTES]) {
     if (!c || !dev_ptr || !handle) return SQPB200_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == SQPB200_IPC_HANDLE_BYTES, "CUDA IPC handle size");
@@ -562,7 +576,11 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
     // draws a QP beyond that count waits (draw_qp). H2D and compute overlap with no per-chunk launch tails.
     int rc = ensure_staging(b);
     if (rc) return rc;
+    // chunking hides the transfer behind the solve; below ~4 MB per chunk the copy calls cost more than they hide (an SQP outer
+    // iteration hands over a few hundred KB): fewer, larger chunks then
+    const size_t total_bytes = (size_t)count * (n * n + n + m * n + 2 * m) * sizeof(double);
     int chunks = c->opt_chunks;
+    if ((size_t)chunks > total_bytes / (4u << 20) + 1) chunks = (int)(total_bytes / (4u << 20) + 1);
     if (chunks > count) chunks = count;
     CK(c, cudaMemsetAsync(c->ready_dev, 0, sizeof(int), stream));
     // the compute stream may still be reading the staging buffers from an earlier call; the flag reset must precede the copies

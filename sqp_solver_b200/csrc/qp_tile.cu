@@ -67,18 +67,21 @@ struct TileCfg {
     static_assert(NP * HS <= NP * LS, "P must fit in the A staging region it aliases");
     static constexpr int OFF_STAGE = 0;
     static constexpr int OFF_P = OFF_STAGE;
+    // Regions that are only live during a (re)factorisation share storage with regions that are only live during iterations:
+    // the pivot columns with the per-warp partial sums, the rho vector (SYRK) with w
+    static constexpr int PIVS = 2 * NP;  // two pivot columns per elimination step
     static constexpr int OFF_PART = OFF_STAGE + NP * LS;
-    static constexpr int OFF_X = OFF_PART + NW * NP;
+    static constexpr int OFF_PIV = OFF_PART;
+    static constexpr int PART_DOUBLES = (NW * NP > 2 * PIVS) ? NW * NP : 2 * PIVS;
+    static constexpr int OFF_X = OFF_PART + PART_DOUBLES;
     static constexpr int OFF_XT = OFF_X + NP;
     static constexpr int OFF_B = OFF_XT + NP;
     static constexpr int OFF_Q = OFF_B + NP;
     static constexpr int OFF_PX = OFF_Q + NP;
     static constexpr int OFF_W = OFF_PX + NP;
-    static constexpr int OFF_RHO = OFF_W + MP;
-    static constexpr int OFF_PIV = OFF_RHO + MP;
-    static constexpr int PIVS = 2 * NP;  // two pivot columns per elimination step
+    static constexpr int OFF_RHO = OFF_W;
     static_assert(CG % 2 == 0, "the rank-2 elimination pairs adjacent pivot columns");
-    static constexpr int OFF_BND = OFF_PIV + 2 * PIVS;  // (l, u) pairs per row: read once per iteration by the row owner
+    static constexpr int OFF_BND = OFF_W + MP;  // (l, u) pairs per row: read once per iteration by the row owner
     static constexpr int OFF_RED = OFF_BND + 2 * MP;
     static constexpr int SMEM_DOUBLES = OFF_RED + 8 * NW;
     static constexpr size_t SMEM_BYTES = sizeof(S) * SMEM_DOUBLES;

@@ -379,9 +379,10 @@ class BatchSQP {
         for (auto *p : probs_)
             if (p->num_var != nx_ || p->num_constr != nc_) throw std::invalid_argument("BatchSQP: problems differ in size");
         detail::install_qp_settings(qp_.settings());
-        const size_t B = probs_.size();
-        P_.resize(B * nx_ * nx_); q_.resize(B * nx_); A_.resize(B * nc_ * nx_); l_.resize(B * nc_); u_.resize(B * nc_);
-        slot_.resize(B);
+        qp_.fetch_full_info(false);  // the outer loop reads x, y, status and iter only (sqp.cpp:224-239)
+        // the packed QP arrays ARE the solver's page-locked staging buffers: one asynchronous copy per array per outer iteration
+        P_ = qp_.staged_P(); q_ = qp_.staged_q(); A_ = qp_.staged_A(); l_ = qp_.staged_l(); u_ = qp_.staged_u();
+        slot_.resize(probs_.size());
     }
 
     Settings &settings() { return settings_; }
@@ -464,7 +465,7 @@ class BatchSQP {
         }
     }
     void solve_packed(int na, unsigned opts) {  // run_solve_qp for every active instance (src/sqp.cpp:210-242)
-        qp_.setup_solve(P_.data(), q_.data(), A_.data(), l_.data(), u_.data(), na, opts);
+        qp_.setup_solve_staged(na, opts);
         ++launches_;
         for (int k = 0; k < na; ++k) {
             auto &I = inst_[slot_[k]];
@@ -485,7 +486,7 @@ class BatchSQP {
     qp_solver::BatchQPSolver qp_;
     std::vector<detail::Instance<double>> inst_;
     Settings settings_;
-    std::vector<double> P_, q_, A_, l_, u_;
+    double *P_ = nullptr, *q_ = nullptr, *A_ = nullptr, *l_ = nullptr, *u_ = nullptr;  // owned by qp_
     std::vector<int> slot_;
     int launches_ = 0;
 };

@@ -131,16 +131,26 @@ class BatchQPSolver {
     using Settings = QPSolverSettings<double>;
     BatchQPSolver(int batch, int n, int m, int device = 0) : dev_(Device::get(device)), batch_(batch), n_(n), m_(m) {
         dev_->check(sqpb200_qp_batch_create(dev_->ctx(), batch, n, m, &h_), "sqpb200_qp_batch_create");
-        x_.resize((size_t)batch * n);
-        y_.resize((size_t)batch * m);
-        status_.assign(batch, UNINITIALIZED);
-        iter_.assign(batch, 0);
-        rho_updates_.assign(batch, 0);
-        rho_estimate_.assign(batch, 0.0);
-        res_prim_.assign(batch, 0.0);
-        res_dual_.assign(batch, 0.0);
+        // results land in page-locked host memory (asynchronous device-to-host copies, no driver-side staging)
+        const size_t B = (size_t)batch;
+        x_ = pinned<double>(B * n);
+        y_ = pinned<double>(B * (m > 0 ? m : 1));
+        rho_estimate_ = pinned<double>(B);
+        res_prim_ = pinned<double>(B);
+        res_dual_ = pinned<double>(B);
+        status_ = pinned<int>(B);
+        iter_ = pinned<int>(B);
+        rho_updates_ = pinned<int>(B);
+        for (size_t i = 0; i < B; ++i) {
+            status_[i] = UNINITIALIZED;
+            iter_[i] = rho_updates_[i] = 0;
+            rho_estimate_[i] = res_prim_[i] = res_dual_[i] = 0.0;
+        }
     }
-    ~BatchQPSolver() { sqpb200_qp_batch_destroy(h_); }
+    ~BatchQPSolver() {
+        sqpb200_qp_batch_destroy(h_);
+        for (void *p : pinned_) sqpb200_host_free(dev_->ctx(), p);
+    }
     BatchQPSolver(const BatchQPSolver &) = delete;
     BatchQPSolver &operator=(const BatchQPSolver &) = delete;
 
@@ -152,6 +162,8 @@ class BatchQPSolver {
     int num_constr() const { return m_; }
     Settings &settings() { return settings_; }
     const Settings &settings() const { return settings_; }
+    // read back rho_updates / rho_estimate / res_prim / res_dual after every call (default) or only x, y, status, iter
+    void fetch_full_info(bool on) { full_info_ = on; }
 
     // QPSolver::setup / update_qp / solve over the first `count` instances (host pointers)
     void setup(const double *P, const double *q, const double *A, const double *l, const double *u, int count = -1) {
@@ -174,6 +186,17 @@ class BatchQPSolver {
         call(fn, "setup_solve", P, q, A, l, u, count);
     }
 
+    // Page-locked input buffers owned by this object, sized for the whole batch: callers that re-solve every few hundred
+    // microseconds (the SQP outer loop) pack the problem data straight into them and call setup_solve_staged().
+    double *staged_P() { return staged(0, (size_t)n_ * n_); }
+    double *staged_q() { return staged(1, (size_t)n_); }
+    double *staged_A() { return staged(2, (size_t)(m_ > 0 ? m_ : 1) * n_); }
+    double *staged_l() { return staged(3, (size_t)(m_ > 0 ? m_ : 1)); }
+    double *staged_u() { return staged(4, (size_t)(m_ > 0 ? m_ : 1)); }
+    void setup_solve_staged(int count = -1, unsigned opts = 0) {
+        setup_solve(staged_P(), staged_q(), staged_A(), staged_l(), staged_u(), count, opts);
+    }
+
     // The reference's intended sparse variant (Eigen::SparseMatrix A: include/solvers/qp.hpp:22-25,
     // include/unsupported/qp_solver.hpp:363-394; tests/qp_solver_sparse_test.cpp): A in compressed column storage
     // (layout SQPB200_SPARSE_CSC, Eigen's outerIndexPtr / innerIndexPtr / valuePtr) or compressed row storage, ONE pattern for
@@ -185,13 +208,11 @@ class BatchQPSolver {
         dev_->check(sqpb200_qp_batch_setup_solve_sparse(h_, &s, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u,
                                                         SQPB200_HOST_PTRS, nullptr),
                     "setup_solve_sparse");
-        dev_->check(sqpb200_qp_batch_get(h_, count, x_.data(), y_.data(), nullptr, status_.data(), iter_.data(), rho_updates_.data(),
-                                         rho_estimate_.data(), res_prim_.data(), res_dual_.data(), SQPB200_HOST_PTRS, nullptr),
-                    "get");
+        fetch(count);
     }
 
-    const double *primal_solution(int i = 0) const { return x_.data() + (size_t)i * n_; }
-    const double *dual_solution(int i = 0) const { return y_.data() + (size_t)i * m_; }
+    const double *primal_solution(int i = 0) const { return x_ + (size_t)i * n_; }
+    const double *dual_solution(int i = 0) const { return y_ + (size_t)i * m_; }
     QPSolverInfo<double> info(int i) const {
         QPSolverInfo<double> r;
         r.status = (QPSolverStatus)status_[i];
@@ -209,21 +230,39 @@ class BatchQPSolver {
     }
 
    private:
+    template <typename T>
+    T *pinned(size_t count) {
+        void *p = nullptr;
+        dev_->check(sqpb200_host_alloc(dev_->ctx(), sizeof(T) * (count ? count : 1), &p), "sqpb200_host_alloc");
+        pinned_.push_back(p);
+        return static_cast<T *>(p);
+    }
+    double *staged(int k, size_t per_instance) {
+        if (!in_[k]) in_[k] = pinned<double>((size_t)batch_ * per_instance);
+        return in_[k];
+    }
+    void fetch(int count) {
+        dev_->check(sqpb200_qp_batch_get(h_, count, x_, y_, nullptr, status_, iter_, full_info_ ? rho_updates_ : nullptr,
+                                         full_info_ ? rho_estimate_ : nullptr, full_info_ ? res_prim_ : nullptr,
+                                         full_info_ ? res_dual_ : nullptr, SQPB200_HOST_PTRS, nullptr),
+                    "get");
+    }
     template <typename F>
     void call(F fn, const char *what, const double *P, const double *q, const double *A, const double *l, const double *u, int count) {
         if (count < 0) count = batch_;
         sqpb200_qp_settings s = settings_.to_c();
         dev_->check(fn(h_, &s, count, P, q, A, l, u, SQPB200_HOST_PTRS, nullptr), what);
-        dev_->check(sqpb200_qp_batch_get(h_, count, x_.data(), y_.data(), nullptr, status_.data(), iter_.data(), rho_updates_.data(),
-                                         rho_estimate_.data(), res_prim_.data(), res_dual_.data(), SQPB200_HOST_PTRS, nullptr),
-                    "get");
+        fetch(count);
     }
     std::shared_ptr<Device> dev_;
     sqpb200_qp_batch *h_ = nullptr;
     int batch_, n_, m_;
     Settings settings_;
-    std::vector<double> x_, y_, rho_estimate_, res_prim_, res_dual_;
-    std::vector<int> status_, iter_, rho_updates_;
+    bool full_info_ = true;
+    double *x_ = nullptr, *y_ = nullptr, *rho_estimate_ = nullptr, *res_prim_ = nullptr, *res_dual_ = nullptr;
+    int *status_ = nullptr, *iter_ = nullptr, *rho_updates_ = nullptr;
+    double *in_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<void *> pinned_;
 };
 
 /**
