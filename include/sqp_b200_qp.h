@@ -207,6 +207,20 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
                                         const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
                                         int layout, const double *l, const double *u, unsigned flags, void *stream);
 
+/* The object API with a sparse A (same arguments): setup / update_qp / solve as separate calls on persistent solver state, the
+ * call sequence of the reference's sparse tests (tests/qp_solver_sparse_test.cpp:68-98: setup, solve, solve; setup, solve, update_qp,
+ * solve). With the cluster kernel the distributed factor is not kept between launches: solve() rebuilds it from the stored constraint
+ * classes and rho (results identical to a kept factor). */
+int sqpb200_qp_batch_setup_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                                  const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz, int layout,
+                                  const double *l, const double *u, unsigned flags, void *stream);
+int sqpb200_qp_batch_update_qp_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                                      const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
+                                      int layout, const double *l, const double *u, unsigned flags, void *stream);
+int sqpb200_qp_batch_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *settings, int count, const double *P,
+                                  const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz, int layout,
+                                  const double *l, const double *u, unsigned flags, void *stream);
+
 /* Read back solutions and info (any pointer may be NULL). primal_solution()/dual_solution()/info(),
  * qp.hpp:159-169; z is exposed in addition so a caller can checkpoint a warm start. */
 int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,

@@ -35,7 +35,8 @@ ABI_SYMBOLS = [
     "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_set_precision", "sqpb200_dev_alloc", "sqpb200_dev_free", "sqpb200_dev_copy",
     "sqpb200_ipc_export", "sqpb200_ipc_import", "sqpb200_ipc_release", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
-    "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to", "sqpb200_host_alloc", "sqpb200_host_free",
+    "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to", "sqpb200_host_alloc", "sqpb200_host_free", "sqpb200_qp_batch_setup_sparse",
+    "sqpb200_qp_batch_update_qp_sparse", "sqpb200_qp_batch_solve_sparse",
 ]
 
 
@@ -90,8 +91,9 @@ def load_library(path=None):
     for name in ("setup", "update_qp", "solve", "setup_solve"):
         getattr(L, "sqpb200_qp_batch_" + name).argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp]
     L.sqpb200_qp_batch_setup_solve_opts.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, C.c_uint, vp, C.c_uint]
-    L.sqpb200_qp_batch_setup_solve_sparse.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, ip, ip, C.c_int, C.c_int, dp, dp,
-                                                      C.c_uint, vp]
+    for name in ("setup_solve_sparse", "setup_sparse", "update_qp_sparse", "solve_sparse"):
+        getattr(L, "sqpb200_qp_batch_" + name).argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, ip, ip, C.c_int, C.c_int, dp, dp,
+                                                           C.c_uint, vp]
     L.sqpb200_qp_batch_setup_solve_to.argtypes = [vp, C.POINTER(Settings), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip, ip, dp, dp, dp, vp]
     L.sqpb200_qp_batch_set_precision.argtypes = [vp, C.c_int]
     L.sqpb200_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -342,9 +344,19 @@ class QPBatch:
         self.ctx._check(self._L.sqpb200_qp_batch_setup_solve_to(self._h, C.byref(self.settings), count, *ins, *outs, C.c_void_p(stream or 0)),
                         "setup_solve_to")
 
-    def setup_solve_sparse(self, P, q, A_values, A_outer, A_inner, l, u, layout=SPARSE_CSC, count=None, stream=None):
+    def setup_sparse(self, P, q, A_values, A_outer, A_inner, l, u, layout=SPARSE_CSC, count=None, stream=None):
+        self.setup_solve_sparse(P, q, A_values, A_outer, A_inner, l, u, layout, count, stream, _fn="setup_sparse")
+
+    def update_qp_sparse(self, P, q, A_values, A_outer, A_inner, l, u, layout=SPARSE_CSC, count=None, stream=None):
+        self.setup_solve_sparse(P, q, A_values, A_outer, A_inner, l, u, layout, count, stream, _fn="update_qp_sparse")
+
+    def solve_sparse(self, P, q, A_values, A_outer, A_inner, l, u, layout=SPARSE_CSC, count=None, stream=None):
+        self.setup_solve_sparse(P, q, A_values, A_outer, A_inner, l, u, layout, count, stream, _fn="solve_sparse")
+
+    def setup_solve_sparse(self, P, q, A_values, A_outer, A_inner, l, u, layout=SPARSE_CSC, count=None, stream=None, _fn="setup_solve_sparse"):
         """setup + solve with A given as CSC (Eigen::SparseMatrix layout) or CSR: one pattern for the whole batch
-        (A_outer, A_inner: int32), per-instance values A_values[B, nnz]."""
+        (A_outer, A_inner: int32), per-instance values A_values[B, nnz]. setup_sparse / update_qp_sparse / solve_sparse are the
+        separate calls of the object API with the same arguments."""
         count = self.batch if count is None else int(count)
         ptrs, spaces = [], set()
         for nm, a, dt in (("P", P, np.float64), ("q", q, np.float64), ("A_values", A_values, np.float64), ("A_outer", A_outer, np.int32),
@@ -362,9 +374,8 @@ class QPBatch:
 
             stream = torch.cuda.current_stream().cuda_stream
         P_, q_, Av, Ao, Ai, l_, u_ = ptrs
-        self.ctx._check(self._L.sqpb200_qp_batch_setup_solve_sparse(self._h, C.byref(self.settings), count, P_, q_, Av, Ao, Ai, nnz,
-                                                                    int(layout), l_, u_, flags, C.c_void_p(stream or 0)),
-                        "setup_solve_sparse")
+        self.ctx._check(getattr(self._L, "sqpb200_qp_batch_" + _fn)(self._h, C.byref(self.settings), count, P_, q_, Av, Ao, Ai, nnz,
+                                                                    int(layout), l_, u_, flags, C.c_void_p(stream or 0)), _fn)
 
     def get(self, count=None, fields=("x", "y", "z", "status", "iter", "rho_updates", "rho_estimate", "res_prim", "res_dual")):
         """Copy results to fresh host arrays (synchronises; ordered behind the last launch on this object whatever stream that used)."""

@@ -459,7 +459,7 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     int kind = KERNEL_NONE, clusters = 0;
     if (sp) {
         // a cluster of 4 CTAs per QP with H^-1 distributed over their shared memory when the instance fits, else the blocked kernel
-        if ((opt == 0 || opt == 4) && sp->cluster_size > 0 && mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE))
+        if ((opt == 0 || opt == 4) && sp->cluster_size > 0)
             clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap, sp->cluster_size);
         // Eight CTAs per QP buy latency, not throughput (measured at n = 256, nnz = 8.9 k: 0.84 ms per QP on 8 SMs against 7.7 ms on one SM
         // with the blocked kernel, i.e. the same QPs per SM-second): keep them for batches that cannot fill the SMs one QP each
@@ -468,6 +468,14 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
             clusters = 0;
         if (opt == 4 && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel forced but the problem is outside its range");
         kind = clusters >= 1 ? KERNEL_CLUSTER : KERNEL_BLOCK;
+        // solve() after setup()/update_qp(): the blocked kernel's factor lives in the slab, the cluster kernel rebuilds its own --
+        // keep the kernel that ran the setup
+        if ((mode & MODE_LOAD_FACTOR) && b->fact_valid) {
+            if (b->fact_kernel == KERNEL_BLOCK) kind = KERNEL_BLOCK, clusters = 0;
+            else if (b->fact_kernel == KERNEL_CLUSTER && clusters < 1)
+                clusters = cluster_max_clusters(b->n, b->m, sp->nnz, sp->col_slice_cap, sp->cluster_size), kind = KERNEL_CLUSTER;
+        }
+        if (kind == KERNEL_CLUSTER && clusters < 1) return fail(c, SQPB200_ERR_UNSUPPORTED, "cluster kernel required by the stored state but unavailable");
     } else if (opt == 1) {
         kind = KERNEL_GENERIC;
     } else if (opt == 2) {
@@ -681,9 +689,12 @@ int sqpb200_qp_batch_setup_solve_opts(sqpb200_qp_batch *b, const sqpb200_qp_sett
     return run(b, s, mode, count, P, q, A, l, u, flags, stream);
 }
 
-int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P,
-                                        const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
-                                        int layout, const double *l, const double *u, unsigned flags, void *stream_) {
+}  // extern "C"
+
+// One call of the sparse-A entry points: `mode` as in the dense ones (setup = RESET|FACTOR|STORE_FACTOR, ...)
+static int run_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, unsigned mode, int count, const double *P,
+                      const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
+                      int layout, const double *l, const double *u, unsigned flags, void *stream_) {
     if (!b) return SQPB200_ERR_INVALID;
     sqpb200_ctx *c = b->ctx;
     if (!s) return fail(c, SQPB200_ERR_INVALID, "settings is NULL");
@@ -752,9 +763,6 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
         dP = b->dP; dq = b->dq; dl = b->dl; du = b->du;
     }
     CK(c, cudaMemsetAsync(b->total_iters, 0, sizeof(unsigned long long), stream));
-    b->fact_valid = false;
-    b->fused_used = true;
-    const unsigned mode = MODE_RESET | MODE_FACTOR | MODE_SOLVE;
 
     // Shapes the register-tiled kernel covers keep A in registers anyway: densify. Larger ones run the blocked kernel with the
     // values of one instance staged in shared memory and both compressed views of the pattern.
@@ -861,6 +869,40 @@ int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_se
     if (rc) return rc;
     if (!dev) CK(c, cudaStreamSynchronize(stream));
     return SQPB200_OK;
+}
+
+extern "C" {
+
+int sqpb200_qp_batch_setup_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P,
+                                        const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
+                                        int layout, const double *l, const double *u, unsigned flags, void *stream) {
+    if (b) {
+        b->fact_valid = false;
+        b->fused_used = true;
+    }
+    return run_sparse(b, s, MODE_RESET | MODE_FACTOR | MODE_SOLVE, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u, flags, stream);
+}
+int sqpb200_qp_batch_setup_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P, const double *q,
+                                  const double *A_values, const int *A_outer, const int *A_inner, int nnz, int layout, const double *l,
+                                  const double *u, unsigned flags, void *stream) {
+    int rc = run_sparse(b, s, MODE_RESET | MODE_FACTOR | MODE_STORE_FACTOR, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u, flags, stream);
+    if (!rc && b) b->fact_valid = true;
+    return rc;
+}
+int sqpb200_qp_batch_update_qp_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P, const double *q,
+                                      const double *A_values, const int *A_outer, const int *A_inner, int nnz, int layout,
+                                      const double *l, const double *u, unsigned flags, void *stream) {
+    int rc = run_sparse(b, s, MODE_FACTOR | MODE_STORE_FACTOR, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u, flags, stream);
+    if (!rc && b) b->fact_valid = true;
+    return rc;
+}
+int sqpb200_qp_batch_solve_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P, const double *q,
+                                  const double *A_values, const int *A_outer, const int *A_inner, int nnz, int layout, const double *l,
+                                  const double *u, unsigned flags, void *stream) {
+    if (b && !b->fact_valid && b->fused_used)
+        return fail(b->ctx, SQPB200_ERR_INVALID,
+                    "sqpb200_qp_batch_solve_sparse: the last setup was the fused setup_solve, which does not keep the factor; call setup first");
+    return run_sparse(b, s, MODE_LOAD_FACTOR | MODE_SOLVE | MODE_STORE_FACTOR, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u, flags, stream);
 }
 
 int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, double *z, int *status, int *iter,

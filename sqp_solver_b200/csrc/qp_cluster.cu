@@ -197,11 +197,19 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         const double *P = p.P + b * n * n, *q = p.q + b * n, *l = p.l + b * m, *u = p.u + b * m;
         const double *gvals = sp.vals + b * (size_t)nnz;
 
-        int status = SQPB200_UNSOLVED;
-        int rho_updates = p.rho_updates[b] + 1;  // rho_vec_update, qp.cpp:313
+        // Launch modes (qp_common.cuh): setup = RESET|FACTOR, update_qp = FACTOR, solve = LOAD_FACTOR|SOLVE, fused = RESET|FACTOR|SOLVE.
+        // The distributed H^-1 never leaves the cluster's shared memory: a solve() after a separate setup()/update_qp() launch
+        // rebuilds it from the stored constraint classes and rho (deterministic: the same factor setup computed), at the cost of
+        // ~40 iterations' worth of work per instance.
+        const bool m_reset = (p.mode & MODE_RESET) != 0, m_factor = (p.mode & MODE_FACTOR) != 0, m_solve = (p.mode & MODE_SOLVE) != 0;
+        int status = p.status[b];
+        int rho_updates = p.rho_updates[b] + (m_factor ? 1 : 0);  // rho_vec_update, qp.cpp:313
         double rho_est = p.rho_estimate[b], res_prim = p.res_prim[b], res_dual = p.res_dual[b];
-        double rho = st.rho;
+        double rho = m_factor ? st.rho : p.rho[b];
         int iter_out = p.iter[b];
+        const signed char *ctype = p.ctype + b * m;
+        // constraint class of row i: classified from the bounds by setup/update_qp (qp.cpp:31, :48), read back by solve
+        auto row_type = [&](int i) -> int { return m_factor ? classify(__ldg(l + i), __ldg(u + i)) : (int)ctype[i]; };
 
         // values of this instance + the batch-shared pattern -> shared memory (the region is reused by the sweep: restaged after it)
         auto stage_sparse = [&]() {
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         };
         for (int j = tid; j < np; j += CT) {
             s.sq[j] = j < n ? __ldg(q + j) : 0.0;
-            s.sx[j] = 0.0;
+            s.sx[j] = (j < n && !m_reset) ? p.x[b * n + j] : 0.0;
             s.sxt[j] = 0.0;
         }
         // per-row state of the owned constraint rows lives in registers (qp.cpp:16-18, 31-32)
@@ -239,8 +247,11 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         if (has_row) {
             lo = l[my_row];
             up = u[my_row];
-            typ = classify(lo, up);
-            if (row_half == 0) p.ctype[b * m + my_row] = (signed char)typ;
+            typ = row_type(my_row);
+            if (!m_reset) {
+                zr = p.z[b * m + my_row];
+                yr = p.y[b * m + my_row];
+            }
             rhor = rho_of(typ, rho);
             rinv = 1.0 / rhor;
         }
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             tlast = clock64();
 #endif
             // rho of every row (form H touches all rows of a column): recomputed from the bounds, as classified at setup
-            for (int i = tid; i < m; i += CT) s.sw[i] = rho_of(classify(__ldg(l + i), __ldg(u + i)), rho);
+            for (int i = tid; i < m; i += CT) s.sw[i] = rho_of(row_type(i), rho);
             // P_lowsym + sigma I (LDLT<Lower> reads the lower triangle only); padded variables get a unit diagonal
             // (two passes so that both triangles are read along P's columns: lanes over rows for j <= i, lanes over columns above)
 #pragma unroll 8
@@ -583,15 +594,19 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             for (int o = 1; o < TPC; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             return acc;
         };
-        bool ok = factorize();
-        load_slice();
+        // setup / update_qp factor (qp.cpp:34-43, :51-61); a separate solve() rebuilds the factor unless it is a no-op (qp.cpp:68-71)
+        bool ok = true;
+        if (m_factor || (m_solve && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES)) {
+            ok = factorize();
+            load_slice();
+        }
 #ifdef SQPB200_CLUSTER_TIMING
         long long tq1 = clock64();
 #endif
-        status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
+        if (m_factor) status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
 
         long long executed = 0;
-        if ((p.mode & MODE_SOLVE) && ok) {
+        if (m_solve && ok && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES) {
             int iter;
             for (iter = 1; iter <= st.max_iter; ++iter) {
 #ifdef SQPB200_CLUSTER_TIMING
@@ -759,6 +774,8 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         if (row_writer) {
             p.z[b * m + my_row] = zr;
             p.y[b * m + my_row] = yr;
+            // the classes are written LAST: every CTA of the cluster read the old ones (row_type in a solve launch) before this point
+            if (m_factor) p.ctype[b * m + my_row] = (signed char)typ;
         }
         if (rank == 0 && tid == 0) {
             p.status[b] = status;

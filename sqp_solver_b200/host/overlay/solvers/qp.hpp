@@ -203,12 +203,20 @@ class BatchQPSolver {
     // the batch, values[batch][nnz]. setup + solve in one launch.
     void setup_solve_sparse(const double *P, const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
                             int layout, const double *l, const double *u, int count = -1) {
-        if (count < 0) count = batch_;
-        sqpb200_qp_settings s = settings_.to_c();
-        dev_->check(sqpb200_qp_batch_setup_solve_sparse(h_, &s, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u,
-                                                        SQPB200_HOST_PTRS, nullptr),
-                    "setup_solve_sparse");
-        fetch(count);
+        call_sparse(sqpb200_qp_batch_setup_solve_sparse, "setup_solve_sparse", P, q, A_values, A_outer, A_inner, nnz, layout, l, u, count);
+    }
+    // the separate calls of the object API with a sparse A (tests/qp_solver_sparse_test.cpp:68-98: setup, solve, solve, update_qp, solve)
+    void setup_sparse(const double *P, const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz, int layout,
+                      const double *l, const double *u, int count = -1) {
+        call_sparse(sqpb200_qp_batch_setup_sparse, "setup_sparse", P, q, A_values, A_outer, A_inner, nnz, layout, l, u, count);
+    }
+    void update_qp_sparse(const double *P, const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz,
+                          int layout, const double *l, const double *u, int count = -1) {
+        call_sparse(sqpb200_qp_batch_update_qp_sparse, "update_qp_sparse", P, q, A_values, A_outer, A_inner, nnz, layout, l, u, count);
+    }
+    void solve_sparse(const double *P, const double *q, const double *A_values, const int *A_outer, const int *A_inner, int nnz, int layout,
+                      const double *l, const double *u, int count = -1) {
+        call_sparse(sqpb200_qp_batch_solve_sparse, "solve_sparse", P, q, A_values, A_outer, A_inner, nnz, layout, l, u, count);
     }
 
     const double *primal_solution(int i = 0) const { return x_ + (size_t)i * n_; }
@@ -246,6 +254,14 @@ class BatchQPSolver {
                                          full_info_ ? rho_estimate_ : nullptr, full_info_ ? res_prim_ : nullptr,
                                          full_info_ ? res_dual_ : nullptr, SQPB200_HOST_PTRS, nullptr),
                     "get");
+    }
+    template <typename F>
+    void call_sparse(F fn, const char *what, const double *P, const double *q, const double *A_values, const int *A_outer, const int *A_inner,
+                     int nnz, int layout, const double *l, const double *u, int count) {
+        if (count < 0) count = batch_;
+        sqpb200_qp_settings s = settings_.to_c();
+        dev_->check(fn(h_, &s, count, P, q, A_values, A_outer, A_inner, nnz, layout, l, u, SQPB200_HOST_PTRS, nullptr), what);
+        fetch(count);
     }
     template <typename F>
     void call(F fn, const char *what, const double *P, const double *q, const double *A, const double *l, const double *u, int count) {
