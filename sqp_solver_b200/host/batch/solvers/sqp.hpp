@@ -132,6 +132,8 @@ struct Instance {
     Scalar dual_step_norm_ = 0, primal_step_norm_ = 0;
     Info info_;
     bool active = true;
+    bool verbose = true;      // print "Hessian not positive definite" like the reference (sqp.cpp:172); BatchSQP counts instead
+    int hessian_repairs = 0;  // how many times the PD repair of sqp.cpp:171-180 ran
     int last_qp_iter = 0;  // info().iter of this instance's own QPSolver: a setup that fails leaves it stale (qp.cpp:68-71, sqp.cpp:224)
 
     void init(Problem &prob) {  // src/sqp.cpp:48-66
@@ -174,7 +176,8 @@ struct Instance {
             BFGS_update(Hess_, step_prev_, delta_grad_L_);
         }
         if (!is_posdef(Hess_)) {
-            std::cout << "Hessian not positive definite\n";
+            if (verbose) std::cout << "Hessian not positive definite\n";
+            ++hessian_repairs;
             Scalar tau = 1e-3;
             while (!is_posdef(Hess_)) {
                 for (int i = 0; i < nx; ++i) Hess_(i, i) += tau;
@@ -392,6 +395,11 @@ class BatchSQP {
     const Vector &dual_solution(size_t i) const { return inst_[i].lambda_; }
     const Info &info(size_t i) const { return inst_[i].info_; }
     int qp_launches() const { return launches_; }
+    long long hessian_repairs() const {
+        long long t = 0;
+        for (const auto &I : inst_) t += I.hessian_repairs;
+        return t;
+    }
 
     void solve(const std::vector<Vector> &x0, const std::vector<Vector> &lambda0) {
         const size_t B = probs_.size();
@@ -399,6 +407,8 @@ class BatchSQP {
             inst_[i].x_ = x0[i];
             inst_[i].lambda_ = lambda0[i];
             inst_[i].init(*probs_[i]);
+            inst_[i].verbose = false;  // thousands of instances: the repair message of sqp.cpp:172 is counted, not printed
+            inst_[i].hessian_repairs = 0;
         }
         launches_ = 0;
         for (int iter = 1; iter <= settings_.max_iter; ++iter) {

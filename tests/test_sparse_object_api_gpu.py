@@ -85,8 +85,9 @@ def test_sparse_object_api_against_the_oracle(api, ctx, oracle, n, m, batch, den
             dd["vals"] = np.ascontiguousarray(dd["vals"][:, order])
         outer = np.concatenate([[0], np.cumsum(np.bincount(d["cols"], minlength=n))]).astype(np.int32)
         inner = np.ascontiguousarray(d["rows"][order].astype(np.int32))
+        rows_c, cols_c = d["rows"][order], d["cols"][order]
         for dd in (d, d2):
-            dd["rows"], dd["cols"] = d["rows"][order], d["cols"][order]
+            dd["rows"], dd["cols"] = rows_c, cols_c
     else:
         outer, inner = d["outer"], d["inner"]
     lay = api.SPARSE_CSC if layout == "csc" else api.SPARSE_CSR
