@@ -21,14 +21,11 @@ struct sqpb200_ctx {
     cudaStream_t stream = nullptr;       // internal housekeeping stream (state initialisation)
     cudaStream_t copy_stream = nullptr;  // H2D staging for HOST_PTRS calls
     int *counters = nullptr;             // ring of work-queue counters, one per launch
-    int *ready_dev = nullptr;            // device flag: QPs staged so far (host-pointer calls)
-    int *ready_host = nullptr;           // pinned: chunk boundaries, source of the flag copies
     static constexpr int kCounters = 1024;
     long long launches = 0;
     int opt_kernel = 0, opt_chunks = 16, opt_ctas_per_sm = 0, opt_tile_warps = 0;
     std::string err;
     char last_kernel[64] = "none";
-    cudaEvent_t chunk_events[64]{};
 };
 
 struct sqpb200_qp_batch {
@@ -46,6 +43,10 @@ struct sqpb200_qp_batch {
     bool fact_valid = false;  // a setup()/update_qp()/solve() launch has stored H^-1, rho and classes
     int fact_kernel = 0;      // which kernel family wrote the stored factor (its layout differs per kernel): KERNEL_* below, 0 = none
     int keep_kernel = 0;      // which kernel family wrote the factor kept by SQPB200_KEEP_FACTOR
+    // HOST_PTRS staging protocol, per batch object (two objects of one context may stage concurrently): the device flag holding
+    // the number of QPs whose inputs have landed, the pinned chunk boundaries the flag copies read, and the ordering event
+    int *ready_dev = nullptr, *ready_host = nullptr;
+    cudaEvent_t stage_event = nullptr;
     cudaStream_t last_stream = nullptr;  // stream of the last launch on this object, and an event recorded behind it:
     cudaEvent_t last_event = nullptr;    // get / set_iterates / total_iters on ANOTHER stream wait for it first
     double *gen_scratch = nullptr;  // generic kernel: per-CTA n*n factorisation workspace (owned by the batch object: launches of
@@ -124,13 +125,11 @@ int sqpb200_ctx_create(int device, sqpb200_ctx **out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&c->counters, sizeof(int) * sqpb200_ctx::kCounters)) != cudaSuccess ||
-        (e = cudaMalloc(&c->ready_dev, sizeof(int))) != cudaSuccess || (e = cudaMallocHost(&c->ready_host, sizeof(int) * 64)) != cudaSuccess) {
+        (e = cudaMalloc(&c->counters, sizeof(int) * sqpb200_ctx::kCounters)) != cudaSuccess) {
         int rc = fail(nullptr, SQPB200_ERR_CUDA, "sqpb200_ctx_create", e);
         delete c;
         return rc;
     }
-    for (auto &ev : c->chunk_events) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (c->prop.major < 10) {
         delete c;
         return fail(nullptr, SQPB200_ERR_UNSUPPORTED, "sqpb200_ctx_create: kernels are built for sm_100a only");
@@ -143,11 +142,7 @@ int sqpb200_ctx_destroy(sqpb200_ctx *c) {
     if (!c) return SQPB200_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (auto &ev : c->chunk_events)
-        if (ev) cudaEventDestroy(ev);
     if (c->counters) cudaFree(c->counters);
-    if (c->ready_dev) cudaFree(c->ready_dev);
-    if (c->ready_host) cudaFreeHost(c->ready_host);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -287,6 +282,9 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (b->last_event) cudaEventDestroy(b->last_event);
+    if (b->stage_event) cudaEventDestroy(b->stage_event);
+    if (b->ready_dev) cudaFree(b->ready_dev);
+    if (b->ready_host) cudaFreeHost(b->ready_host);
     delete b;
     return SQPB200_OK;
 }
@@ -408,6 +406,12 @@ static int ensure_fact(sqpb200_qp_batch *b, size_t doubles_per_qp) {
 }
 
 static int ensure_staging(sqpb200_qp_batch *b) {
+    if (!b->ready_dev) {
+        cudaError_t e0 = cudaMalloc(&b->ready_dev, sizeof(int));
+        if (e0 == cudaSuccess) e0 = cudaMallocHost(&b->ready_host, sizeof(int) * 64);
+        if (e0 == cudaSuccess) e0 = cudaEventCreateWithFlags(&b->stage_event, cudaEventDisableTiming);
+        if (e0 != cudaSuccess) return fail(b->ctx, SQPB200_ERR_NOMEM, "staging flag allocation", e0);
+    }
     if (b->dP) return SQPB200_OK;
     size_t B = (size_t)b->batch, n = b->n, m = b->m > 0 ? b->m : 1;
     cudaError_t e = cudaMalloc(&b->dP, B * n * n * sizeof(double));
@@ -497,6 +501,8 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
         kind = KERNEL_SMALL;
     } else if (tile_supported(b->n, b->m)) {
         kind = KERNEL_TILE;
+    } else if (b->f32 && generic_supported(b->n, b->m, optin)) {
+        kind = KERNEL_GENERIC;  // QPSolver<float> beyond the tile kernel's shapes: the generic kernel's float instantiation
     } else if (block_supported(b->n, b->m, optin)) {
         kind = KERNEL_BLOCK;
     } else {
@@ -506,8 +512,10 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     // LDL^T panels for the blocked kernel, nothing for the thread-per-QP kernel): solve() after setup()/update_qp() keeps that
     // kernel even when the option or settings.verbose changed in between, and a REUSE of a factor another kernel kept is dropped.
     if ((mode & MODE_LOAD_FACTOR) && b->fact_valid && b->fact_kernel != KERNEL_NONE && !sp) {
-        const bool compatible = (kind == b->fact_kernel) || (kind == KERNEL_TILE && b->fact_kernel == KERNEL_GENERIC) ||
-                                (kind == KERNEL_GENERIC && b->fact_kernel == KERNEL_TILE);  // both store the dense n x n inverse
+        // the fp64 tile and generic kernels both store the dense n x n inverse (fp32: the tile kernel widens to double, the generic
+        // kernel packs floats)
+        const bool compatible = (kind == b->fact_kernel) || (!b->f32 && ((kind == KERNEL_TILE && b->fact_kernel == KERNEL_GENERIC) ||
+                                                                         (kind == KERNEL_GENERIC && b->fact_kernel == KERNEL_TILE)));
         if (!compatible) kind = b->fact_kernel;
     }
     if ((mode & MODE_REUSE) && b->keep_kernel != kind) mode &= ~MODE_REUSE;
@@ -555,8 +563,8 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
         int rc = ensure_scratch(b, generic_scratch_bytes(b->n, grid));
         if (rc) return rc;
         p.scratch = b->gen_scratch;
-        e = launch_generic(p, c->prop.multiProcessorCount, optin, stream, nullptr);
-        snprintf(c->last_kernel, sizeof c->last_kernel, "generic");
+        e = launch_generic(p, c->prop.multiProcessorCount, optin, b->f32, stream, nullptr);
+        snprintf(c->last_kernel, sizeof c->last_kernel, b->f32 ? "generic<f32>" : "generic");
     }
     if (e != cudaSuccess) return fail(c, SQPB200_ERR_CUDA, "kernel launch", e);
     c->launches += 1;
@@ -590,10 +598,10 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
     int chunks = c->opt_chunks;
     if ((size_t)chunks > total_bytes / (4u << 20) + 1) chunks = (int)(total_bytes / (4u << 20) + 1);
     if (chunks > count) chunks = count;
-    CK(c, cudaMemsetAsync(c->ready_dev, 0, sizeof(int), stream));
+    CK(c, cudaMemsetAsync(b->ready_dev, 0, sizeof(int), stream));
     // the compute stream may still be reading the staging buffers from an earlier call; the flag reset must precede the copies
-    CK(c, cudaEventRecord(c->chunk_events[63], stream));
-    CK(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_events[63], 0));
+    CK(c, cudaEventRecord(b->stage_event, stream));
+    CK(c, cudaStreamWaitEvent(c->copy_stream, b->stage_event, 0));
     for (int k = 0; k < chunks; ++k) {
         // early chunks are small so the first CTAs start after ~1 % of the transfer
         size_t lo = (size_t)count * k / chunks, hi = (size_t)count * (k + 1) / chunks, cnt = hi - lo;
@@ -604,10 +612,10 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
             CK(c, cudaMemcpyAsync(b->dl + lo * m, l + lo * m, cnt * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
             CK(c, cudaMemcpyAsync(b->du + lo * m, u + lo * m, cnt * m * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
         }
-        c->ready_host[k] = (int)hi;
-        CK(c, cudaMemcpyAsync(c->ready_dev, c->ready_host + k, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+        b->ready_host[k] = (int)hi;
+        CK(c, cudaMemcpyAsync(b->ready_dev, b->ready_host + k, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
     }
-    rc = launch_range(b, st, mode, 0, count, b->dP, b->dq, b->dA, b->dl, b->du, stream, c->ready_dev);
+    rc = launch_range(b, st, mode, 0, count, b->dP, b->dq, b->dA, b->dl, b->du, stream, b->ready_dev);
     if (rc) {
         cudaStreamSynchronize(c->copy_stream);
         return rc;
@@ -852,16 +860,16 @@ static int run_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, unsigne
             // (same protocol as the dense entry points: a 4-byte copy after each chunk publishes how many QPs have landed)
             int chunks = c->opt_chunks;
             if (chunks > count) chunks = count;
-            CK(c, cudaMemsetAsync(c->ready_dev, 0, sizeof(int), stream));
-            CK(c, cudaEventRecord(c->chunk_events[63], stream));
-            CK(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_events[63], 0));
+            CK(c, cudaMemsetAsync(b->ready_dev, 0, sizeof(int), stream));
+            CK(c, cudaEventRecord(b->stage_event, stream));
+            CK(c, cudaStreamWaitEvent(c->copy_stream, b->stage_event, 0));
             for (int k = 0; k < chunks; ++k) {
                 const size_t lo = (size_t)count * k / chunks, hi = (size_t)count * (k + 1) / chunks;
                 CK(c, copy_instances(c->copy_stream, lo, hi - lo));
-                c->ready_host[k] = (int)hi;
-                CK(c, cudaMemcpyAsync(c->ready_dev, c->ready_host + k, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+                b->ready_host[k] = (int)hi;
+                CK(c, cudaMemcpyAsync(b->ready_dev, b->ready_host + k, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
             }
-            ready = c->ready_dev;
+            ready = b->ready_dev;
         }
         rc = launch_range(b, s, mode, 0, count, dP, dq, nullptr, dl, du, stream, ready, &sp);
         if (rc && !dev) cudaStreamSynchronize(c->copy_stream);

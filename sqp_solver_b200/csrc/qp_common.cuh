@@ -108,7 +108,13 @@ __device__ __forceinline__ double absmax(double r, double v) {
 __device__ __forceinline__ int draw_qp(const KernelParams &p) {
     const int v = atomicAdd(p.work_counter, 1);
     if (p.ready != nullptr && v < p.count) {
-        while (*reinterpret_cast<const volatile int *>(p.ready) <= v) __nanosleep(500);
+        // bounded wait: if the staging copies never arrive (a failed copy on the host side) the launch aborts with an error after
+        // ~8 s instead of hanging the device
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile int *>(p.ready) <= v) {
+            __nanosleep(500);
+            if (clock64() - t0 > (1LL << 34)) __trap();
+        }
         __threadfence();
     }
     return v;
@@ -177,7 +183,7 @@ __device__ __forceinline__ S rho_estimate_clamped_t(S rho, S rp, S rd, S sc_p, S
 #endif  // __CUDACC__
 
 // launchers implemented in the kernel translation units
-cudaError_t launch_generic(const KernelParams &p, int sm_count, size_t smem_optin, cudaStream_t stream, int *grid_out);
+cudaError_t launch_generic(const KernelParams &p, int sm_count, size_t smem_optin, int f32, cudaStream_t stream, int *grid_out);
 size_t generic_scratch_bytes(int n, int grid);
 int generic_grid(int count, int sm_count);
 bool generic_supported(int n, int m, size_t smem_optin);

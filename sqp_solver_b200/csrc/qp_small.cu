@@ -49,7 +49,11 @@ __global__ void __launch_bounds__(ST) qp_small_kernel(KernelParams p) {
     const int local = blockIdx.x * ST + tid;
     if (local >= p.count) return;
     if (p.ready != nullptr) {  // host-staged call: wait until the chunk holding this QP has landed (draw_qp's protocol)
-        while (*reinterpret_cast<const volatile int *>(p.ready) <= local) __nanosleep(500);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile int *>(p.ready) <= local) {
+            __nanosleep(500);
+            if (clock64() - t0 > (1LL << 34)) __trap();  // the staging copies never arrived: fail instead of hanging
+        }
         __threadfence();
     }
     const int n = p.n, m = p.m, N = n + m;
@@ -320,7 +324,11 @@ __global__ void __launch_bounds__(ST) qp_small_reg_kernel(KernelParams p) {
     const int local = blockIdx.x * ST + tid;
     if (local >= p.count) return;
     if (p.ready != nullptr) {
-        while (*reinterpret_cast<const volatile int *>(p.ready) <= local) __nanosleep(500);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile int *>(p.ready) <= local) {
+            __nanosleep(500);
+            if (clock64() - t0 > (1LL << 34)) __trap();
+        }
         __threadfence();
     }
     constexpr int n = N_;
