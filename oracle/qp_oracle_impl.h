@@ -10,11 +10,14 @@
  * (CMakeLists.txt:12 "find_package(Eigen3 3.3 REQUIRED NO_MODULE)") and is absent from this
  * image, so the reference itself cannot be compiled here.
  *
- * PARITY PINNING: this oracle is checked against every known-answer assertion the
- * reference's tests hold for this path (tests/qp_solver_test.cpp:43-156, see
- * tests/test_oracle_reference_kats.py). Those pins are 1e-2-level solution checks, status
- * checks and one exact integer vector. Below that level (iteration counts, 1e-6 digits)
- * parity is UNPINNED against the real Eigen build: the restatement is the oracle.
+ * PARITY PINNING: (1) every known-answer assertion the reference's tests hold for this path
+ * (tests/qp_solver_test.cpp:43-156, see tests/test_oracle_reference_kats.py); (2) BIT IDENTITY with oracle/_ref --
+ * the reference's own src/qp.cpp compiled unmodified against oracle/eigen_lite (a stand-in for the absent Eigen) --
+ * over random shapes and settings, the object API, the float instantiation and NaN inputs
+ * (tests/test_reference_build.py), plus the committed outputs of that build (tests/golden/reference_outputs.json).
+ * Every line of the ADMM loop is thereby pinned to the reference's source; what stays unpinned against a real Eigen
+ * build is only the arithmetic inside Eigen's own kernels (LDLT pivot ties, reduction order), restated here and in
+ * eigen_lite from the published algorithm.
  *
  * This header is included twice by qp_oracle.c with SCALAR = double and float
  * (the reference instantiates both, src/qp.cpp:385-386).

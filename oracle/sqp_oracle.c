@@ -14,8 +14,9 @@
  * tests/sqp_test_autodiff.cpp are built in with hand-derived gradients (the reference uses
  * Eigen::AutoDiffScalar, which gives the same derivatives up to rounding).
  *
- * PARITY PINNING: checked against the reference's own assertions for these problems (solution within
- * isApprox 1e-2, iter < max_iter). Iteration counts are unpinned against a real Eigen build.
+ * PARITY PINNING: the reference's own assertions for these problems (solution within isApprox 1e-2, iter < max_iter), and BIT
+ * IDENTITY of whole trajectories (outer and inner iteration counts, iterates, per-iteration ADMM totals) with oracle/_ref -- the
+ * reference's own src/sqp.cpp + src/qp.cpp compiled unmodified against oracle/eigen_lite (tests/test_reference_build.py).
  */
 #include <float.h>
 #include <math.h>
