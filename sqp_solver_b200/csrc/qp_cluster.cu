@@ -136,7 +136,9 @@ __device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p
     return (a0 + a1) + (a2 + a3);
 }
 
-template <int CS>
+// FUSED: the launch is setup + solve of fresh instances (MODE_RESET | MODE_FACTOR | MODE_SOLVE, the hot path): the mode tests fold away at
+// compile time and the kernel is the round-1 one, free of spills at its 255 registers. !FUSED: the object API's separate launches.
+template <int CS, bool FUSED>
 __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, double *scratch) {
     extern __shared__ __align__(16) double smem_raw[];
     __shared__ int s_qp;
@@ -201,15 +203,17 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         // The distributed H^-1 never leaves the cluster's shared memory: a solve() after a separate setup()/update_qp() launch
         // rebuilds it from the stored constraint classes and rho (deterministic: the same factor setup computed), at the cost of
         // ~40 iterations' worth of work per instance.
-        const bool m_reset = (p.mode & MODE_RESET) != 0, m_factor = (p.mode & MODE_FACTOR) != 0, m_solve = (p.mode & MODE_SOLVE) != 0;
-        int status = p.status[b];
+        // (the mode bits are re-read from the kernel parameters where needed: this kernel sits at the 255-register limit)
+#define m_reset (FUSED || (p.mode & MODE_RESET) != 0)
+#define m_factor (FUSED || (p.mode & MODE_FACTOR) != 0)
+#define m_solve (FUSED || (p.mode & MODE_SOLVE) != 0)
+        int status = FUSED ? (int)SQPB200_UNSOLVED : p.status[b];
         int rho_updates = p.rho_updates[b] + (m_factor ? 1 : 0);  // rho_vec_update, qp.cpp:313
         double rho_est = p.rho_estimate[b], res_prim = p.res_prim[b], res_dual = p.res_dual[b];
         double rho = m_factor ? st.rho : p.rho[b];
         int iter_out = p.iter[b];
-        const signed char *ctype = p.ctype + b * m;
         // constraint class of row i: classified from the bounds by setup/update_qp (qp.cpp:31, :48), read back by solve
-        auto row_type = [&](int i) -> int { return m_factor ? classify(__ldg(l + i), __ldg(u + i)) : (int)ctype[i]; };
+        auto row_type = [&](int i) -> int { return m_factor ? classify(__ldg(l + i), __ldg(u + i)) : (int)p.ctype[b * m + i]; };
 
         // values of this instance + the batch-shared pattern -> shared memory (the region is reused by the sweep: restaged after it)
         auto stage_sparse = [&]() {
@@ -790,11 +794,14 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         cluster.sync();  // nobody is still reading this QP's exchanged vectors (or s_qp) when the next one starts
     }
     cluster.sync();  // no CTA exits while a peer may still touch its shared memory
+#undef m_reset
+#undef m_factor
+#undef m_solve
 }
 
 template <int CS>
 static cudaError_t cluster_config(size_t smem, int *max_clusters) {
-    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel<CS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS * 16, 1, 1);
@@ -807,7 +814,7 @@ static cudaError_t cluster_config(size_t smem, int *max_clusters) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(max_clusters, qp_cluster_kernel<CS>, &cfg);
+    return cudaOccupancyMaxActiveClusters(max_clusters, qp_cluster_kernel<CS, true>, &cfg);
 }
 
 int cluster_max_clusters(int n, int m, int nnz, int ccap, int cs) {
@@ -824,7 +831,9 @@ size_t cluster_scratch_bytes(int clusters) { return sizeof(double) * cluster_scr
 template <int CS>
 static cudaError_t launch_cluster_cs(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len) {
     const size_t smem = sizeof(double) * cluster_smem_doubles(cluster_np(p.n), p.m, p.sp.nnz, p.sp.col_slice_cap, CS);
-    cudaError_t e = cudaFuncSetAttribute(qp_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool fused = p.mode == (MODE_RESET | MODE_FACTOR | MODE_SOLVE);
+    auto kernel = fused ? qp_cluster_kernel<CS, true> : qp_cluster_kernel<CS, false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (clusters > p.count) clusters = p.count;
     if (clusters < 1) return cudaErrorLaunchOutOfResources;
@@ -841,7 +850,7 @@ static cudaError_t launch_cluster_cs(const KernelParams &p, int clusters, double
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (name) snprintf(name, name_len, "cluster<%d>/sparse x%d", CS, clusters);
-    return cudaLaunchKernelEx(&cfg, qp_cluster_kernel<CS>, p, scratch);
+    return cudaLaunchKernelEx(&cfg, kernel, p, scratch);
 }
 
 cudaError_t launch_cluster(const KernelParams &p, int clusters, double *scratch, cudaStream_t stream, char *name, size_t name_len) {

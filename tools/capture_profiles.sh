@@ -11,6 +11,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-fil
 full() {  # name, kernel regex, bench args
     ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -o $OUT/${R}_$1 -f $B $3 > $OUT/${R}_$1.log 2>&1
     echo "$1 rc=$?"
+    python tools/ncu_summary.py $OUT/${R}_$1.ncu-rep $OUT/${R}_$1_full.json
+    # gpurun merges at most 64 MiB back: keep the summaries, and the report itself only for the headline kernel
+    if [ "$1" != "tile64x128_S1" ]; then rm -f $OUT/${R}_$1.ncu-rep; fi
 }
 full tile64x128_S1 qp_tile_kernel ""
 full tile64x128_S2 qp_tile_kernel "--settings S2"
@@ -20,4 +23,6 @@ full block_dense256x512_b592_S2 qp_block "--batch 592 --n 256 --m 512 --settings
 ncu --set full --clock-control none --import-source on -k regex:qp_cluster -s 1 -c 1 -o $OUT/${R}_cluster256x512_S2 -f \
     python bench.py --workload config5 --settings S2 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${R}_cluster256x512_S2.log 2>&1
 echo "cluster rc=$?"
-ls -la $OUT/${R}_*.ncu-rep
+python tools/ncu_summary.py $OUT/${R}_cluster256x512_S2.ncu-rep $OUT/${R}_cluster256x512_S2_full.json
+rm -f $OUT/${R}_cluster256x512_S2.ncu-rep
+ls -la $OUT/
