@@ -221,16 +221,21 @@ def run_reference(args, rank, world):
 WORKLOADS = {"config3": (8192, 64, 128), "config2": (1024, 32, 64), "config5": (2048, 256, 512)}
 
 
-def csrc_hash():
-    """Short hash of the kernel sources: ncu-derived constants under profiles/ (DRAM traffic per launch) are only quoted while the
-    sources they were captured from are unchanged."""
-    import glob
+KERNEL_SOURCES = {"tile": "qp_tile.cu", "cluster": "qp_cluster.cu", "small": "qp_small.cu", "block": "qp_block.cu", "generic": "qp_generic.cu"}
+
+
+def csrc_hash(kernel):
+    """Short hash of the sources of one kernel (its .cu + the shared headers): ncu-derived constants under profiles/ (DRAM traffic per
+    launch) are only quoted while the sources they were captured from are unchanged. `kernel`: a name as reported by
+    sqpb200_last_kernel ("tile<64,128,4>x2", "cluster<4>/sparse x33", ...)."""
     import hashlib
 
+    family = next((f for f in KERNEL_SOURCES if kernel.startswith(f)), None)
+    files = ["qp_common.cuh", "qp_tile.cuh"] + ([KERNEL_SOURCES[family]] if family else sorted(KERNEL_SOURCES.values()))
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "sqp_solver_b200", "csrc", "*.cu*"))):
-        h.update(os.path.basename(f).encode())
-        h.update(open(f, "rb").read())
+    for f in files:
+        h.update(f.encode())
+        h.update(open(os.path.join(ROOT, "sqp_solver_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -243,7 +248,7 @@ def traffic_for(key):
         e = None
     if not isinstance(e, dict):
         return None, "no ncu capture recorded for this workload"
-    if e.get("csrc") != csrc_hash():
+    if e.get("csrc") != csrc_hash(key):
         return None, "stale: the ncu capture (%s) predates the current kernel sources" % e.get("capture", "?")
     return float(e["bytes"]), "ncu --set full capture %s (dram__bytes_read.sum + dram__bytes_write.sum of the solve kernel, one launch)" % e.get("capture", "?")
 

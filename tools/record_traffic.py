@@ -19,9 +19,9 @@ def main():
     path = os.path.join(ROOT, "profiles", "traffic.json")
     t = json.load(open(path)) if os.path.exists(path) else {}
     t = {k: v for k, v in t.items() if isinstance(v, dict)}  # drop the pre-hash format
-    t[key] = {"bytes": total, "csrc": bench.csrc_hash(), "capture": os.path.basename(summary)}
+    t[key] = {"bytes": total, "csrc": bench.csrc_hash(key), "capture": os.path.basename(summary)}
     json.dump(t, open(path, "w"), indent=1, sort_keys=True)
-    print(key, total, "bytes per launch; csrc", bench.csrc_hash())
+    print(key, total, "bytes per launch; csrc", bench.csrc_hash(key))
 
 
 if __name__ == "__main__":
