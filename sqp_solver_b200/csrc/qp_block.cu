@@ -33,7 +33,8 @@ size_t block_fact_doubles(int n) { return block_fact_doubles_hd(n); }
 
 struct BlockSmem {
     double *x, *xt, *b, *q, *t, *dinv;             // np each
-    double *z, *y, *w, *l, *u, *rho, *rhoinv;      // m each
+    double *z, *y, *w, *l, *u, *rho;               // m each (1/rho is recomputed where it is used: one division per row and iteration buys
+                                                   // the 4 KB that let a second CTA share the SM at n = 256, m = 512)
     double *panel;                                 // np x 32 (factorisation only)
     double *wsm;                                   // 32 x 32 + 32
     double *vals;                                  // nnz (sparse A: this instance's values), else unused
@@ -42,8 +43,8 @@ struct BlockSmem {
 __device__ __forceinline__ BlockSmem carve_block(double *base, int np, int m, int nnz) {
     BlockSmem s;
     s.x = base; s.xt = s.x + np; s.b = s.xt + np; s.q = s.b + np; s.t = s.q + np; s.dinv = s.t + np;
-    s.z = s.dinv + np; s.y = s.z + m; s.w = s.y + m; s.l = s.w + m; s.u = s.l + m; s.rho = s.u + m; s.rhoinv = s.rho + m;
-    s.panel = s.rhoinv + m + (m & 1);
+    s.z = s.dinv + np; s.y = s.z + m; s.w = s.y + m; s.l = s.w + m; s.u = s.l + m; s.rho = s.u + m;
+    s.panel = s.rho + m + (m & 1);
     s.wsm = s.panel + (size_t)np * NB;
     s.vals = s.wsm + WBLK;
     s.type = reinterpret_cast<signed char *>(s.vals + nnz);
@@ -51,7 +52,7 @@ __device__ __forceinline__ BlockSmem carve_block(double *base, int np, int m, in
 }
 static size_t block_smem_bytes(int n, int m, int nnz = 0) {
     const size_t np = block_np(n);
-    return sizeof(double) * (6 * np + 7 * (size_t)m + 1 + np * NB + WBLK + (size_t)nnz) + (size_t)m + 16;
+    return sizeof(double) * (6 * np + 6 * (size_t)m + 1 + np * NB + WBLK + (size_t)nnz) + (size_t)m + 16;
 }
 bool block_supported(int n, int m, size_t smem_optin) { return n >= 1 && n <= 256 && m >= 0 && m <= 1024 && block_smem_bytes(n, m) <= smem_optin; }
 // sparse A: this instance's nnz values are staged in shared memory next to the vectors
@@ -409,7 +410,6 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
         for (int i = tid; i < m; i += BT) {
             const double r = rho_of(s.type[i], rho);
             s.rho[i] = r;
-            s.rhoinv[i] = 1.0 / r;
         }
         __syncthreads();
         if (p.mode & MODE_FACTOR) {
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                         acc = (acc0 + acc1) + (acc2 + acc3);
                     }
                     const double zh = alpha * acc + (1.0 - alpha) * s.z[i];
-                    const double zn = box_project(zh + s.rhoinv[i] * s.y[i], s.l[i], s.u[i]);
+                    const double zn = box_project(zh + (1.0 / s.rho[i]) * s.y[i], s.l[i], s.u[i]);
                     s.y[i] = s.y[i] + s.rho[i] * (zh - zn);
                     s.z[i] = zn;
                 }
@@ -540,7 +540,6 @@ __global__ void __launch_bounds__(BT, 2) qp_block_kernel(KernelParams p) {
                             for (int i = tid; i < m; i += BT) {
                                 const double r = rho_of(s.type[i], rho);
                                 s.rho[i] = r;
-                                s.rhoinv[i] = 1.0 / r;
                             }
                             __syncthreads();
                             if (sparse) form_H_sparse(P, sp, vals, s, n, np, sigma, Hw);
