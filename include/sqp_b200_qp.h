@@ -80,6 +80,9 @@ typedef enum sqpb200_error {
 /* pointer-space flags for the data arguments of one call */
 #define SQPB200_HOST_PTRS 0u   /* caller passes host buffers; the call copies and synchronises */
 #define SQPB200_DEVICE_PTRS 1u /* caller passes device buffers; the call is asynchronous on `stream` */
+#define SQPB200_HOST_ASYNC 2u  /* caller passes PAGE-LOCKED host buffers (sqpb200_host_alloc) that stay untouched until `stream` has been
+                                  synchronised: copies and launch are enqueued on `stream` and the call returns at once. For callers that
+                                  pipeline host work against the GPU (sqp::BatchSQP advances two groups of instances alternately) */
 /* `stream` is a cudaStream_t passed as void*; NULL is the CUDA legacy default stream. */
 
 /* context options for sqpb200_ctx_set_option */
@@ -137,6 +140,10 @@ int sqpb200_qp_batch_set_precision(sqpb200_qp_batch *b, int fp32);
  * results straight into the owner's arrays (sqpb200_qp_batch_get with device pointers into the imported mapping): no separate split
  * or gather step, the transfer overlaps the solve QP by QP. Buffers come from sqpb200_dev_alloc (so that a handle maps the whole
  * allocation), are exported as 64-byte CUDA IPC handles, and imported by the other processes of the node. */
+/* streams for SQPB200_HOST_ASYNC / SQPB200_DEVICE_PTRS callers that have no CUDA runtime of their own (non-blocking streams) */
+int sqpb200_stream_create(sqpb200_ctx *ctx, void **stream);
+int sqpb200_stream_destroy(sqpb200_ctx *ctx, void *stream);
+int sqpb200_stream_sync(sqpb200_ctx *ctx, void *stream);
 /* page-locked host buffers for HOST_PTRS callers that call every few hundred microseconds (the SQP outer loop, src/sqp.cpp:210-242):
  * copies from pinned memory are asynchronous and need no intermediate staging by the driver */
 int sqpb200_host_alloc(sqpb200_ctx *ctx, size_t bytes, void **host_ptr);

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libsqp_b200.so")
 SOLVED, MAX_ITER_EXCEEDED, UNSOLVED, NUMERICAL_ISSUES, UNINITIALIZED = range(5)  # qp.hpp:70
 INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = range(3)  # qp.hpp:134
 STATUS_NAMES = ["SOLVED", "MAX_ITER_EXCEEDED", "UNSOLVED", "NUMERICAL_ISSUES", "UNINITIALIZED"]
-HOST_PTRS, DEVICE_PTRS = 0, 1
+HOST_PTRS, DEVICE_PTRS, HOST_ASYNC = 0, 1, 2
 OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS = 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE, KERNEL_BLOCK, KERNEL_CLUSTER, KERNEL_SMALL = 0, 1, 2, 3, 4, 5
 KEEP_FACTOR, REUSE_FACTOR = 1, 2
@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "sqpb200_qp_batch_setup_solve_opts", "sqpb200_qp_batch_setup_solve_sparse", "sqpb200_qp_batch_set_precision", "sqpb200_dev_alloc", "sqpb200_dev_free", "sqpb200_dev_copy",
     "sqpb200_ipc_export", "sqpb200_ipc_import", "sqpb200_ipc_release", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
-    "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to", "sqpb200_host_alloc", "sqpb200_host_free", "sqpb200_qp_batch_setup_sparse",
+    "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to", "sqpb200_host_alloc", "sqpb200_host_free", "sqpb200_stream_create", "sqpb200_stream_destroy", "sqpb200_stream_sync", "sqpb200_qp_batch_setup_sparse",
     "sqpb200_qp_batch_update_qp_sparse", "sqpb200_qp_batch_solve_sparse",
 ]
 
@@ -98,6 +98,9 @@ def load_library(path=None):
     L.sqpb200_qp_batch_set_precision.argtypes = [vp, C.c_int]
     L.sqpb200_dev_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
     L.sqpb200_dev_free.argtypes = [vp, vp]
+    L.sqpb200_stream_create.argtypes = [vp, C.POINTER(C.c_void_p)]
+    L.sqpb200_stream_destroy.argtypes = [vp, vp]
+    L.sqpb200_stream_sync.argtypes = [vp, vp]
     L.sqpb200_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
     L.sqpb200_host_free.argtypes = [vp, vp]
     L.sqpb200_dev_copy.argtypes = [vp, vp, vp, C.c_size_t, vp]

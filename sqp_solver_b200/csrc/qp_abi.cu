@@ -221,6 +221,26 @@ int sqpb200_dev_copy(sqpb200_ctx *c, void *dst, const void *src, size_t bytes, v
     if (bytes) CK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return SQPB200_OK;
 }
+int sqpb200_stream_create(sqpb200_ctx *c, void **stream) {
+    if (!c || !stream) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = nullptr;
+    CK(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return SQPB200_OK;
+}
+int sqpb200_stream_destroy(sqpb200_ctx *c, void *stream) {
+    if (!c) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (stream) CK(c, cudaStreamDestroy((cudaStream_t)stream));
+    return SQPB200_OK;
+}
+int sqpb200_stream_sync(sqpb200_ctx *c, void *stream) {
+    if (!c) return SQPB200_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize((cudaStream_t)stream));
+    return SQPB200_OK;
+}
 int sqpb200_host_alloc(sqpb200_ctx *c, size_t bytes, void **host_ptr) {
     if (!c || !host_ptr) return SQPB200_ERR_INVALID;
     *host_ptr = nullptr;
@@ -598,6 +618,20 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
     int chunks = c->opt_chunks;
     if ((size_t)chunks > total_bytes / (4u << 20) + 1) chunks = (int)(total_bytes / (4u << 20) + 1);
     if (chunks > count) chunks = count;
+    if (chunks <= 1 || (flags & SQPB200_HOST_ASYNC)) {
+        // small call: the copies go on the caller's stream ahead of the launch -- no copy stream, no flag, no cross-stream event
+        CK(c, cudaMemcpyAsync(b->dP, P, (size_t)count * n * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(c, cudaMemcpyAsync(b->dA, A, (size_t)count * m * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        CK(c, cudaMemcpyAsync(b->dq, q, (size_t)count * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (m > 0) {
+            CK(c, cudaMemcpyAsync(b->dl, l, (size_t)count * m * sizeof(double), cudaMemcpyHostToDevice, stream));
+            CK(c, cudaMemcpyAsync(b->du, u, (size_t)count * m * sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        rc = launch_range(b, st, mode, 0, count, b->dP, b->dq, b->dA, b->dl, b->du, stream);
+        if (rc) return rc;
+        if (!(flags & SQPB200_HOST_ASYNC)) CK(c, cudaStreamSynchronize(stream));
+        return SQPB200_OK;
+    }
     CK(c, cudaMemsetAsync(b->ready_dev, 0, sizeof(int), stream));
     // the compute stream may still be reading the staging buffers from an earlier call; the flag reset must precede the copies
     CK(c, cudaEventRecord(b->stage_event, stream));
@@ -933,7 +967,7 @@ int sqpb200_qp_batch_get(sqpb200_qp_batch *b, int count, double *x, double *y, d
     if (rho_estimate) CK(c, cudaMemcpyAsync(rho_estimate, b->rho_estimate, B * sizeof(double), kind, stream));
     if (res_prim) CK(c, cudaMemcpyAsync(res_prim, b->res_prim, B * sizeof(double), kind, stream));
     if (res_dual) CK(c, cudaMemcpyAsync(res_dual, b->res_dual, B * sizeof(double), kind, stream));
-    if (!(flags & SQPB200_DEVICE_PTRS)) CK(c, cudaStreamSynchronize(stream));
+    if (!(flags & (SQPB200_DEVICE_PTRS | SQPB200_HOST_ASYNC))) CK(c, cudaStreamSynchronize(stream));
     return SQPB200_OK;
 }
 

@@ -10,10 +10,12 @@
 // l1-merit backtracking line search, step, termination on step norms + constraint violation.
 // The outer loop and BFGS stay on the host (user callbacks are host virtuals); only the QP is on the GPU.
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <functional>
 #include <iostream>
 #include <limits>
+#include <memory>
 #include <vector>
 
 #include "../../overlay/solvers/qp.hpp"
@@ -367,7 +369,10 @@ class SQP {
     qp_solver::QPSolver<Scalar> qp_solver_;
 };
 
-/** B SQP instances in lock-step; the QP subproblems of one outer iteration are one batched GPU solve. */
+/** B SQP instances in lock-step; the QP subproblems of one outer iteration are batched GPU solves.
+ *  The instances are split into (up to) two groups, each with its own BatchQPSolver and stream: while the GPU solves one group's QPs
+ *  the host forms the other group's QPs or runs its line searches, so host and device work overlap (each instance's trajectory is
+ *  independent of the grouping). */
 class BatchSQP {
    public:
     using Scalar = double;
@@ -375,26 +380,39 @@ class BatchSQP {
     using Vector = Problem::Vector;
     using Settings = sqp_settings_t<double>;
 
-    /** All problems must share num_var and num_constr. The problems are not owned. */
-    explicit BatchSQP(const std::vector<Problem *> &problems, int device = 0)
-        : probs_(problems), nx_(problems.at(0)->num_var), nc_(problems.at(0)->num_constr),
-          qp_((int)problems.size(), nx_, nc_, device), inst_(problems.size()) {
+    /** All problems must share num_var and num_constr. The problems are not owned. `groups`: 0 = automatic (two groups from 512
+     *  instances on), 1 = a single group (one batched solve per outer iteration). */
+    explicit BatchSQP(const std::vector<Problem *> &problems, int device = 0, int groups = 0)
+        : probs_(problems), nx_(problems.at(0)->num_var), nc_(problems.at(0)->num_constr), inst_(problems.size()) {
         for (auto *p : probs_)
             if (p->num_var != nx_ || p->num_constr != nc_) throw std::invalid_argument("BatchSQP: problems differ in size");
-        detail::install_qp_settings(qp_.settings());
-        qp_.fetch_full_info(false);  // the outer loop reads x, y, status and iter only (sqp.cpp:224-239)
-        // the packed QP arrays ARE the solver's page-locked staging buffers: one asynchronous copy per array per outer iteration
-        P_ = qp_.staged_P(); q_ = qp_.staged_q(); A_ = qp_.staged_A(); l_ = qp_.staged_l(); u_ = qp_.staged_u();
-        slot_.resize(probs_.size());
+        const size_t B = probs_.size();
+        const int ng = groups > 0 ? (groups > 2 ? 2 : groups) : (B >= 512 ? 2 : 1);
+        for (int g = 0; g < ng; ++g) {
+            Group G;
+            G.lo = B * g / ng;
+            G.hi = B * (g + 1) / ng;
+            G.qp.reset(new qp_solver::BatchQPSolver((int)(G.hi - G.lo), nx_, nc_, device));
+            detail::install_qp_settings(G.qp->settings());
+            G.qp->fetch_full_info(false);  // the outer loop reads x, y, status and iter only (sqp.cpp:224-239)
+            // the packed QP arrays ARE the solver's page-locked staging buffers: one asynchronous copy per array per outer iteration
+            G.P = G.qp->staged_P(); G.q = G.qp->staged_q(); G.A = G.qp->staged_A(); G.l = G.qp->staged_l(); G.u = G.qp->staged_u();
+            G.slot.resize(G.hi - G.lo);
+            groups_.push_back(std::move(G));
+        }
     }
 
     Settings &settings() { return settings_; }
-    qp_solver::BatchQPSolver &qp_solver() { return qp_; }
+    qp_solver::BatchQPSolver &qp_solver(int group = 0) { return *groups_[group].qp; }
     size_t size() const { return probs_.size(); }
     const Vector &primal_solution(size_t i) const { return inst_[i].x_; }
     const Vector &dual_solution(size_t i) const { return inst_[i].lambda_; }
     const Info &info(size_t i) const { return inst_[i].info_; }
     int qp_launches() const { return launches_; }
+    // wall-clock seconds of the last solve() spent in: [0] forming and packing the QPs (host), [1] WAITING for the batched GPU QP calls
+    // (whatever of staging + launch + read-back did not hide behind host work), [2] unpacking the results (host), [3] line search /
+    // step / termination (host)
+    const double *phase_seconds() const { return phase_; }
     long long hessian_repairs() const {
         long long t = 0;
         for (const auto &I : inst_) t += I.hessian_repairs;
@@ -411,44 +429,75 @@ class BatchSQP {
             inst_[i].hessian_repairs = 0;
         }
         launches_ = 0;
+        for (double &t : phase_) t = 0;
         for (int iter = 1; iter <= settings_.max_iter; ++iter) {
-            // compact the still-active instances into the leading slots of the packed QP arrays
-            int na = 0;
-            for (size_t i = 0; i < B; ++i)
-                if (inst_[i].active) slot_[na++] = (int)i;
-            if (na == 0) break;
-            // host side of the outer iteration: independent per instance (user callbacks must be re-entrant across
-            // DIFFERENT problem objects when built with OpenMP)
+            bool any = false;
+            // phase A: per group, form the QPs of the still-active instances and hand them to the GPU (asynchronous)
+            for (auto &G : groups_) {
+                const auto t0 = now();
+                G.na = 0;
+                for (size_t i = G.lo; i < G.hi; ++i)
+                    if (inst_[i].active) G.slot[G.na++] = (int)i;  // compact into the leading slots of the packed QP arrays
+                if (G.na == 0) continue;
+                any = true;
+                // host side of the outer iteration: independent per instance (user callbacks must be re-entrant across
+                // DIFFERENT problem objects when built with OpenMP)
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
-            for (int k = 0; k < na; ++k) {
-                auto &I = inst_[slot_[k]];
-                I.info_.iter = iter;
-                I.form_qp(*probs_[slot_[k]]);
-                pack(k, I, true);
-            }
-            solve_packed(na, settings_.second_order_correction ? SQPB200_KEEP_FACTOR : 0u);
-            if (settings_.second_order_correction) {
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static)
-#endif
-                for (int k = 0; k < na; ++k) {
-                    auto &I = inst_[slot_[k]];
-                    I.form_soc_bounds(*probs_[slot_[k]]);
-                    pack(k, I, false);  // only l and u change (the TODO at src/sqp.cpp:273)
+                for (int k = 0; k < G.na; ++k) {
+                    auto &I = inst_[G.slot[k]];
+                    I.info_.iter = iter;
+                    I.form_qp(*probs_[G.slot[k]]);
+                    pack(G, k, I, true);
                 }
-                solve_packed(na, SQPB200_REUSE_FACTOR);  // same P, A: instances with unchanged constraint classes skip the factorisation
+                phase_[0] += secs(t0, now());
+                G.qp->setup_solve_staged_async(G.na, settings_.second_order_correction ? SQPB200_KEEP_FACTOR : 0u);
+                ++launches_;
             }
+            if (!any) break;
+            // phase B: per group, collect the steps, optionally re-solve with the second-order-corrected bounds, line search
+            for (auto &G : groups_) {
+                if (G.na == 0) continue;
+                auto t0 = now();
+                G.qp->wait();
+                auto t1 = now();
+                phase_[1] += secs(t0, t1);
+                unpack(G);
+                phase_[2] += secs(t1, now());
+                if (settings_.second_order_correction) {
+                    t0 = now();
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
-            for (int k = 0; k < na; ++k) {
-                auto &I = inst_[slot_[k]];
-                if (I.finish_iteration(*probs_[slot_[k]], settings_)) {
-                    I.info_.status = SOLVED;
-                    I.active = false;
+                    for (int k = 0; k < G.na; ++k) {
+                        auto &I = inst_[G.slot[k]];
+                        I.form_soc_bounds(*probs_[G.slot[k]]);
+                        pack(G, k, I, false);  // only l and u change (the TODO at src/sqp.cpp:273)
+                    }
+                    t1 = now();
+                    phase_[0] += secs(t0, t1);
+                    // same P, A: instances with unchanged constraint classes skip the factorisation
+                    G.qp->setup_solve_staged_async(G.na, SQPB200_REUSE_FACTOR);
+                    ++launches_;
+                    G.qp->wait();
+                    auto t2 = now();
+                    phase_[1] += secs(t1, t2);
+                    unpack(G);
+                    phase_[2] += secs(t2, now());
                 }
+                t0 = now();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+                for (int k = 0; k < G.na; ++k) {
+                    auto &I = inst_[G.slot[k]];
+                    if (I.finish_iteration(*probs_[G.slot[k]], settings_)) {
+                        I.info_.status = SOLVED;
+                        I.active = false;
+                    }
+                }
+                phase_[3] += secs(t0, now());
             }
         }
         for (auto &I : inst_)
@@ -460,32 +509,44 @@ class BatchSQP {
     }
 
    private:
-    void pack(int k, const detail::Instance<double> &I, bool all) {
+    struct Group {
+        size_t lo = 0, hi = 0;  // instances [lo, hi)
+        std::unique_ptr<qp_solver::BatchQPSolver> qp;
+        double *P = nullptr, *q = nullptr, *A = nullptr, *l = nullptr, *u = nullptr;  // packed QP arrays, owned by qp
+        std::vector<int> slot;
+        int na = 0;
+    };
+    typedef std::chrono::steady_clock::time_point tp;
+    static tp now() { return std::chrono::steady_clock::now(); }
+    static double secs(tp a, tp b) { return std::chrono::duration<double>(b - a).count(); }
+
+    void pack(Group &G, int k, const detail::Instance<double> &I, bool all) {
         const size_t nn = (size_t)nx_ * nx_, mn = (size_t)nc_ * nx_;
         if (all) {
             for (int j = 0; j < nx_; ++j)
-                for (int i = 0; i < nx_; ++i) P_[k * nn + i + (size_t)nx_ * j] = I.Hess_(i, j);
+                for (int i = 0; i < nx_; ++i) G.P[k * nn + i + (size_t)nx_ * j] = I.Hess_(i, j);
             for (int j = 0; j < nx_; ++j)
-                for (int i = 0; i < nc_; ++i) A_[k * mn + i + (size_t)nc_ * j] = I.Jac_constr_(i, j);
-            for (int i = 0; i < nx_; ++i) q_[(size_t)k * nx_ + i] = I.grad_obj_(i);
+                for (int i = 0; i < nc_; ++i) G.A[k * mn + i + (size_t)nc_ * j] = I.Jac_constr_(i, j);
+            for (int i = 0; i < nx_; ++i) G.q[(size_t)k * nx_ + i] = I.grad_obj_(i);
         }
         for (int i = 0; i < nc_; ++i) {
-            l_[(size_t)k * nc_ + i] = I.ql(i);
-            u_[(size_t)k * nc_ + i] = I.qu(i);
+            G.l[(size_t)k * nc_ + i] = I.ql(i);
+            G.u[(size_t)k * nc_ + i] = I.qu(i);
         }
     }
-    void solve_packed(int na, unsigned opts) {  // run_solve_qp for every active instance (src/sqp.cpp:210-242)
-        qp_.setup_solve_staged(na, opts);
-        ++launches_;
-        for (int k = 0; k < na; ++k) {
-            auto &I = inst_[slot_[k]];
-            const auto qi = qp_.info(k);
+    void unpack(Group &G) {  // the tail of run_solve_qp for every active instance (src/sqp.cpp:224-239)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+        for (int k = 0; k < G.na; ++k) {
+            auto &I = inst_[G.slot[k]];
+            const auto qi = G.qp->info(k);
             // A QP whose setup fails is not solved (qp.cpp:68-71), so the reference adds its solver's STALE info().iter (sqp.cpp:224):
             // the count of this instance's previous subproblem -- not whatever instance last occupied batch slot k.
             if (qi.status != qp_solver::NUMERICAL_ISSUES) I.last_qp_iter = qi.iter;
             I.info_.qp_solver_iter += I.last_qp_iter;
             if (qi.status == qp_solver::NUMERICAL_ISSUES) continue;  // keep the stale step, like the reference
-            const double *xs = qp_.primal_solution(k), *ys = qp_.dual_solution(k);
+            const double *xs = G.qp->primal_solution(k), *ys = G.qp->dual_solution(k);
             for (int i = 0; i < nx_; ++i) I.p(i) = xs[i];
             for (int i = 0; i < nc_; ++i) I.p_lambda(i) = ys[i];
         }
@@ -493,12 +554,11 @@ class BatchSQP {
 
     std::vector<Problem *> probs_;
     int nx_, nc_;
-    qp_solver::BatchQPSolver qp_;
+    std::vector<Group> groups_;
     std::vector<detail::Instance<double>> inst_;
     Settings settings_;
-    double *P_ = nullptr, *q_ = nullptr, *A_ = nullptr, *l_ = nullptr, *u_ = nullptr;  // owned by qp_
-    std::vector<int> slot_;
     int launches_ = 0;
+    double phase_[4] = {0, 0, 0, 0};
 };
 
 }  // namespace sqp

@@ -148,6 +148,10 @@ class BatchQPSolver {
         }
     }
     ~BatchQPSolver() {
+        if (stream_) {
+            sqpb200_stream_sync(dev_->ctx(), stream_);
+            sqpb200_stream_destroy(dev_->ctx(), stream_);
+        }
         sqpb200_qp_batch_destroy(h_);
         for (void *p : pinned_) sqpb200_host_free(dev_->ctx(), p);
     }
@@ -195,6 +199,24 @@ class BatchQPSolver {
     double *staged_u() { return staged(4, (size_t)(m_ > 0 ? m_ : 1)); }
     void setup_solve_staged(int count = -1, unsigned opts = 0) {
         setup_solve(staged_P(), staged_q(), staged_A(), staged_l(), staged_u(), count, opts);
+    }
+    // The same, asynchronously on this object's own stream: copies of the staged inputs, the launch and the read-back of x, y, status
+    // and iter are enqueued and the call returns at once; wait() makes the results (primal_solution(i), info(i), ...) valid. The staged
+    // buffers must not be touched in between. Lets a caller pipeline host work against the GPU (sqp::BatchSQP alternates two groups).
+    void setup_solve_staged_async(int count = -1, unsigned opts = 0) {
+        if (count < 0) count = batch_;
+        if (!stream_) dev_->check(sqpb200_stream_create(dev_->ctx(), &stream_), "sqpb200_stream_create");
+        sqpb200_qp_settings s = settings_.to_c();
+        dev_->check(sqpb200_qp_batch_setup_solve_opts(h_, &s, count, staged_P(), staged_q(), staged_A(), staged_l(), staged_u(), SQPB200_HOST_ASYNC,
+                                                      stream_, opts),
+                    "setup_solve (async)");
+        dev_->check(sqpb200_qp_batch_get(h_, count, x_, y_, nullptr, status_, iter_, full_info_ ? rho_updates_ : nullptr,
+                                         full_info_ ? rho_estimate_ : nullptr, full_info_ ? res_prim_ : nullptr,
+                                         full_info_ ? res_dual_ : nullptr, SQPB200_HOST_ASYNC, stream_),
+                    "get (async)");
+    }
+    void wait() {
+        if (stream_) dev_->check(sqpb200_stream_sync(dev_->ctx(), stream_), "sqpb200_stream_sync");
     }
 
     // The reference's intended sparse variant (Eigen::SparseMatrix A: include/solvers/qp.hpp:22-25,
@@ -279,6 +301,7 @@ class BatchQPSolver {
     int *status_ = nullptr, *iter_ = nullptr, *rho_updates_ = nullptr;
     double *in_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<void *> pinned_;
+    void *stream_ = nullptr;  // created on first asynchronous call
 };
 
 /**

@@ -72,9 +72,11 @@ int main(int argc, char **argv) {
             solved += batch.info(i).status == SOLVED;
             if (batch.info(i).status == SOLVED) checksum += batch.primal_solution(i)(0) + batch.primal_solution(i)(1);
         }
+        const double *ph = batch.phase_seconds();  // of the last run
         printf("{\"batch\": %d, \"runs\": %d, \"seconds\": %.6f, \"sqp_per_s\": %.1f, \"qp_launches\": %d, \"solved\": %d, "
-               "\"qp_solver_iter_total\": %lld, \"checksum_solved_x\": %.12g}\n",
-               B, runs, best, B / best, batch.qp_launches(), solved, qp_iters, checksum);
+               "\"qp_solver_iter_total\": %lld, \"checksum_solved_x\": %.12g, \"hessian_repairs\": %lld, "
+               "\"phase_seconds\": {\"form_and_pack_qps_host\": %.6f, \"gpu_qp_calls\": %.6f, \"unpack_host\": %.6f, \"line_search_step_host\": %.6f}}\n",
+               B, runs, best, B / best, batch.qp_launches(), solved, qp_iters, checksum, batch.hessian_repairs(), ph[0], ph[1], ph[2], ph[3]);
     } catch (const std::exception &e) {
         fprintf(stderr, "batch_sqp_bench: %s\n", e.what());
         return 1;

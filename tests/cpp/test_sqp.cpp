@@ -127,6 +127,46 @@ TEST(BatchSQPTest, LockStepMatchesSingleSolves) {
     printf("  batch of %d: %d solved, %d batched QP launches for up to %d outer iterations\n", B, solved, batch.qp_launches(), max_outer);
     EXPECT_GE(solved, B / 3);  // this SQP variant does not converge from every start
     EXPECT_LE(batch.qp_launches(), max_outer);
+    // two pipelined groups (asynchronous staged calls on two streams; the default from 512 instances on): same trajectories
+    BatchSQP two(ptrs, 0, 2);
+    two.settings().max_iter = 100;
+    two.solve(x0, l0);
+    for (int i = 0; i < B; ++i) {
+        EXPECT_EQ(two.info(i).iter, batch.info(i).iter);
+        EXPECT_EQ(two.info(i).qp_solver_iter, batch.info(i).qp_solver_iter);
+        EXPECT_EQ(two.info(i).status, batch.info(i).status);
+        EXPECT_TRUE(two.primal_solution(i)(0) == batch.primal_solution(i)(0) && two.primal_solution(i)(1) == batch.primal_solution(i)(1));
+    }
+    EXPECT_LE(two.qp_launches(), 2 * max_outer);
+}
+
+// second-order correction in the batch (KEEP_FACTOR / REUSE_FACTOR re-solve per outer iteration) == the single solver
+TEST(BatchSQPTest, SecondOrderCorrectionMatchesSingleSolves) {
+    const int B = 24;
+    std::vector<SimpleNLP> probs(B);
+    std::vector<NonLinearProblem<double> *> ptrs;
+    std::vector<Vec> x0, l0;
+    for (int i = 0; i < B; ++i) {
+        ptrs.push_back(&probs[i]);
+        x0.push_back(v2(1.2 + 0.03 * i, 0.1 + 0.02 * i));
+        l0.push_back(zeros(3));
+    }
+    for (int groups = 1; groups <= 2; ++groups) {
+        BatchSQP batch(ptrs, 0, groups);
+        batch.settings().max_iter = 100;
+        batch.settings().second_order_correction = true;
+        batch.solve(x0, l0);
+        for (int i = 0; i < B; ++i) {
+            SQP<double> single;
+            single.settings().max_iter = 100;
+            single.settings().second_order_correction = true;
+            single.solve(probs[i], x0[i], l0[i]);
+            EXPECT_EQ(batch.info(i).iter, single.info().iter);
+            EXPECT_EQ(batch.info(i).qp_solver_iter, single.info().qp_solver_iter);
+            EXPECT_EQ(batch.info(i).status, single.info().status);
+            EXPECT_TRUE(batch.primal_solution(i).isApprox(single.primal_solution(), 1e-9));
+        }
+    }
 }
 
 MINI_TEST_MAIN()
