@@ -430,74 +430,21 @@ class BatchSQP {
         }
         launches_ = 0;
         for (double &t : phase_) t = 0;
-        for (int iter = 1; iter <= settings_.max_iter; ++iter) {
-            bool any = false;
-            // phase A: per group, form the QPs of the still-active instances and hand them to the GPU (asynchronous)
+        // Each group is its own little state machine (form + launch -> wait -> line search -> form + launch ...) and the host
+        // alternates between them: while the GPU solves one group's QPs the host runs the other group's line searches and forms
+        // its next QPs, so with two groups the GPU latency of an outer iteration hides behind host work.
+        for (auto &G : groups_) {
+            G.iter = 1;
+            G.in_flight = start(G);
+        }
+        for (bool any = true; any;) {
+            any = false;
             for (auto &G : groups_) {
-                const auto t0 = now();
-                G.na = 0;
-                for (size_t i = G.lo; i < G.hi; ++i)
-                    if (inst_[i].active) G.slot[G.na++] = (int)i;  // compact into the leading slots of the packed QP arrays
-                if (G.na == 0) continue;
-                any = true;
-                // host side of the outer iteration: independent per instance (user callbacks must be re-entrant across
-                // DIFFERENT problem objects when built with OpenMP)
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static)
-#endif
-                for (int k = 0; k < G.na; ++k) {
-                    auto &I = inst_[G.slot[k]];
-                    I.info_.iter = iter;
-                    I.form_qp(*probs_[G.slot[k]]);
-                    pack(G, k, I, true);
+                if (G.in_flight) {
+                    finish(G);
+                    G.in_flight = (++G.iter <= settings_.max_iter) && start(G);
                 }
-                phase_[0] += secs(t0, now());
-                G.qp->setup_solve_staged_async(G.na, settings_.second_order_correction ? SQPB200_KEEP_FACTOR : 0u);
-                ++launches_;
-            }
-            if (!any) break;
-            // phase B: per group, collect the steps, optionally re-solve with the second-order-corrected bounds, line search
-            for (auto &G : groups_) {
-                if (G.na == 0) continue;
-                auto t0 = now();
-                G.qp->wait();
-                auto t1 = now();
-                phase_[1] += secs(t0, t1);
-                unpack(G);
-                phase_[2] += secs(t1, now());
-                if (settings_.second_order_correction) {
-                    t0 = now();
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static)
-#endif
-                    for (int k = 0; k < G.na; ++k) {
-                        auto &I = inst_[G.slot[k]];
-                        I.form_soc_bounds(*probs_[G.slot[k]]);
-                        pack(G, k, I, false);  // only l and u change (the TODO at src/sqp.cpp:273)
-                    }
-                    t1 = now();
-                    phase_[0] += secs(t0, t1);
-                    // same P, A: instances with unchanged constraint classes skip the factorisation
-                    G.qp->setup_solve_staged_async(G.na, SQPB200_REUSE_FACTOR);
-                    ++launches_;
-                    G.qp->wait();
-                    auto t2 = now();
-                    phase_[1] += secs(t1, t2);
-                    unpack(G);
-                    phase_[2] += secs(t2, now());
-                }
-                t0 = now();
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static)
-#endif
-                for (int k = 0; k < G.na; ++k) {
-                    auto &I = inst_[G.slot[k]];
-                    if (I.finish_iteration(*probs_[G.slot[k]], settings_)) {
-                        I.info_.status = SOLVED;
-                        I.active = false;
-                    }
-                }
-                phase_[3] += secs(t0, now());
+                any = any || G.in_flight;
             }
         }
         for (auto &I : inst_)
@@ -514,11 +461,79 @@ class BatchSQP {
         std::unique_ptr<qp_solver::BatchQPSolver> qp;
         double *P = nullptr, *q = nullptr, *A = nullptr, *l = nullptr, *u = nullptr;  // packed QP arrays, owned by qp
         std::vector<int> slot;
-        int na = 0;
+        int na = 0, iter = 0;
+        bool in_flight = false;
     };
     typedef std::chrono::steady_clock::time_point tp;
     static tp now() { return std::chrono::steady_clock::now(); }
     static double secs(tp a, tp b) { return std::chrono::duration<double>(b - a).count(); }
+
+    // form the QPs of the still-active instances of a group and hand them to the GPU (asynchronous); false when none is left
+    bool start(Group &G) {
+        const auto t0 = now();
+        G.na = 0;
+        for (size_t i = G.lo; i < G.hi; ++i)
+            if (inst_[i].active) G.slot[G.na++] = (int)i;  // compact into the leading slots of the packed QP arrays
+        if (G.na == 0) return false;
+        const int iter = G.iter;
+        // host side of the outer iteration: independent per instance (user callbacks must be re-entrant across
+        // DIFFERENT problem objects when built with OpenMP)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+        for (int k = 0; k < G.na; ++k) {
+            auto &I = inst_[G.slot[k]];
+            I.info_.iter = iter;
+            I.form_qp(*probs_[G.slot[k]]);
+            pack(G, k, I, true);
+        }
+        phase_[0] += secs(t0, now());
+        G.qp->setup_solve_staged_async(G.na, settings_.second_order_correction ? SQPB200_KEEP_FACTOR : 0u);
+        ++launches_;
+        return true;
+    }
+    // collect the steps of a group, optionally re-solve with the second-order-corrected bounds, line search, step, termination
+    void finish(Group &G) {
+        auto t0 = now();
+        G.qp->wait();
+        auto t1 = now();
+        phase_[1] += secs(t0, t1);
+        unpack(G);
+        phase_[2] += secs(t1, now());
+        if (settings_.second_order_correction) {
+            t0 = now();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+            for (int k = 0; k < G.na; ++k) {
+                auto &I = inst_[G.slot[k]];
+                I.form_soc_bounds(*probs_[G.slot[k]]);
+                pack(G, k, I, false);  // only l and u change (the TODO at src/sqp.cpp:273)
+            }
+            t1 = now();
+            phase_[0] += secs(t0, t1);
+            // same P, A: instances with unchanged constraint classes skip the factorisation
+            G.qp->setup_solve_staged_async(G.na, SQPB200_REUSE_FACTOR);
+            ++launches_;
+            G.qp->wait();
+            const auto t2 = now();
+            phase_[1] += secs(t1, t2);
+            unpack(G);
+            phase_[2] += secs(t2, now());
+        }
+        t0 = now();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+        for (int k = 0; k < G.na; ++k) {
+            auto &I = inst_[G.slot[k]];
+            if (I.finish_iteration(*probs_[G.slot[k]], settings_)) {
+                I.info_.status = SOLVED;
+                I.active = false;
+            }
+        }
+        phase_[3] += secs(t0, now());
+    }
 
     void pack(Group &G, int k, const detail::Instance<double> &I, bool all) {
         const size_t nn = (size_t)nx_ * nx_, mn = (size_t)nc_ * nx_;

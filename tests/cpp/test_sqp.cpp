@@ -126,7 +126,7 @@ TEST(BatchSQPTest, LockStepMatchesSingleSolves) {
     }
     printf("  batch of %d: %d solved, %d batched QP launches for up to %d outer iterations\n", B, solved, batch.qp_launches(), max_outer);
     EXPECT_GE(solved, B / 3);  // this SQP variant does not converge from every start
-    EXPECT_LE(batch.qp_launches(), max_outer);
+    EXPECT_LE(batch.qp_launches(), max_outer + 1);
     // two pipelined groups (asynchronous staged calls on two streams; the default from 512 instances on): same trajectories
     BatchSQP two(ptrs, 0, 2);
     two.settings().max_iter = 100;
@@ -137,7 +137,7 @@ TEST(BatchSQPTest, LockStepMatchesSingleSolves) {
         EXPECT_EQ(two.info(i).status, batch.info(i).status);
         EXPECT_TRUE(two.primal_solution(i)(0) == batch.primal_solution(i)(0) && two.primal_solution(i)(1) == batch.primal_solution(i)(1));
     }
-    EXPECT_LE(two.qp_launches(), 2 * max_outer);
+    EXPECT_LE(two.qp_launches(), 2 * max_outer + 2);
 }
 
 // second-order correction in the batch (KEEP_FACTOR / REUSE_FACTOR re-solve per outer iteration) == the single solver

@@ -185,7 +185,7 @@ def test_batch_sqp_config4_full_size(oracle):
     print("config 4: %d SQPs in %.3f s = %.0f SQP/s, %d batched QP launches, %d solved, %d ADMM iterations" %
           (d["batch"], d["seconds"], d["sqp_per_s"], d["qp_launches"], d["solved"], d["qp_solver_iter_total"]))
     assert d["solved"] == d["solved_feasible"] and d["solved"] >= d["batch"] // 3
-    assert d["qp_launches"] <= 101
+    assert d["qp_launches"] <= 2 * 101  # two pipelined groups, one launch each per outer iteration
     agree = 0
     for inst in d["instances"]:
         ref = S.solve(S.CONSTRAINED_ROSENBROCK_2D, inst["x0"], [0, 0], S.default_settings())
