@@ -1,4 +1,4 @@
-// Host-only: mirrors the reference's tests/bfgs_test.cpp:21-65 against sqp_solver_b200/host/solvers/bfgs.hpp.
+// Host-only: mirrors the reference's tests/bfgs_test.cpp:21-65 against sqp_solver_b200/host/batch/solvers/bfgs.hpp.
 #include <cmath>
 
 #include "mini_test.hpp"

@@ -1,5 +1,5 @@
 // GPU: mirrors the reference's tests/qp_solver_test.cpp (all six TESTs, same bodies) against the
-// drop-in qp_solver::QPSolver<Scalar> of sqp_solver_b200/host/solvers/qp.hpp, plus the batched sibling.
+// drop-in qp_solver::QPSolver<Scalar> of sqp_solver_b200/host/overlay/solvers/qp.hpp, plus the batched sibling.
 #include "mini_test.hpp"
 #include "solvers/qp.hpp"
 

@@ -145,3 +145,29 @@ def test_fp32_reuse_factor_hits(api, ctx):
         np.testing.assert_array_equal(reused[k], plain[k], err_msg=k)
     b.close()
     p.close()
+
+
+def test_empty_and_maximum_sizes(api, ctx, oracle):
+    """Edge cases of the boundary: count = 0 is a no-op; the largest shapes of the blocked kernel (256, 1024) and a shape only the generic
+    kernel takes (300, 700); a batch of one; counts smaller than the capacity leave the other instances untouched."""
+    from sqp_solver_b200.synth import make_batch
+
+    d = make_batch(4, 8, 10, seed0=67000)
+    b = api.QPBatch(ctx, 4, 8, 10)
+    b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"], count=0)  # nothing to do, nothing launched
+    assert (b.info()["status"] == api.UNINITIALIZED).all()
+    b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"], count=2)
+    info = b.info()
+    assert (info["status"][:2] != api.UNINITIALIZED).all() and (info["status"][2:] == api.UNINITIALIZED).all()
+    b.close()
+    s = api.default_settings(alpha=1.6, adaptive_rho=1, max_iter=200)
+    for (n, m, batch, expect) in ((256, 1024, 2, "block"), (300, 700, 2, "generic"), (64, 128, 1, "tile"), (1, 0, 1, "small")):
+        d = make_batch(batch, n, m, seed0=68000 + n)
+        b = api.QPBatch(ctx, batch, n, m)
+        b.settings = s
+        b.setup_solve(d["P"], d["q"], d["A"], d["l"], d["u"])
+        assert ctx.last_kernel.startswith(expect), ctx.last_kernel
+        got = b.get()
+        ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
+        assert_parity(got, ref, what="n=%d m=%d (%s)" % (n, m, ctx.last_kernel))
+        b.close()
