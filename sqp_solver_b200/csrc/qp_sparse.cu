@@ -1,8 +1,9 @@
 // Sparse-A input format: the reference's intended sparse variant stores A as an
 // Eigen::SparseMatrix (compressed column storage; include/solvers/qp.hpp:22-25, include/unsupported/qp_solver.hpp:363-394),
 // BASELINE.json config 5 names CSR. Both are accepted here with ONE sparsity pattern shared by the batch (the Jacobian
-// pattern of a batch of same-structure NLPs) and per-instance values. Round 1 densifies on the device and runs the dense
-// kernels: the data format is covered at the boundary with full parity; a kernel that exploits the sparsity is next-round work.
+// pattern of a batch of same-structure NLPs) and per-instance values. This file is the densify step for the shapes whose kernels keep A
+// in registers anyway (n <= 64, m <= 128: thread-per-QP and register-tiled kernels); 64 < n <= 256 stay compressed in the cluster
+// kernel (qp_cluster.cu) or the blocked kernel (qp_block.cu).
 #include "qp_common.cuh"
 
 namespace sqpb200 {
