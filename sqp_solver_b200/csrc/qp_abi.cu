@@ -546,6 +546,15 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
         p.status = ov->status; p.iter = ov->iter; p.rho_updates = ov->rho_updates;
         p.rho_estimate = ov->rho_estimate; p.res_prim = ov->res_prim; p.res_dual = ov->res_dual;
         if (ov_used) *ov_used = true;
+    } else if (ov) {
+        // the other kernels read-modify-write the object's info arrays: make them those of default-constructed solvers
+        // (rho_updates 0, ...; status is overwritten by the factorisation) so that the caller sees per-call values, as documented
+        const size_t B = (size_t)count;
+        CK(c, cudaMemsetAsync(b->rho_updates, 0, B * sizeof(int), stream));
+        CK(c, cudaMemsetAsync(b->iter, 0, B * sizeof(int), stream));
+        CK(c, cudaMemsetAsync(b->rho_estimate, 0, B * sizeof(double), stream));
+        CK(c, cudaMemsetAsync(b->res_prim, 0, B * sizeof(double), stream));
+        CK(c, cudaMemsetAsync(b->res_dual, 0, B * sizeof(double), stream));
     }
     p.mode = mode;
     if (mode & MODE_KEEP_INITIAL) b->keep_kernel = kind;

@@ -171,3 +171,32 @@ def test_empty_and_maximum_sizes(api, ctx, oracle):
         ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"], oracle_settings_from(oracle, s))
         assert_parity(got, ref, what="n=%d m=%d (%s)" % (n, m, ctx.last_kernel))
         b.close()
+
+
+@pytest.mark.parametrize("n,m,expect_direct", [(64, 128, True), (20, 30, True), (2, 3, False), (80, 100, False)])
+def test_setup_solve_to_writes_caller_arrays(api, ctx, oracle, n, m, expect_direct):
+    """sqpb200_qp_batch_setup_solve_to: fused setup + solve of FRESH instances whose results land in caller device arrays -- written by
+    the register-tiled kernel's epilogue, or copied out behind the launch for the other kernels. Repeated calls return per-call info
+    (rho_updates = 1 under the reference defaults), unlike the object API whose counter accumulates (qp.cpp:313)."""
+    import torch
+
+    from sqp_solver_b200.synth import make_batch
+
+    B = 40
+    d = make_batch(B, n, m, seed0=69000 + n)
+    dev = {k: torch.from_numpy(d[k]).cuda() for k in ("P", "q", "A", "l", "u")}
+    out = dict(x=torch.full((B, n), 7.0, dtype=torch.float64, device="cuda"), y=torch.full((B, m), 7.0, dtype=torch.float64, device="cuda"),
+               z=torch.full((B, m), 7.0, dtype=torch.float64, device="cuda"), status=torch.full((B,), 77, dtype=torch.int32, device="cuda"),
+               iter=torch.full((B,), 77, dtype=torch.int32, device="cuda"), rho_updates=torch.full((B,), 77, dtype=torch.int32, device="cuda"),
+               rho_estimate=torch.full((B,), 7.0, dtype=torch.float64, device="cuda"), res_prim=torch.full((B,), 7.0, dtype=torch.float64, device="cuda"),
+               res_dual=torch.full((B,), 7.0, dtype=torch.float64, device="cuda"))
+    b = api.QPBatch(ctx, B, n, m)
+    ref = oracle.solve_batch(d["P"], d["q"], d["A"], d["l"], d["u"])
+    for call in range(2):
+        b.setup_solve_to(dev["P"], dev["q"], dev["A"], dev["l"], dev["u"], out)
+        torch.cuda.synchronize()
+        got = {k: v.cpu().numpy() for k, v in out.items()}
+        assert_parity({k: got[k] for k in ("status", "iter", "rho_updates", "x", "y")}, ref, what="setup_solve_to call %d (%s)" % (call, ctx.last_kernel))
+        np.testing.assert_allclose(got["res_prim"], ref["res_prim"], rtol=1e-4, atol=1e-8)
+    assert ctx.last_kernel.startswith("tile") == expect_direct, ctx.last_kernel
+    b.close()
