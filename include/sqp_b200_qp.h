@@ -93,6 +93,11 @@ typedef enum sqpb200_error {
 #define SQPB200_OPT_CTAS_PER_SM 3  /* 0 = auto */
 #define SQPB200_OPT_TILE_WARPS 4   /* warps per QP of the register-tiled kernel: 0 = default; 4 (default) or 8 for the 64x128 class, 1 (default) or 2 for the 32x64 class (tuning/tests) */
 
+#define SQPB200_OPT_SLICE_ITERS 5  /* time slicing of the register-tiled kernel (n <= 64, m <= 128 class of 64 x 128): a QP is suspended after this
+                                      many ADMM iterations and re-queued, so that a batch of only a few QPs per resident CTA is scheduled in small
+                                      units (strong scaling over several GPUs). -1 = automatic (default: 250 when a launch has fewer than ten QPs
+                                      per CTA slot), 0 = off. Results are bit-identical to an unsliced solve */
+
 typedef struct sqpb200_ctx sqpb200_ctx;           /* one per (host thread, GPU) */
 typedef struct sqpb200_qp_batch sqpb200_qp_batch; /* B solver instances: state x,z,y, info, factor */
 

@@ -21,7 +21,7 @@ SOLVED, MAX_ITER_EXCEEDED, UNSOLVED, NUMERICAL_ISSUES, UNINITIALIZED = range(5) 
 INEQUALITY_CONSTRAINT, EQUALITY_CONSTRAINT, LOOSE_BOUNDS = range(3)  # qp.hpp:134
 STATUS_NAMES = ["SOLVED", "MAX_ITER_EXCEEDED", "UNSOLVED", "NUMERICAL_ISSUES", "UNINITIALIZED"]
 HOST_PTRS, DEVICE_PTRS, HOST_ASYNC = 0, 1, 2
-OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS = 1, 2, 3, 4
+OPT_KERNEL, OPT_H2D_CHUNKS, OPT_CTAS_PER_SM, OPT_TILE_WARPS, OPT_SLICE_ITERS = 1, 2, 3, 4, 5
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILE, KERNEL_BLOCK, KERNEL_CLUSTER, KERNEL_SMALL = 0, 1, 2, 3, 4, 5
 KEEP_FACTOR, REUSE_FACTOR = 1, 2
 SPARSE_CSC, SPARSE_CSR = 0, 1

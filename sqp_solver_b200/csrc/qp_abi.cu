@@ -24,6 +24,7 @@ struct sqpb200_ctx {
     static constexpr int kCounters = 1024;
     long long launches = 0;
     int opt_kernel = 0, opt_chunks = 16, opt_ctas_per_sm = 0, opt_tile_warps = 0;
+    int opt_slice = -1;  // time slicing of the register-tiled kernel: -1 = automatic, 0 = off, > 0 = iterations per slice
     std::string err;
     char last_kernel[64] = "none";
 };
@@ -49,6 +50,8 @@ struct sqpb200_qp_batch {
     cudaEvent_t stage_event = nullptr;
     cudaStream_t last_stream = nullptr;  // stream of the last launch on this object, and an event recorded behind it:
     cudaEvent_t last_event = nullptr;    // get / set_iterates / total_iters on ANOTHER stream wait for it first
+    int *rq = nullptr;  // time slicing: re-queue ring + [rq_cap] = slots handed out, [rq_cap + 1] = QPs finished
+    int rq_cap = 0;
     double *gen_scratch = nullptr;  // generic kernel: per-CTA n*n factorisation workspace (owned by the batch object: launches of
     size_t gen_scratch_bytes = 0;   // different batch objects may overlap on different streams)
     unsigned long long *total_iters = nullptr;
@@ -163,6 +166,10 @@ int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
         case SQPB200_OPT_CTAS_PER_SM:
             if (value < 0 || value > 32) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_CTAS_PER_SM: 0..32");
             c->opt_ctas_per_sm = value;
+            return SQPB200_OK;
+        case SQPB200_OPT_SLICE_ITERS:
+            if (value < -1) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_SLICE_ITERS: -1 (automatic), 0 (off) or iterations per slice");
+            c->opt_slice = value;
             return SQPB200_OK;
         case SQPB200_OPT_TILE_WARPS:
             if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
@@ -298,7 +305,7 @@ int sqpb200_qp_batch_destroy(sqpb200_qp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {b->x, b->y, b->z, b->status, b->iter, b->rho_updates, b->rho_estimate, b->res_prim, b->res_dual,
-                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm, b->sp_pack, b->cl_scratch, b->gen_scratch};
+                    b->rho, b->ctype, b->fact, b->fact_rho, b->total_iters, b->dP, b->dq, b->dA, b->dl, b->du, b->sp_outer, b->sp_inner, b->sp_vals, b->sp2_outer, b->sp2_inner, b->sp2_perm, b->sp_pack, b->cl_scratch, b->gen_scratch, b->rq};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (b->last_event) cudaEventDestroy(b->last_event);
@@ -559,7 +566,46 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     p.mode = mode;
     if (mode & MODE_KEEP_INITIAL) b->keep_kernel = kind;
     if (mode & MODE_STORE_FACTOR) b->fact_kernel = kind;
-    const bool needs_fact = kind == KERNEL_BLOCK || kind == KERNEL_GENERIC ||
+    // Time slicing (register-tiled kernel, fused launches of fresh instances): with only a few QPs per resident CTA -- one batch split
+    // over several GPUs -- whole 500...1001-iteration solves leave a long tail when the queue runs dry (list scheduling: about half a QP
+    // per CTA slot); slices of 250 iterations that re-enter the queue cut it to a fraction. Results are bit-identical to an unsliced solve.
+    int slice = 0;
+    if (kind == KERNEL_TILE && (mode & ~MODE_FRESH) == (MODE_RESET | MODE_FACTOR | MODE_SOLVE) && !ready &&
+        tile_sliceable(b->n, b->m, c->opt_tile_warps, b->f32) && st->max_iter > 0) {
+        const int slots = tile_slots(c->prop.multiProcessorCount);
+        if (c->opt_slice > 0) slice = c->opt_slice;
+        else if (c->opt_slice < 0 && count < 10 * slots && count > slots / 4 && st->max_iter >= 500) slice = 250;
+        if (slice >= st->max_iter) slice = 0;
+    }
+    if (slice > 0) {
+        const int cap = count * ((st->max_iter + slice - 1) / slice + 1);
+        if (cap > b->rq_cap) {
+            CK(c, cudaDeviceSynchronize());
+            if (b->rq) cudaFree(b->rq);
+            b->rq = nullptr;
+            b->rq_cap = 0;
+            cudaError_t ea = cudaMalloc(&b->rq, sizeof(int) * ((size_t)cap + 2));
+            if (ea != cudaSuccess) return fail(c, SQPB200_ERR_NOMEM, "re-queue ring cudaMalloc", ea);
+            b->rq_cap = cap;
+        }
+        CK(c, cudaMemsetAsync(b->rq, 0xff, sizeof(int) * (size_t)b->rq_cap, stream));
+        CK(c, cudaMemsetAsync(b->rq + b->rq_cap, 0, 2 * sizeof(int), stream));
+        p.slice_iters = slice;
+        p.rq = b->rq;
+        p.rq_cap = b->rq_cap;
+        p.rq_alloc = b->rq + b->rq_cap;
+        p.done = b->rq + b->rq_cap + 1;
+        p.sus_x = b->x; p.sus_z = b->z; p.sus_y = b->y;
+        p.sus_status = b->status; p.sus_iter = b->iter; p.sus_rho_updates = b->rho_updates;
+        p.sus_rho_estimate = b->rho_estimate; p.sus_res_prim = b->res_prim; p.sus_res_dual = b->res_dual;
+        if (P != b->dP) {  // inputs that are not the object's own staging copies may live in peer memory: keep local copies for the resumes
+            int rc = ensure_staging(b);
+            if (rc) return rc;
+            p.loc_P = b->dP;
+            p.loc_A = b->dA;
+        }
+    }
+    const bool needs_fact = kind == KERNEL_BLOCK || kind == KERNEL_GENERIC || slice > 0 ||
                             (kind == KERNEL_TILE && (mode & (MODE_STORE_FACTOR | MODE_LOAD_FACTOR | MODE_KEEP_INITIAL | MODE_REUSE)));
     if (needs_fact) {
         int rc = ensure_fact(b, kind == KERNEL_BLOCK ? block_fact_doubles(b->n) : (size_t)b->n * b->n);

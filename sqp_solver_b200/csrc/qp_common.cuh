@@ -77,6 +77,18 @@ struct KernelParams {
     const int *ready;    // optional: number of leading QPs whose inputs have landed in device memory (host-staged calls);
                          // a CTA that draws QP i waits until *ready > i. nullptr: everything is resident
     unsigned long long *total_iters;
+    // Time slicing (register-tiled kernel, fused launches of fresh instances): a QP is suspended after `slice_iters` iterations of one
+    // slice -- x, z, y, info and H^-1 go to the object's arrays -- and re-queued, so that a batch of only a few QPs per resident CTA
+    // (one batch split over 8 GPUs) is list-scheduled in small units instead of whole 500...1001-iteration solves. 0: off.
+    int slice_iters;
+    int *rq;        // re-queue ring: entry e holds the local index of the e-th suspended QP (-1: not published yet)
+    int *rq_alloc;  // ring slots handed out so far
+    int *done;      // QPs of this launch that have finished
+    int rq_cap;
+    double *sus_x, *sus_z, *sus_y;  // suspended state (the batch object's own arrays; the final results go to x, z, y, status, ... above)
+    int *sus_status, *sus_iter, *sus_rho_updates;
+    double *sus_rho_estimate, *sus_res_prim, *sus_res_dual;
+    double *loc_P, *loc_A;  // local copies of P and A for the resumes when the inputs live in another GPU's memory (else nullptr)
     unsigned mode;
     sqpb200_qp_settings s;
     SparseA sp;  // all-zero for dense A

@@ -291,7 +291,40 @@ struct Tile {
 // SWEEP2 selects the elimination variant of the (re)factorisation: two pivots per barrier step (fewer, heavier steps: the
 // better choice when adaptive rho refactors often) or one pivot per step (leaves the compiler the leaner hot loop: the better
 // choice when the launch is iteration-dominated). Measured on config 3: S1 24.6 vs 25.1 ms, S2 5.58 vs 5.32 ms.
-template <class Cfg, bool SWEEP2>
+constexpr int RESUME_FLAG = 1 << 30;
+// Next unit of work of a time-sliced launch (one thread per CTA): a fresh QP while there are any, then suspended QPs from the re-queue
+// ring in the order they were published; -1 once every QP of the launch has finished.
+__device__ __forceinline__ int draw_sliced(const KernelParams &p) {
+    const int v = atomicAdd(p.work_counter, 1);
+    if (v < p.count) {
+        if (p.ready != nullptr) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<const volatile int *>(p.ready) <= v) {
+                __nanosleep(500);
+                if (clock64() - t0 > (1LL << 34)) __trap();
+            }
+            __threadfence();
+        }
+        return v;
+    }
+    const int e = v - p.count;
+    if (e >= p.rq_cap) return -1;
+    const long long t0 = clock64();
+    for (;;) {
+        const int q = *reinterpret_cast<const volatile int *>(p.rq + e);
+        if (q >= 0) {
+            __threadfence();
+            return q | RESUME_FLAG;
+        }
+        if (*reinterpret_cast<const volatile int *>(p.done) >= p.count) return -1;
+        __nanosleep(200);
+        if (clock64() - t0 > (1LL << 35)) __trap();  // ~17 s without any progress: fail instead of hanging
+    }
+}
+
+// SLICED: time-sliced launch (KernelParams::slice_iters > 0); the unsliced instantiation is the one the benchmarks of one GPU run and is
+// untouched by the slicing logic (the kernel sits at the 255-register limit).
+template <class Cfg, bool SWEEP2, bool SLICED = false>
 __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams p) {
     using TL = Tile<Cfg>;
     using S = typename Cfg::S;
@@ -325,32 +358,38 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 
     for (;;) {
         cta_sync<NW>();
-        if (tid == 0) s_qp = draw_qp(p);
+        if (tid == 0) s_qp = SLICED ? draw_sliced(p) : draw_qp(p);
         cta_sync<NW>();
-        const int local = s_qp;
+        // SLICED: a resumed QP continues like a solve() after a stored setup (state and H^-1 from the object's arrays), with the
+        // iteration counter carried on -- the arithmetic sequence is the one of an unsliced solve, bit for bit
+        const bool resumed = SLICED && s_qp >= 0 && (s_qp & RESUME_FLAG) != 0;
+        const int local = SLICED ? (s_qp < 0 ? p.count : (s_qp & ~RESUME_FLAG)) : s_qp;
         if (local >= p.count) break;
         // Only the batch index stays live across the solve; problem pointers are re-derived from the kernel
         // parameters (constant bank) where needed -- the hot loop is register-limited.
         const int bi = p.first + local;
         const size_t b = (size_t)bi;
-#define gP (p.P + (size_t)bi * n * n)
-#define gA (p.A + (size_t)bi * m * n)
+#define PMODE ((SLICED && resumed) ? (unsigned)(MODE_LOAD_FACTOR | MODE_SOLVE) : p.mode)
+#define gP (((SLICED && resumed && p.loc_P) ? p.loc_P : p.P) + (size_t)bi * n * n)
+#define gA (((SLICED && resumed && p.loc_A) ? p.loc_A : p.A) + (size_t)bi * m * n)
 #define gq (p.q + (size_t)bi * n)
 #define gl (p.l + (size_t)bi * m)
 #define gu (p.u + (size_t)bi * m)
+        // where the iterates and the info come from: the caller-visible arrays, or (resumed) the arrays holding suspended state
+#define ST_(field) ((SLICED && resumed) ? p.sus_##field : p.field)
 
-        const bool fresh = (p.mode & MODE_FRESH) != 0;  // default-constructed solvers: the info arrays are write-only
-        int status = fresh ? (int)SQPB200_UNINITIALIZED : p.status[b];
+        const bool fresh = !resumed && (p.mode & MODE_FRESH) != 0;  // default-constructed solvers: the info arrays are write-only
+        int status = fresh ? (int)SQPB200_UNINITIALIZED : ST_(status)[b];
         // rho_estimate / res_prim / res_dual (QPSolverInfo, qp.hpp:76-78) only change at checks: kept in shared memory
         if (tid == 0) {
-            s_info[0] = fresh ? 0.0 : p.rho_estimate[b];
-            s_info[1] = fresh ? 0.0 : p.res_prim[b];
-            s_info[2] = fresh ? 0.0 : p.res_dual[b];
-            s_info[3] = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
-            s_cnt[0] = (fresh ? 0 : p.rho_updates[b]) + ((p.mode & MODE_FACTOR) ? 1 : 0);  // rho_vec_update, qp.cpp:313
+            s_info[0] = fresh ? 0.0 : ST_(rho_estimate)[b];
+            s_info[1] = fresh ? 0.0 : ST_(res_prim)[b];
+            s_info[2] = fresh ? 0.0 : ST_(res_dual)[b];
+            s_info[3] = (PMODE & MODE_FACTOR) ? st.rho : p.rho[b];
+            s_cnt[0] = (fresh ? 0 : ST_(rho_updates)[b]) + ((PMODE & MODE_FACTOR) ? 1 : 0);  // rho_vec_update, qp.cpp:313
         }
-        const S rho0 = (p.mode & MODE_FACTOR) ? st.rho : p.rho[b];
-        const bool reset = (p.mode & MODE_RESET) != 0;
+        const S rho0 = (PMODE & MODE_FACTOR) ? st.rho : p.rho[b];
+        const bool reset = (PMODE & MODE_RESET) != 0;
 
         // ---- per-row state in the owner lanes' registers ----------------------------------------
         S zr[RO], yr[RO], rhor[RO], rinv[RO];
@@ -361,13 +400,13 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             const bool real = i < m;
             const S lo = real ? gl[i] : -INF, up = real ? gu[i] : INF;
             if (row_primary) *reinterpret_cast<V2 *>(sbnd + 2 * i) = mk2(lo, up);
-            zr[t] = (real && !reset) ? p.z[b * m + i] : S(0.0);
-            yr[t] = (real && !reset) ? p.y[b * m + i] : S(0.0);
+            zr[t] = (real && !reset) ? ST_(z)[b * m + i] : S(0.0);
+            yr[t] = (real && !reset) ? ST_(y)[b * m + i] : S(0.0);
             int typ;
-            if (p.mode & MODE_FACTOR) {
+            if (PMODE & MODE_FACTOR) {
                 typ = classify_t<S>(lo, up);
                 if (real) {
-                    if ((p.mode & MODE_REUSE) && p.ctype[b * m + i] != (signed char)typ) same_classes = false;
+                    if ((PMODE & MODE_REUSE) && p.ctype[b * m + i] != (signed char)typ) same_classes = false;
                     if (row_primary) p.ctype[b * m + i] = (signed char)typ;
                 }
             } else {
@@ -378,7 +417,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         }
         if (tid < NP) {
             sq[tid] = tid < n ? gq[tid] : S(0.0);
-            sx[tid] = (tid < n && !reset) ? p.x[b * n + tid] : S(0.0);
+            sx[tid] = (tid < n && !reset) ? ST_(x)[b * n + tid] : S(0.0);
         }
 
         // ---- stage A (zero padded) and pull this lane's tile into registers -----------------------
@@ -648,8 +687,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 a[0][kk] = colp[0];
             }
         }
-        bool do_factor = (p.mode & MODE_FACTOR) != 0, first_factor = true, in_solve = false;
-        if (do_factor && (p.mode & MODE_REUSE)) {
+        if constexpr (SLICED) {
+            // the first slice of a QP whose inputs live in another GPU's memory leaves a local copy of A for the resumes
+            if (!resumed && p.loc_A) {
+                double *dst = p.loc_A + (size_t)bi * m * n;
+                for (int e = tid; e < n * m; e += T) dst[e] = sA[(e % m) + LS * (e / m)];
+            }
+        }
+        bool do_factor = (PMODE & MODE_FACTOR) != 0, first_factor = true, in_solve = false;
+        if (do_factor && (PMODE & MODE_REUSE)) {
             // same P and A as the launch that kept the factor: reuse it where classes and rho are unchanged
             // (duplicate owner lanes read the old classes before the primary wrote the same row: benign, values equal or both differ)
             // (compared in the compute scalar: the fp32 instantiation tags the slab with the rounded rho)
@@ -678,6 +724,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 
         long long executed = 0;
         int iter = 0;
+        int slice_left = SLICED ? p.slice_iters : 0;  // iterations left in this slice
+        bool suspended = false;
         // Outer loop: one (re)factorisation, then ADMM iterations until convergence, max_iter, or the
         // next adaptive-rho refactorisation.  A single factorisation call site keeps the code compact.
         for (;;) {
@@ -690,14 +738,20 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 }
                 cta_sync<NW>();
                 const bool ok = factorize();
+                if constexpr (SLICED) {
+                    if (first_factor && !resumed && p.loc_P) {  // P was just staged: local copy for the resumes
+                        double *dst = p.loc_P + (size_t)bi * n * n;
+                        for (int e = tid; e < n * n; e += T) dst[e] = sP[(e % n) + HS * (e / n)];
+                    }
+                }
                 first_factor = false;
                 do_factor = false;
                 if (!in_solve) {
                     status = ok ? SQPB200_UNSOLVED : SQPB200_NUMERICAL_ISSUES;  // qp.cpp:39-43
                     // A factorisation that is not written to the slab leaves an older kept factor behind whose classes were just
                     // overwritten: forget it (also on failure), or a later REUSE would match the new classes against the old factor.
-                    if (tid == 0 && !(ok && (p.mode & MODE_KEEP_INITIAL))) p.fact_rho[b] = __longlong_as_double(0x7ff8000000000000LL);
-                    if (ok && (p.mode & MODE_KEEP_INITIAL)) {
+                    if (tid == 0 && !(ok && (PMODE & MODE_KEEP_INITIAL))) p.fact_rho[b] = __longlong_as_double(0x7ff8000000000000LL);
+                    if (ok && (PMODE & MODE_KEEP_INITIAL)) {
                         double *gF = p.fact + b * n * n;
 #pragma unroll
                         for (int s = 0; s < HC; ++s) {
@@ -717,9 +771,12 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 }
             }
             if (!in_solve) {
-                if (!((p.mode & MODE_SOLVE) && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES)) break;
+                if (!((PMODE & MODE_SOLVE) && status != SQPB200_UNINITIALIZED && status != SQPB200_NUMERICAL_ISSUES)) break;
                 in_solve = true;
                 iter = 1;
+                if constexpr (SLICED) {
+                    if (resumed) iter = p.sus_iter[b];  // the next iteration of the suspended solve
+                }
             }
             bool refactor = false;
             // iterations until the next termination check / adaptive-rho step (replaces iter % N, qp.cpp:105,125)
@@ -858,18 +915,68 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                         }
                     }
                 }
+                if constexpr (SLICED) {
+                    // end of the slice: suspend after this iteration unless it was the last one anyway
+                    if (--slice_left <= 0 && iter < st.max_iter) {
+                        suspended = true;
+                        ++iter;  // the iteration the resume starts with
+                        break;
+                    }
+                }
             }
             if (!refactor) break;
             ++iter;  // the reference finishes the iteration (loop increment) after refactoring
             do_factor = true;
         }
-        if (in_solve) {
+        if (in_solve && !suspended) {
             executed = iter <= st.max_iter ? iter : st.max_iter;
             if (iter > st.max_iter) status = SQPB200_MAX_ITER_EXCEEDED;  // qp.cpp:147-149
         }
 
         // ---- write back -----------------------------------------------------------------------------
         cta_sync<NW>();
+        if constexpr (SLICED) {
+            if (suspended) {
+                // park the solve: iterates, info and H^-1 into the object's arrays, then publish the QP in the re-queue ring
+                if (tid < n) p.sus_x[b * n + tid] = sx[tid];
+                if (row_primary) {
+#pragma unroll
+                    for (int t = 0; t < RO; ++t) {
+                        const int i = own0 + t;
+                        if (i < m) {
+                            p.sus_z[b * m + i] = zr[t];
+                            p.sus_y[b * m + i] = yr[t];
+                        }
+                    }
+                }
+                double *gF = p.fact + b * n * n;
+#pragma unroll
+                for (int s = 0; s < HC; ++s) {
+                    const int j = cg + CG * s;
+#pragma unroll
+                    for (int r = 0; r < HR; ++r) {
+                        const int i = i0 + r;
+                        if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
+                    }
+                }
+                if (tid == 0) {
+                    p.sus_status[b] = status;
+                    p.sus_iter[b] = iter;
+                    p.sus_rho_updates[b] = s_cnt[0];
+                    p.sus_rho_estimate[b] = s_info[0];
+                    p.sus_res_prim[b] = s_info[1];
+                    p.sus_res_dual[b] = s_info[2];
+                    p.rho[b] = s_info[3];
+                }
+                __threadfence();
+                cta_sync<NW>();
+                if (tid == 0) {
+                    const int e = atomicAdd(p.rq_alloc, 1);
+                    *reinterpret_cast<volatile int *>(p.rq + e) = local;
+                }
+                continue;
+            }
+        }
         if (tid < n) p.x[b * n + tid] = sx[tid];
         if (row_primary) {
 #pragma unroll
@@ -881,7 +988,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 }
             }
         }
-        if ((p.mode & MODE_STORE_FACTOR) && status != SQPB200_NUMERICAL_ISSUES && status != SQPB200_UNINITIALIZED) {
+        if ((PMODE & MODE_STORE_FACTOR) && status != SQPB200_NUMERICAL_ISSUES && status != SQPB200_UNINITIALIZED) {
             double *gF = p.fact + b * n * n;
 #pragma unroll
             for (int s = 0; s < HC; ++s) {
@@ -904,9 +1011,16 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             p.rho[b] = s_info[3];
             if (executed) atomicAdd(p.total_iters, (unsigned long long)executed);
         }
+        if constexpr (SLICED) {  // this QP is finished: the launch ends when all are
+            __threadfence();
+            cta_sync<NW>();
+            if (tid == 0) atomicAdd(p.done, 1);
+        }
     }
 }
 
+#undef PMODE
+#undef ST_
 #undef gP
 #undef gA
 #undef gq
@@ -922,15 +1036,19 @@ using Cfg16x32 = TileCfg<16, 32, 1, 4, 2, 16>;
 using Cfg8x16 = TileCfg<8, 16, 1, 4, 2, 16>;
 // fp32 compute (QPSolver<float>): half the registers and shared memory per QP, so more resident CTAs per SM
 using Cfg64x128w4f = TileCfg<64, 128, 4, 8, 4, 4, float>;
+using Cfg64x128w4f3 = TileCfg<64, 128, 4, 8, 4, 3, float>;  // EXPERIMENT: 168 registers, three CTAs per SM
 using Cfg32x64w1f = TileCfg<32, 64, 1, 4, 4, 16, float>;
 using Cfg16x32f = TileCfg<16, 32, 1, 4, 2, 16, float>;
 using Cfg8x16f = TileCfg<8, 16, 1, 4, 2, 16, float>;
 
 bool tile_supported(int n, int m) { return n >= 1 && m >= 0 && n <= 64 && m <= 128; }
+// time slicing is instantiated for the 64 x 128 class in fp64 with four warps per QP (the headline configuration)
+bool tile_sliceable(int n, int m, int tile_warps, int f32) { return tile_supported(n, m) && (n > 32 || m > 64) && !f32 && tile_warps != 8; }
+int tile_slots(int sm_count) { return 2 * sm_count; }  // resident CTAs of that configuration
 
-template <class Cfg>
+template <class Cfg, bool SLICED = false>
 static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
-    auto kernel = p.s.adaptive_rho ? qp_tile_kernel<Cfg, true> : qp_tile_kernel<Cfg, false>;
+    auto kernel = p.s.adaptive_rho ? qp_tile_kernel<Cfg, true, SLICED> : qp_tile_kernel<Cfg, false, SLICED>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -940,7 +1058,7 @@ static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_
     if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
     long long grid = (long long)sm_count * occ;  // persistent: a multiple of the SM count
     if (grid > p.count) grid = p.count;
-    if (name) snprintf(name, name_len, "tile<%d,%d,%d%s>x%d", Cfg::NP, Cfg::MP, Cfg::NW, Cfg::F64 ? "" : ",f32", occ);  // (the sweep variant is not part of the name)
+    if (name) snprintf(name, name_len, "tile<%d,%d,%d%s>x%d%s", Cfg::NP, Cfg::MP, Cfg::NW, Cfg::F64 ? "" : ",f32", occ, SLICED ? "/sliced" : "");  // (the sweep variant is not part of the name)
     kernel<<<(int)grid, Cfg::T, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
@@ -951,6 +1069,7 @@ cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, in
         if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16f>(p, sm_count, ctas_per_sm, stream, name, name_len);
         if (p.n <= 16 && p.m <= 32) return launch_cfg<Cfg16x32f>(p, sm_count, ctas_per_sm, stream, name, name_len);
         if (p.n <= 32 && p.m <= 64) return launch_cfg<Cfg32x64w1f>(p, sm_count, ctas_per_sm, stream, name, name_len);
+        if (tile_warps == 2) return launch_cfg<Cfg64x128w4f3>(p, sm_count, ctas_per_sm, stream, name, name_len);
         return launch_cfg<Cfg64x128w4f>(p, sm_count, ctas_per_sm, stream, name, name_len);
     }
     if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16>(p, sm_count, ctas_per_sm, stream, name, name_len);
@@ -961,6 +1080,7 @@ cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, in
         return launch_cfg<Cfg32x64w1>(p, sm_count, ctas_per_sm, stream, name, name_len);
     }
     if (tile_warps == 8) return launch_cfg<Cfg64x128w8>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    if (p.slice_iters > 0) return launch_cfg<Cfg64x128w4, true>(p, sm_count, ctas_per_sm, stream, name, name_len);
     return launch_cfg<Cfg64x128w4>(p, sm_count, ctas_per_sm, stream, name, name_len);
 }
 
