@@ -724,8 +724,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 
         long long executed = 0;
         int iter = 0;
-        int slice_left = SLICED ? p.slice_iters : 0;  // iterations left in this slice
         bool suspended = false;
+        int iter_lim = st.max_iter;  // SLICED: last iteration of this slice
         // Outer loop: one (re)factorisation, then ADMM iterations until convergence, max_iter, or the
         // next adaptive-rho refactorisation.  A single factorisation call site keeps the code compact.
         for (;;) {
@@ -776,6 +776,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 iter = 1;
                 if constexpr (SLICED) {
                     if (resumed) iter = p.sus_iter[b];  // the next iteration of the suspended solve
+                    iter_lim = min(st.max_iter, iter + p.slice_iters - 1);
                 }
             }
             bool refactor = false;
@@ -783,7 +784,8 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             int to_chk = st.check_termination > 0 ? st.check_termination - (iter - 1) % st.check_termination : 0x7fffffff;
             int to_adapt = (st.adaptive_rho && st.adaptive_rho_interval > 0)
                                ? st.adaptive_rho_interval - (iter - 1) % st.adaptive_rho_interval : 0x7fffffff;
-            for (; iter <= st.max_iter; ++iter) {
+            bool stopped = false;  // left the loop by a break (converged / refactorisation), not by running into the limit
+            for (; iter <= (SLICED ? iter_lim : st.max_iter); ++iter) {
                 // P1: w = rho .* z - y (owner lanes) -> sw; partial A^T w over this warp's rows -> part[warp]
                 if (row_primary) {
 #pragma unroll
@@ -892,6 +894,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     if (chk) {  // termination_criteria, qp.cpp:363-371
                         if (res_prim <= st.eps_abs + st.eps_rel * sc_p && res_dual <= st.eps_abs + st.eps_rel * sc_d) {
                             status = SQPB200_SOLVED;
+                            stopped = true;
                             break;
                         }
                     }
@@ -911,18 +914,15 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                                 rinv[t] = S(1.0) / rhor[t];
                             }
                             refactor = true;
+                            stopped = true;
                             break;
                         }
                     }
                 }
-                if constexpr (SLICED) {
-                    // end of the slice: suspend after this iteration unless it was the last one anyway
-                    if (--slice_left <= 0 && iter < st.max_iter) {
-                        suspended = true;
-                        ++iter;  // the iteration the resume starts with
-                        break;
-                    }
-                }
+            }
+            if constexpr (SLICED) {
+                // ran into the end of the slice (not of the solve): suspend; `iter` is the iteration the resume starts with
+                if (!stopped && iter <= st.max_iter) suspended = true;
             }
             if (!refactor) break;
             ++iter;  // the reference finishes the iteration (loop increment) after refactoring

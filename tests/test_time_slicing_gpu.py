@@ -68,17 +68,21 @@ def test_sliced_solve_is_bit_identical(api, ctx, n, m, batch, settings_name):
 
 
 def test_automatic_slicing_and_host_pointers(api, ctx):
-    """-1 = automatic: on for a batch of a few QPs per CTA slot, off for a large batch or a tiny one; host-pointer calls (single staging chunk) slice too."""
+    """-1 = automatic: on for a batch of a few QPs per CTA slot (device pointers, or host pointers staged in one piece), off for a large
+    batch, a tiny one, or a host-pointer call whose chunked staging runs behind the kernel."""
     from sqp_solver_b200.synth import make_batch
 
     s = api.default_settings()
     d = make_batch(600, 64, 128, seed0=82000)
     ref = solve(api, ctx, d, s, 0)
-    auto = solve(api, ctx, d, s, -1)
+    auto = solve(api, ctx, d, s, -1, device=True)
     assert auto["kernel"].endswith("/sliced"), auto["kernel"]
+    host = solve(api, ctx, d, s, 250)  # host pointers, chunked staging: unsliced
+    assert "/sliced" not in host["kernel"]
     for k in FIELDS:
         np.testing.assert_array_equal(auto[k], ref[k], err_msg=k)
-    small = solve(api, ctx, make_batch(40, 64, 128, seed0=82100), s, -1)
+        np.testing.assert_array_equal(host[k], ref[k], err_msg=k)
+    small = solve(api, ctx, make_batch(40, 64, 128, seed0=82100), s, -1, device=True)
     assert "/sliced" not in small["kernel"]
 
 
