@@ -574,8 +574,11 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
         tile_sliceable(b->n, b->m, c->opt_tile_warps, b->f32) && st->max_iter > 0) {
         const int slots = tile_slots(c->prop.multiProcessorCount);
         if (c->opt_slice > 0) slice = c->opt_slice;
-        // measured (1 B200, S1): 1024 QPs 3.53 -> 3.42 ms, 2048 QPs 6.54 -> 6.76 ms: worth it below ~4 QPs per CTA slot only
-        else if (c->opt_slice < 0 && count <= 4 * slots && count > slots / 4 && st->max_iter >= 500) slice = 250;
+        // measured (1 B200, S1, inputs in local HBM): 1024 QPs 3.53 -> 3.36 ms, 2048 QPs 6.55 -> 6.64 ms: automatic below ~4 QPs per CTA
+        // slot only. With the inputs in PEER memory and the results written to caller arrays (the 8-GPU flow, 1024 QPs per GPU) it
+        // measured 3.84 against 3.76 ms unsliced -- the local copies of A and P the first slice leaves behind eat the gain -- so the
+        // automatic mode leaves those launches alone.
+        else if (c->opt_slice < 0 && !ov && count <= 4 * slots && count > slots / 4 && st->max_iter >= 500) slice = 250;
         if (slice >= st->max_iter) slice = 0;
     }
     if (slice > 0) {
