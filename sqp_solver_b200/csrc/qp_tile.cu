@@ -1034,9 +1034,9 @@ using Cfg32x64 = TileCfg<32, 64, 2, 4, 2, 8>;      // two warps per QP
 using Cfg32x64w1 = TileCfg<32, 64, 1, 4, 4, 8>;    // ONE warp per QP: no CTA barrier anywhere (BASELINE config 2's mapping)
 using Cfg16x32 = TileCfg<16, 32, 1, 4, 2, 16>;
 using Cfg8x16 = TileCfg<8, 16, 1, 4, 2, 16>;
-// fp32 compute (QPSolver<float>): half the registers and shared memory per QP, so more resident CTAs per SM
+// fp32 compute (QPSolver<float>): half the registers and shared memory per QP, so more resident CTAs per SM. (Four CTAs per SM at 128
+// registers with a few spills and three at 168 registers without any measure the same: 13.36 / 13.43 ms on config 3.)
 using Cfg64x128w4f = TileCfg<64, 128, 4, 8, 4, 4, float>;
-using Cfg64x128w4f3 = TileCfg<64, 128, 4, 8, 4, 3, float>;  // EXPERIMENT: 168 registers, three CTAs per SM
 using Cfg32x64w1f = TileCfg<32, 64, 1, 4, 4, 16, float>;
 using Cfg16x32f = TileCfg<16, 32, 1, 4, 2, 16, float>;
 using Cfg8x16f = TileCfg<8, 16, 1, 4, 2, 16, float>;
@@ -1069,7 +1069,6 @@ cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, in
         if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16f>(p, sm_count, ctas_per_sm, stream, name, name_len);
         if (p.n <= 16 && p.m <= 32) return launch_cfg<Cfg16x32f>(p, sm_count, ctas_per_sm, stream, name, name_len);
         if (p.n <= 32 && p.m <= 64) return launch_cfg<Cfg32x64w1f>(p, sm_count, ctas_per_sm, stream, name, name_len);
-        if (tile_warps == 2) return launch_cfg<Cfg64x128w4f3>(p, sm_count, ctas_per_sm, stream, name, name_len);
         return launch_cfg<Cfg64x128w4f>(p, sm_count, ctas_per_sm, stream, name, name_len);
     }
     if (p.n <= 8 && p.m <= 16) return launch_cfg<Cfg8x16>(p, sm_count, ctas_per_sm, stream, name, name_len);
