@@ -435,7 +435,7 @@ static int ensure_fact(sqpb200_qp_batch *b, size_t doubles_per_qp) {
 static int ensure_staging(sqpb200_qp_batch *b) {
     if (!b->ready_dev) {
         cudaError_t e0 = cudaMalloc(&b->ready_dev, sizeof(int));
-        if (e0 == cudaSuccess) e0 = cudaMallocHost(&b->ready_host, sizeof(int) * 64);
+        if (e0 == cudaSuccess) e0 = cudaMallocHost(&b->ready_host, sizeof(int) * 96);
         if (e0 == cudaSuccess) e0 = cudaEventCreateWithFlags(&b->stage_event, cudaEventDisableTiming);
         if (e0 != cudaSuccess) return fail(b->ctx, SQPB200_ERR_NOMEM, "staging flag allocation", e0);
     }
@@ -652,6 +652,21 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     return SQPB200_OK;
 }
 
+// Chunk boundaries of a staged HOST_PTRS call: equal chunks, preceded by a short geometric ramp (an eighth, a quarter, a half of a wave
+// of resident CTAs, ...) while the ramp stays below the equal chunk size -- the first CTAs of the persistent launch then start after a
+// fraction of a per cent of the transfer instead of after the first sixteenth. bound[0] = 0 < bound[1] < ... < bound[return value] = count.
+static int chunk_bounds(int count, int chunks, int wave, int *bound, int cap) {
+    int nb = 0;
+    bound[nb++] = 0;
+    const int uniform = count / chunks;
+    for (int r = wave / 8 > 0 ? wave / 8 : 1; r < uniform && nb + chunks + 1 < cap; r *= 2) bound[nb++] = r;
+    for (int k = 1; k <= chunks; ++k) {
+        const int hi = (int)((size_t)count * k / chunks);
+        if (hi > bound[nb - 1]) bound[nb++] = hi;
+    }
+    return nb - 1;
+}
+
 static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode, int count, const double *P,
                const double *q, const double *A, const double *l, const double *u, unsigned flags, void *stream_) {
     if (!b) return SQPB200_ERR_INVALID;
@@ -695,9 +710,10 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
     // the compute stream may still be reading the staging buffers from an earlier call; the flag reset must precede the copies
     CK(c, cudaEventRecord(b->stage_event, stream));
     CK(c, cudaStreamWaitEvent(c->copy_stream, b->stage_event, 0));
+    int bound[96];
+    chunks = chunk_bounds(count, chunks, 2 * c->prop.multiProcessorCount, bound, 96);
     for (int k = 0; k < chunks; ++k) {
-        // early chunks are small so the first CTAs start after ~1 % of the transfer
-        size_t lo = (size_t)count * k / chunks, hi = (size_t)count * (k + 1) / chunks, cnt = hi - lo;
+        size_t lo = (size_t)bound[k], hi = (size_t)bound[k + 1], cnt = hi - lo;
         CK(c, cudaMemcpyAsync(b->dP + lo * n * n, P + lo * n * n, cnt * n * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
         CK(c, cudaMemcpyAsync(b->dA + lo * m * n, A + lo * m * n, cnt * m * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
         CK(c, cudaMemcpyAsync(b->dq + lo * n, q + lo * n, cnt * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
@@ -956,8 +972,10 @@ static int run_sparse(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, unsigne
             CK(c, cudaMemsetAsync(b->ready_dev, 0, sizeof(int), stream));
             CK(c, cudaEventRecord(b->stage_event, stream));
             CK(c, cudaStreamWaitEvent(c->copy_stream, b->stage_event, 0));
+            int bound[96];
+            chunks = chunk_bounds(count, chunks, c->prop.multiProcessorCount / 4, bound, 96);  // a wave here: one QP per 4-CTA cluster
             for (int k = 0; k < chunks; ++k) {
-                const size_t lo = (size_t)count * k / chunks, hi = (size_t)count * (k + 1) / chunks;
+                const size_t lo = (size_t)bound[k], hi = (size_t)bound[k + 1];
                 CK(c, copy_instances(c->copy_stream, lo, hi - lo));
                 b->ready_host[k] = (int)hi;
                 CK(c, cudaMemcpyAsync(b->ready_dev, b->ready_host + k, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));

@@ -34,9 +34,11 @@ template <> struct Vec2<float> { using type = float2; };
 __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
 __device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 
-template <int NP_, int MP_, int NW_, int LC_, int HR_, int MINB_, typename S_ = double>
+template <int NP_, int MP_, int NW_, int LC_, int HR_, int MINB_, typename S_ = double, bool SF_ = true>
 struct TileCfg {
     using S = S_;
+    // SF: select-free reduce-scatter trees -- the A and H^-1 tiles sit in the registers in a lane-dependent permutation (HalveSF below)
+    static constexpr bool SF = SF_;
     static constexpr bool F64 = sizeof(S_) == 8;
     static constexpr int NP = NP_, MP = MP_, NW = NW_, LC = LC_, HR = HR_, MINB = MINB_;
     static constexpr int T = 32 * NW;
@@ -168,6 +170,41 @@ __device__ __forceinline__ int halve_base(int lane, bool &primary) {
     }
     return base;
 }
+// Select-free reduce-scatter. A lane that keeps the logical value (slot ^ sf_perm(lane)) in physical slot `slot` holds, at every halving
+// step, the values it must keep in the low half of its slots and the values its partner wants in the high half: v[k] += shfl(v[k + V/2])
+// with no selects (the select form costs 4 FSEL per fp64 value and step, a sixth of the instructions of an ADMM iteration). The sums are
+// formed exactly as in Halve (keep + received), and a lane ends up owning the same logical values. Steps whose halves are smaller than
+// MINHALF values fall back to Halve (MINHALF = 2 keeps adjacent pairs adjacent, so 16-byte loads of the operands stay possible).
+template <int V, int HI, int LO, int MINHALF>
+struct HalveSF {
+    template <typename T>
+    static __device__ __forceinline__ void run(T *v, int lane) {
+        if constexpr (HI >= LO && HI >= 1) {
+            if constexpr (V > 1 && V / 2 >= MINHALF) {
+#pragma unroll
+                for (int k = 0; k < V / 2; ++k) v[k] = v[k] + __shfl_xor_sync(FULL, v[k + V / 2], HI);
+                HalveSF<V / 2, HI / 2, LO, MINHALF>::run(v, lane);
+            } else {
+                Halve<V, HI, LO>::run(v, lane);
+            }
+        }
+    }
+};
+// the permutation that goes with HalveSF<V, HI, LO, MINHALF>: logical index = physical slot ^ sf_perm(lane)
+template <int V, int HI, int LO, int MINHALF>
+__device__ __forceinline__ int sf_perm(int lane) {
+    int perm = 0, v = V;
+#pragma unroll
+    for (int mask = HI; mask >= LO && mask >= 1; mask >>= 1) {
+        if (v > 1 && v / 2 >= MINHALF) {
+            v >>= 1;
+            if (lane & mask) perm += v;
+        } else {
+            break;
+        }
+    }
+    return perm;
+}
 template <class Cfg>
 struct Tile {
     using S = typename Cfg::S;
@@ -179,6 +216,11 @@ struct Tile {
     // column (0..NP) of the kk-th entry of this lane's A tile: interleaved pairs so that the x~ loads
     // of one warp form contiguous 16-byte chunks
     static __device__ __forceinline__ int colA(int lc, int kk) { return 2 * lc + 2 * LC * (kk >> 1) + (kk & 1); }
+    // Register permutations of the select-free trees (0 when Cfg::SF is off): slot (kr, kk) of the A tile holds row (kr ^ px) and
+    // column slot (kk ^ py) of the lane's logical tile, row slot r of the H^-1 tile holds logical row (r ^ ph). px and py are even.
+    static __device__ __forceinline__ int perm_rows(int lane) { return Cfg::SF ? sf_perm<R, LC / 2, 1, 2>(lane) : 0; }
+    static __device__ __forceinline__ int perm_cols(int lane) { return Cfg::SF ? sf_perm<C, 16, LC, 2>(lane) : 0; }
+    static __device__ __forceinline__ int perm_sym(int lane) { return Cfg::SF ? sf_perm<HR, CG / 2, 1, 1>(lane) : 0; }
 
     // ---- z~ = A v (v in shared memory); result: RO fully reduced rows per lane -----------------
     static __device__ __forceinline__ void mv_A(const S (&a)[R][C], const S *sv, int lc, int lane, S (&out)[RO]) {
@@ -187,14 +229,15 @@ struct Tile {
         for (int kr = 0; kr < R; ++kr) acc[kr] = S(0);
 #pragma unroll
         for (int t = 0; t < C / 2; ++t) {
-            const V2 xv = *reinterpret_cast<const V2 *>(sv + 2 * lc + 2 * LC * t);
+            const V2 xv = *reinterpret_cast<const V2 *>(sv + 2 * lc + 2 * LC * (t ^ (perm_cols(lane) >> 1)));
 #pragma unroll
             for (int kr = 0; kr < R; ++kr) {
                 acc[kr] = fma(a[kr][2 * t], xv.x, acc[kr]);
                 acc[kr] = fma(a[kr][2 * t + 1], xv.y, acc[kr]);
             }
         }
-        Halve<R, LC / 2, 1>::run(acc, lane);
+        if constexpr (Cfg::SF) HalveSF<R, LC / 2, 1, 2>::run(acc, lane);
+        else Halve<R, LC / 2, 1>::run(acc, lane);
 #pragma unroll
         for (int t = 0; t < RO; ++t) out[t] = acc[t];
     }
@@ -215,7 +258,7 @@ struct Tile {
             if constexpr (WCH >= 2) {
 #pragma unroll
                 for (int kr = 0; kr < WCH; kr += 2) {
-                    const V2 t2 = *reinterpret_cast<const V2 *>(sw + row0 + h + kr);
+                    const V2 t2 = *reinterpret_cast<const V2 *>(sw + row0 + ((h + kr) ^ perm_rows(lane)));
                     wv[kr] = t2.x;
                     wv[kr + 1] = t2.y;
                 }
@@ -227,7 +270,8 @@ struct Tile {
 #pragma unroll
                 for (int kr = 0; kr < WCH; ++kr) acc[kk] = fma(a[h + kr][kk], wv[kr], acc[kk]);
         }
-        Halve<C, 16, LC>::run(acc, lane);
+        if constexpr (Cfg::SF) HalveSF<C, 16, LC, 2>::run(acc, lane);
+        else Halve<C, 16, LC>::run(acc, lane);
         bool primary;
         const int kb = halve_base<C, 16, LC>(lane, primary);
         if (primary) {
@@ -261,9 +305,30 @@ struct Tile {
 #pragma unroll
             for (int r = 0; r < HR; ++r) acc[r] += acc2[r];
         }
-        Halve<HR, CG / 2, 1>::run(acc, lane);
+        if constexpr (Cfg::SF) HalveSF<HR, CG / 2, 1, 1>::run(acc, lane);
+        else Halve<HR, CG / 2, 1>::run(acc, lane);
         row = HR * rg + halve_base<HR, CG / 2, 1>(lane, primary);
         return acc[0];
+    }
+    // Bring a freshly built H^-1 tile (logical row r in slot r) into the slot order mv_sym_reg expects: slot r <- logical row r ^ ph
+    static __device__ __forceinline__ void permute_sym(S (&hv)[HR][HC], int lane) {
+        if constexpr (Cfg::SF) {
+            const int ph = perm_sym(lane);
+#pragma unroll
+            for (int bit = 1; bit < HR; bit <<= 1) {
+                const bool sw = (ph & bit) != 0;
+#pragma unroll
+                for (int r = 0; r < HR; ++r) {
+                    if (r & bit) continue;
+#pragma unroll
+                    for (int s = 0; s < HC; ++s) {
+                        const S lo = hv[r][s], hi = hv[r | bit][s];
+                        hv[r][s] = sw ? hi : lo;
+                        hv[r | bit][s] = sw ? lo : hi;
+                    }
+                }
+            }
+        }
     }
     // M in shared memory (P at the residual checks): padded column-major, column stride HS
     static __device__ __forceinline__ S mv_sym_smem(const S *sM, const S *sv, int rg, int cg, int lane, int &row,
@@ -664,6 +729,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             for (int s = 0; s < HC; ++s)
 #pragma unroll
                 for (int r = 0; r < HR; ++r) hv[r][s] = -hv[r][s];
+            TL::permute_sym(hv, lane);
             cta_sync<NW>();
             stage(false, true);  // P replaces the staging copy of A
             cta_sync<NW>();
@@ -675,11 +741,11 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
         cta_sync<NW>();
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) {
-            const S *colp = sA + row0 + LS * TL::colA(lc, kk);
+            const S *colp = sA + row0 + LS * TL::colA(lc, kk ^ TL::perm_cols(lane));  // slot (kr, kk) <- logical (kr ^ px, kk ^ py)
             if constexpr (R >= 2) {
 #pragma unroll
                 for (int kr = 0; kr < R; kr += 2) {
-                    const V2 t2 = *reinterpret_cast<const V2 *>(colp + kr);
+                    const V2 t2 = *reinterpret_cast<const V2 *>(colp + (kr ^ TL::perm_rows(lane)));
                     a[kr][kk] = t2.x;
                     a[kr + 1][kk] = t2.y;
                 }
@@ -712,7 +778,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 const int j = cg + CG * s;
 #pragma unroll
                 for (int r = 0; r < HR; ++r) {
-                    const int i = i0 + r;
+                    const int i = i0 + (r ^ TL::perm_sym(lane));
                     hv[r][s] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? S(1.0) : S(0.0));
                 }
             }
@@ -758,7 +824,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                             const int j = cg + CG * s;
 #pragma unroll
                             for (int r = 0; r < HR; ++r) {
-                                const int i = i0 + r;
+                                const int i = i0 + (r ^ TL::perm_sym(lane));
                                 if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
                             }
                         }
@@ -955,7 +1021,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     const int j = cg + CG * s;
 #pragma unroll
                     for (int r = 0; r < HR; ++r) {
-                        const int i = i0 + r;
+                        const int i = i0 + (r ^ TL::perm_sym(lane));
                         if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
                     }
                 }
@@ -995,7 +1061,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 const int j = cg + CG * s;
 #pragma unroll
                 for (int r = 0; r < HR; ++r) {
-                    const int i = i0 + r;
+                    const int i = i0 + (r ^ TL::perm_sym(lane));
                     if (i < n && j < n) gF[i + (size_t)n * j] = hv[r][s];
                 }
             }
@@ -1058,7 +1124,7 @@ static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_
     if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
     long long grid = (long long)sm_count * occ;  // persistent: a multiple of the SM count
     if (grid > p.count) grid = p.count;
-    if (name) snprintf(name, name_len, "tile<%d,%d,%d%s>x%d%s", Cfg::NP, Cfg::MP, Cfg::NW, Cfg::F64 ? "" : ",f32", occ, SLICED ? "/sliced" : "");  // (the sweep variant is not part of the name)
+    if (name) snprintf(name, name_len, "tile<%d,%d,%d%s%s>x%d%s", Cfg::NP, Cfg::MP, Cfg::NW, Cfg::F64 ? "" : ",f32", Cfg::SF ? "" : ",sel", occ, SLICED ? "/sliced" : "");  // (the sweep variant is not part of the name)
     kernel<<<(int)grid, Cfg::T, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
