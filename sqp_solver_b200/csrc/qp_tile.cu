@@ -760,6 +760,11 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 for (int e = tid; e < n * m; e += T) dst[e] = sA[(e % m) + LS * (e / m)];
             }
         }
+        S xown = S(0);  // x entry of the row this lane ends up with after the H^-1 b tree (sx was written before the staging barriers)
+        if constexpr (NW > 1) {
+            bool prim;
+            xown = sx[HR * rg + halve_base<HR, CG / 2, 1>(lane, prim)];
+        }
         bool do_factor = (PMODE & MODE_FACTOR) != 0, first_factor = true, in_solve = false;
         if (do_factor && (PMODE & MODE_REUSE)) {
             // same P and A as the launch that kept the factor: reuse it where classes and rho are unchanged
@@ -877,12 +882,22 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     int row;
                     bool prim;
                     const S xt = TL::mv_sym_reg(hv, sb, rg, cg, lane, row, prim);
-                    if (prim) {
-                        sxt[row] = xt;
-                        sx[row] = alpha * xt + (S(1.0) - alpha) * sx[row];
+                    // the owner lanes carry their x entry in a register: x~ reaches shared memory (and the barrier) straight from the
+                    // tree, the x update and its store (first read by the b stage of the NEXT iteration) leave the critical path
+                    if constexpr (NW > 1) {
+                        if (prim) sxt[row] = xt;
+                        cta_sync<NW>();
+                        // (sx is next read by the b stage of the following iteration, two barriers on; the check block synchronises first)
+                        xown = alpha * xt + (S(1.0) - alpha) * xown;
+                        if (prim) sx[row] = xown;
+                    } else {  // one warp per QP: the "barrier" is a __syncwarp, nothing to hide
+                        if (prim) {
+                            sxt[row] = xt;
+                            sx[row] = alpha * xt + (S(1.0) - alpha) * sx[row];
+                        }
+                        cta_sync<NW>();
                     }
                 }
-                cta_sync<NW>();
                 // P4: z~ = A x~ ; z, y updates in the owner lanes (qp.cpp:93-103)
                 {
                     S zt[RO];
@@ -902,6 +917,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 if (adapt) to_adapt = st.adaptive_rho_interval;
                 if (chk || adapt) {
                     // update_state, qp.cpp:316-331
+                    if constexpr (NW > 1) cta_sync<NW>();  // the x entries stored after the last barrier of the iteration are read below
                     S mx[7] = {0, 0, 0, 0, 0, 0, 0};  // |Ax| |z| |Px| |A^T y| |q| |Ax - z| |Px + q + A^T y|
                     {
                         S ax[RO];  // A x (x, not x~: they differ when alpha != 1), qp.cpp:319
