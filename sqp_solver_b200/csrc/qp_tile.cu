@@ -34,8 +34,11 @@ template <> struct Vec2<float> { using type = float2; };
 __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
 __device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 
-template <int NP_, int MP_, int NW_, int LC_, int HR_, int MINB_, typename S_ = double, bool SF_ = true>
+template <int NP_, int MP_, int NW_, int LC_, int HR_, int MINB_, typename S_ = double, bool SF_ = true, bool SEPP_ = false>
 struct TileCfg {
+    // SEPP: P keeps a shared-memory region of its own next to the staging copy of A (instead of replacing it after every
+    // factorisation): A and P are staged together, a refactorisation reads P_lowsym from shared memory and re-stages A only
+    static constexpr bool SEPP = SEPP_;
     using S = S_;
     // SF: select-free reduce-scatter trees -- the A and H^-1 tiles sit in the registers in a lane-dependent permutation (HalveSF below)
     static constexpr bool SF = SF_;
@@ -67,8 +70,8 @@ struct TileCfg {
     // P*x at the checks) share one region: a second 34 KB region would shrink the L1 that backs the few register
     // spills of the hot loop and measurably slows it (26.7 ms vs 24.9 ms on config 3).
     static_assert(NP * HS <= NP * LS, "P must fit in the A staging region it aliases");
-    static constexpr int OFF_STAGE = 0;
-    static constexpr int OFF_P = OFF_STAGE;
+    static constexpr int OFF_STAGE = SEPP ? NP * HS : 0;
+    static constexpr int OFF_P = 0;
     // Regions that are only live during a (re)factorisation share storage with regions that are only live during iterations:
     // the pivot columns with the per-warp partial sums, the rho vector (SYRK) with w
     static constexpr int PIVS = 2 * NP;  // two pivot columns per elimination step
@@ -528,7 +531,9 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             // padded variables get a unit diagonal block
             auto h_init = [&](int i, int j) -> S {
                 if (i >= n || j >= n) return (i == j) ? S(1.0) : S(0.0);
-                const S v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
+                S v;
+                if constexpr (Cfg::SEPP) v = (i >= j) ? sP[i + HS * j] : sP[j + HS * i];  // P is resident in shared memory
+                else v = (i >= j) ? gP[i + (size_t)n * j] : gP[j + (size_t)n * i];
                 return (i == j) ? v + sigma : v;
             };
             if constexpr (Cfg::DMMA) {
@@ -730,14 +735,16 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #pragma unroll
                 for (int r = 0; r < HR; ++r) hv[r][s] = -hv[r][s];
             TL::permute_sym(hv, lane);
-            cta_sync<NW>();
-            stage(false, true);  // P replaces the staging copy of A
+            if constexpr (!Cfg::SEPP) {
+                cta_sync<NW>();
+                stage(false, true);  // P replaces the staging copy of A
+            }
             cta_sync<NW>();
             return ok;
         };
 
         cta_sync<NW>();
-        stage(true, false);
+        stage(true, Cfg::SEPP);
         cta_sync<NW>();
 #pragma unroll
         for (int kk = 0; kk < C; ++kk) {
@@ -787,10 +794,12 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                     hv[r][s] = (i < n && j < n) ? gF[i + (size_t)n * j] : (i == j ? S(1.0) : S(0.0));
                 }
             }
-            cta_sync<NW>();  // tiles are in registers; the staging area may be overwritten
-            stage(false, true);
-            cta_sync<NW>();
-            first_factor = false;  // the staging copy of A is gone
+            if constexpr (!Cfg::SEPP) {
+                cta_sync<NW>();  // tiles are in registers; the staging area may be overwritten
+                stage(false, true);
+                cta_sync<NW>();
+                first_factor = false;  // the staging copy of A is gone
+            }
         }
 
         long long executed = 0;
@@ -1111,6 +1120,9 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 
 // ---- dispatch ------------------------------------------------------------------------------------
 using Cfg64x128w4 = TileCfg<64, 128, 4, 8, 4, 2>;  // 128 threads: 8x8 A tile + 4x8 H^-1 tile per lane
+// the same with P in a region of its own: adaptive-rho launches (S2 on config 3: 5.11 -> 5.02 ms; without refactorisations the larger
+// shared-memory footprint costs 2 %: 23.04 against 22.56 ms)
+using Cfg64x128w4P = TileCfg<64, 128, 4, 8, 4, 2, double, true, true>;
 using Cfg64x128w8 = TileCfg<64, 128, 8, 8, 2, 2>;  // 256 threads: 4x8 A tile + 2x8 H^-1 tile per lane
 using Cfg32x64 = TileCfg<32, 64, 2, 4, 2, 8>;      // two warps per QP
 using Cfg32x64w1 = TileCfg<32, 64, 1, 4, 4, 8>;    // ONE warp per QP: no CTA barrier anywhere (BASELINE config 2's mapping)
@@ -1128,9 +1140,9 @@ bool tile_supported(int n, int m) { return n >= 1 && m >= 0 && n <= 64 && m <= 1
 bool tile_sliceable(int n, int m, int tile_warps, int f32) { return tile_supported(n, m) && (n > 32 || m > 64) && !f32 && tile_warps != 8; }
 int tile_slots(int sm_count) { return 2 * sm_count; }  // resident CTAs of that configuration
 
-template <class Cfg, bool SLICED = false>
-static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
-    auto kernel = p.s.adaptive_rho ? qp_tile_kernel<Cfg, true, SLICED> : qp_tile_kernel<Cfg, false, SLICED>;
+template <class Cfg, bool SWEEP2, bool SLICED>
+static cudaError_t launch_one(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
+    auto kernel = qp_tile_kernel<Cfg, SWEEP2, SLICED>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -1140,9 +1152,16 @@ static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_
     if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
     long long grid = (long long)sm_count * occ;  // persistent: a multiple of the SM count
     if (grid > p.count) grid = p.count;
-    if (name) snprintf(name, name_len, "tile<%d,%d,%d%s%s>x%d%s", Cfg::NP, Cfg::MP, Cfg::NW, Cfg::F64 ? "" : ",f32", Cfg::SF ? "" : ",sel", occ, SLICED ? "/sliced" : "");  // (the sweep variant is not part of the name)
+    if (name) snprintf(name, name_len, "tile<%d,%d,%d%s%s>x%d%s", Cfg::NP, Cfg::MP, Cfg::NW, Cfg::F64 ? "" : ",f32", Cfg::SEPP ? ",sepP" : "", occ, SLICED ? "/sliced" : "");  // (the sweep variant is not part of the name)
     kernel<<<(int)grid, Cfg::T, Cfg::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
+}
+// CfgA: the configuration of launches with adaptive rho (frequent refactorisations: the rank-2 sweep, and for the headline class P in a
+// shared-memory region of its own); Cfg: iteration-dominated launches
+template <class Cfg, bool SLICED = false, class CfgA = Cfg>
+static cudaError_t launch_cfg(const KernelParams &p, int sm_count, int ctas_per_sm, cudaStream_t stream, char *name, size_t name_len) {
+    if (p.s.adaptive_rho) return launch_one<CfgA, true, SLICED>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    return launch_one<Cfg, false, SLICED>(p, sm_count, ctas_per_sm, stream, name, name_len);
 }
 
 cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, int tile_warps, int f32, cudaStream_t stream, char *name,
@@ -1162,7 +1181,7 @@ cudaError_t launch_tile(const KernelParams &p, int sm_count, int ctas_per_sm, in
     }
     if (tile_warps == 8) return launch_cfg<Cfg64x128w8>(p, sm_count, ctas_per_sm, stream, name, name_len);
     if (p.slice_iters > 0) return launch_cfg<Cfg64x128w4, true>(p, sm_count, ctas_per_sm, stream, name, name_len);
-    return launch_cfg<Cfg64x128w4>(p, sm_count, ctas_per_sm, stream, name, name_len);
+    return launch_cfg<Cfg64x128w4, false, Cfg64x128w4P>(p, sm_count, ctas_per_sm, stream, name, name_len);
 }
 
 }  // namespace sqpb200
