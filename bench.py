@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tile"])
     ap.add_argument("--tile-warps", type=int, default=0, choices=[0, 1, 2, 4, 8])
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--slice-iters", type=int, default=-1, help="time slicing of the register-tiled kernel: -1 automatic, 0 off, else iterations per slice")
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="auto (default): strong when N > 1 -- ONE batch on rank 0 solved by all ranks, the north star's split/gather "
                          "flow -- with the weak figure under extra.weak. weak: every rank solves its own batch and nothing else")
@@ -750,6 +751,7 @@ def main():
         ctx.set_option(api.OPT_KERNEL, {"auto": 0, "generic": 1, "tile": 2}[args.kernel])
         ctx.set_option(api.OPT_TILE_WARPS, args.tile_warps)
         ctx.set_option(api.OPT_CTAS_PER_SM, args.ctas_per_sm)
+        ctx.set_option(api.OPT_SLICE_ITERS, args.slice_iters)
         if world > 1 and args.scaling in ("auto", "strong"):
             run_strong(args, rank, world, local_rank, ctx, api, torch, dist)
             return

@@ -168,7 +168,7 @@ int sqpb200_ctx_set_option(sqpb200_ctx *c, int option, int value) {
             c->opt_ctas_per_sm = value;
             return SQPB200_OK;
         case SQPB200_OPT_SLICE_ITERS:
-            if (value < -1) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_SLICE_ITERS: -1 (automatic), 0 (off) or iterations per slice");
+            if (value < -1) return fail(c, SQPB200_ERR_INVALID, "SQPB200_OPT_SLICE_ITERS: -1 (automatic), 0 (off) or iterations per slice (+ 65536 x iterations of the first slice)");
             c->opt_slice = value;
             return SQPB200_OK;
         case SQPB200_OPT_TILE_WARPS:
@@ -573,13 +573,17 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     if (kind == KERNEL_TILE && (mode & ~MODE_FRESH) == (MODE_RESET | MODE_FACTOR | MODE_SOLVE) && !ready &&
         tile_sliceable(b->n, b->m, c->opt_tile_warps, b->f32) && st->max_iter > 0) {
         const int slots = tile_slots(c->prop.multiProcessorCount);
-        if (c->opt_slice > 0) slice = c->opt_slice;
-        // measured (1 B200, S1, inputs in local HBM): 1024 QPs 3.53 -> 3.36 ms, 2048 QPs 6.55 -> 6.64 ms: automatic below ~4 QPs per CTA
-        // slot only. With the inputs in PEER memory and the results written to caller arrays (the 8-GPU flow, 1024 QPs per GPU) it
-        // measured 3.84 against 3.76 ms unsliced -- the local copies of A and P the first slice leaves behind eat the gain -- so the
-        // automatic mode leaves those launches alone.
-        else if (c->opt_slice < 0 && !ov && count <= 4 * slots && count > slots / 4 && st->max_iter >= 500) slice = 250;
+        int slice_first = 0;
+        if (c->opt_slice > 0) slice = c->opt_slice & 0xffff, slice_first = c->opt_slice >> 16;
+        // measured (1 B200, S1, inputs in local HBM): 1024 QPs 3.25 ms unsliced, 3.14 ms in slices of 250, 3.09 ms with a first slice of
+        // 500 iterations (every solve of this workload needs them anyway) and slices of 125 after it; 2048 QPs 6.03 -> 6.10 ms: automatic
+        // below ~4 QPs per CTA slot only. With the inputs in PEER memory and the results written to caller arrays (the 8-GPU flow, 1024 QPs
+        // per GPU; two GPUs: 3.42 -> 3.33 ms) the first slice leaves local copies of P, A, q, l, u behind, so that a resume reads nothing
+        // over NVLink. (value > 0: iterations per slice + 65536 x iterations of the first slice.)
+        else if (c->opt_slice < 0 && count <= 4 * slots && count > slots / 4 && st->max_iter >= 500)
+            slice = st->max_iter / 8, slice_first = st->max_iter / 2;
         if (slice >= st->max_iter) slice = 0;
+        p.slice_first = slice_first > slice ? slice_first : slice;
     }
     if (slice > 0) {
         const int cap = count * ((st->max_iter + slice - 1) / slice + 1);
@@ -607,6 +611,9 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
             if (rc) return rc;
             p.loc_P = b->dP;
             p.loc_A = b->dA;
+            p.loc_q = b->dq;
+            p.loc_l = b->dl;
+            p.loc_u = b->du;
         }
     }
     const bool needs_fact = kind == KERNEL_BLOCK || kind == KERNEL_GENERIC || slice > 0 ||

@@ -81,6 +81,7 @@ struct KernelParams {
     // slice -- x, z, y, info and H^-1 go to the object's arrays -- and re-queued, so that a batch of only a few QPs per resident CTA
     // (one batch split over 8 GPUs) is list-scheduled in small units instead of whole 500...1001-iteration solves. 0: off.
     int slice_iters;
+    int slice_first;  // length of a QP's FIRST slice (>= slice_iters: every solve needs its first few hundred iterations anyway)
     int *rq;        // re-queue ring: entry e holds the local index of the e-th suspended QP (-1: not published yet)
     int *rq_alloc;  // ring slots handed out so far
     int *done;      // QPs of this launch that have finished
@@ -89,6 +90,7 @@ struct KernelParams {
     int *sus_status, *sus_iter, *sus_rho_updates;
     double *sus_rho_estimate, *sus_res_prim, *sus_res_dual;
     double *loc_P, *loc_A;  // local copies of P and A for the resumes when the inputs live in another GPU's memory (else nullptr)
+    double *loc_q, *loc_l, *loc_u;  // likewise q, l, u (set together with loc_P / loc_A): a resume then touches local memory only
     unsigned mode;
     sqpb200_qp_settings s;
     SparseA sp;  // all-zero for dense A

@@ -440,9 +440,9 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
 #define PMODE ((SLICED && resumed) ? (unsigned)(MODE_LOAD_FACTOR | MODE_SOLVE) : p.mode)
 #define gP (((SLICED && resumed && p.loc_P) ? p.loc_P : p.P) + (size_t)bi * n * n)
 #define gA (((SLICED && resumed && p.loc_A) ? p.loc_A : p.A) + (size_t)bi * m * n)
-#define gq (p.q + (size_t)bi * n)
-#define gl (p.l + (size_t)bi * m)
-#define gu (p.u + (size_t)bi * m)
+#define gq (((SLICED && resumed && p.loc_A) ? p.loc_q : p.q) + (size_t)bi * n)
+#define gl (((SLICED && resumed && p.loc_A) ? p.loc_l : p.l) + (size_t)bi * m)
+#define gu (((SLICED && resumed && p.loc_A) ? p.loc_u : p.u) + (size_t)bi * m)
         // where the iterates and the info come from: the caller-visible arrays, or (resumed) the arrays holding suspended state
 #define ST_(field) ((SLICED && resumed) ? p.sus_##field : p.field)
 
@@ -765,6 +765,18 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
             if (!resumed && p.loc_A) {
                 double *dst = p.loc_A + (size_t)bi * m * n;
                 for (int e = tid; e < n * m; e += T) dst[e] = sA[(e % m) + LS * (e / m)];
+                // q, l, u as well (out of the shared-memory copies made above): a resume then reads nothing over NVLink
+                if (tid < n) p.loc_q[(size_t)bi * n + tid] = sq[tid];
+                if (row_primary) {
+#pragma unroll
+                    for (int t = 0; t < RO; ++t) {
+                        const int i = own0 + t;
+                        if (i < m) {
+                            p.loc_l[(size_t)bi * m + i] = sbnd[2 * i];
+                            p.loc_u[(size_t)bi * m + i] = sbnd[2 * i + 1];
+                        }
+                    }
+                }
             }
         }
         S xown = S(0);  // x entry of the row this lane ends up with after the H^-1 b tree (sx was written before the staging barriers)
@@ -856,7 +868,7 @@ __global__ void __launch_bounds__(Cfg::T, Cfg::MINB) qp_tile_kernel(KernelParams
                 iter = 1;
                 if constexpr (SLICED) {
                     if (resumed) iter = p.sus_iter[b];  // the next iteration of the suspended solve
-                    iter_lim = min(st.max_iter, iter + p.slice_iters - 1);
+                    iter_lim = min(st.max_iter, iter + (resumed ? p.slice_iters : p.slice_first) - 1);
                 }
             }
             bool refactor = false;

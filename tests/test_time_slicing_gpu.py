@@ -54,11 +54,11 @@ def test_sliced_solve_is_bit_identical(api, ctx, n, m, batch, settings_name):
                                      adaptive_rho_tolerance=2.0)}[settings_name]
     ref = solve(api, ctx, d, s, 0, device=True)
     assert "/sliced" not in ref["kernel"]
-    for sl in (250, 100, 37, 1):
+    for sl in (250, 100, 37, 1, 150 * 65536 + 40):  # the last: a first slice of 150 iterations, then slices of 40
         if sl == 1 and batch > 200:
             continue  # one iteration per slice: a stress test of the queue, kept to the small batch
         got = solve(api, ctx, d, s, sl, device=True)
-        if sl < s.max_iter:
+        if (sl & 0xffff) < s.max_iter:
             assert got["kernel"].endswith("/sliced"), got["kernel"]
         for k in FIELDS:
             a, b_ = got[k], ref[k]
