@@ -659,14 +659,19 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
     return SQPB200_OK;
 }
 
-// Chunk boundaries of a staged HOST_PTRS call: equal chunks, preceded by a short geometric ramp (an eighth, a quarter, a half of a wave
-// of resident CTAs, ...) while the ramp stays below the equal chunk size -- the first CTAs of the persistent launch then start after a
-// fraction of a per cent of the transfer instead of after the first sixteenth. bound[0] = 0 < bound[1] < ... < bound[return value] = count.
+// Chunk boundaries of a staged HOST_PTRS call. The transfer delivers QPs only ~1.5x faster than the resident CTAs consume them, so for
+// the first few waves every CTA that finishes a QP is waiting for the next flag: a geometric ramp (an eighth, a quarter, a half of a wave
+// of resident CTAs, a wave), then half-wave steps for eight waves, and only then the equal chunks (count / chunks) that keep the number
+// of copy calls down. bound[0] = 0 < bound[1] < ... < bound[return value] = count; at most cap - 1 chunks.
 static int chunk_bounds(int count, int chunks, int wave, int *bound, int cap) {
     int nb = 0;
     bound[nb++] = 0;
-    const int uniform = count / chunks;
-    for (int r = wave / 8 > 0 ? wave / 8 : 1; r < uniform && nb + chunks + 1 < cap; r *= 2) bound[nb++] = r;
+    const int uniform = count / chunks > 0 ? count / chunks : 1;
+    const int room = cap - chunks - 2;  // entries the fine-grained prefix may use
+    int r = wave / 8 > 0 ? wave / 8 : 1;
+    for (; r < wave && r < uniform && nb < room; r *= 2) bound[nb++] = r;
+    const int half = wave / 2 > 0 ? wave / 2 : 1;
+    for (r = wave; half < uniform && r < 8 * wave && r < count && nb < room; r += half) bound[nb++] = r;
     for (int k = 1; k <= chunks; ++k) {
         const int hi = (int)((size_t)count * k / chunks);
         if (hi > bound[nb - 1]) bound[nb++] = hi;

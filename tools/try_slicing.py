@@ -9,7 +9,7 @@ from sqp_solver_b200 import api  # noqa: E402
 from sqp_solver_b200.synth import make_batch  # noqa: E402
 
 ctx = api.Context(0)
-data = {B: make_batch(B, 64, 128, seed0=0) for B in (1024, 2048)}
+data = {B: make_batch(B, 64, 128, seed0=0) for B in (1024, 2048, 4096)}
 for sl in [int(a) for a in sys.argv[1:]] or [0, 250, 125]:
     ctx.set_option(api.OPT_SLICE_ITERS, sl)
     for B, d in data.items():
