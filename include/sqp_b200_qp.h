@@ -96,7 +96,7 @@ typedef enum sqpb200_error {
 #define SQPB200_OPT_SLICE_ITERS 5  /* time slicing of the register-tiled kernel (n <= 64, m <= 128 class of 64 x 128): a QP is suspended after this
                                       many ADMM iterations and re-queued, so that a batch of only a few QPs per resident CTA is scheduled in small
                                       units (strong scaling over several GPUs). -1 = automatic (default: a first slice of max_iter / 2 and slices
-                                      of max_iter / 8 after it when a launch has at most four QPs per CTA slot), 0 = off; value > 0: iterations per
+                                      of max_iter / 8 after it when a launch on local data has at most four QPs per CTA slot), 0 = off; value > 0: iterations per
                                       slice, + 65536 x the length of a QP's first slice if that is to be longer. Results are bit-identical to an
                                       unsliced solve */
 

@@ -577,10 +577,12 @@ static int launch_range(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsi
         if (c->opt_slice > 0) slice = c->opt_slice & 0xffff, slice_first = c->opt_slice >> 16;
         // measured (1 B200, S1, inputs in local HBM): 1024 QPs 3.25 ms unsliced, 3.14 ms in slices of 250, 3.09 ms with a first slice of
         // 500 iterations (every solve of this workload needs them anyway) and slices of 125 after it; 2048 QPs 6.03 -> 6.10 ms: automatic
-        // below ~4 QPs per CTA slot only. With the inputs in PEER memory and the results written to caller arrays (the 8-GPU flow, 1024 QPs
-        // per GPU; two GPUs: 3.42 -> 3.33 ms) the first slice leaves local copies of P, A, q, l, u behind, so that a resume reads nothing
-        // over NVLink. (value > 0: iterations per slice + 65536 x iterations of the first slice.)
-        else if (c->opt_slice < 0 && count <= 4 * slots && count > slots / 4 && st->max_iter >= 500)
+        // below ~4 QPs per CTA slot only. With the inputs in PEER memory and the results written to caller arrays (the multi-GPU flow,
+        // 1024 QPs per GPU; the first slice leaves local copies of P, A, q, l, u behind so that a resume reads nothing over NVLink) it
+        // gains with one remote GPU (two GPUs: 3.41 -> 3.24 ms) but loses with seven of them pulling from the owner (eight GPUs: 3.47 ->
+        // 3.54 ... 3.62 ms: all first slices, and with them all transfers, crowd into the first half of the launch), so the automatic mode
+        // leaves those launches alone. (value > 0: iterations per slice + 65536 x iterations of the first slice.)
+        else if (c->opt_slice < 0 && !ov && count <= 4 * slots && count > slots / 4 && st->max_iter >= 500)
             slice = st->max_iter / 8, slice_first = st->max_iter / 2;
         if (slice >= st->max_iter) slice = 0;
         p.slice_first = slice_first > slice ? slice_first : slice;
