@@ -126,6 +126,12 @@ void sqpb200_qp_default_settings(sqpb200_qp_settings *s);
 /* host-side, no GPU: static QPSolver::constr_type_init (qp.cpp:283-294) */
 int sqpb200_constr_type_init(const double *l, const double *u, int m, int *constr_type);
 
+/* host-side, no GPU: the chunk boundaries a staged HOST_PTRS call of `count` instances uses (SQPB200_OPT_H2D_CHUNKS = `chunks`, `wave` =
+ * resident CTAs of the kernel): bound[0] = 0 < bound[1] < ... < bound[return value] = count, a geometric ramp and half-wave steps first
+ * (the first CTAs start after a fraction of a per cent of the transfer), equal chunks after eight waves; -1 on invalid arguments
+ * (cap must be at least chunks + 3). Exposed for the tests. */
+int sqpb200_staging_chunk_bounds(int count, int chunks, int wave, int *bound, int cap);
+
 /* ---- batched solver object ---------------------------------------------------------------- */
 /* `batch` is the capacity; every call below processes the first `count` instances. A new batch
  * object is B default-constructed solvers: status UNINITIALIZED, iter 0, rho_updates 0 (qp.hpp:72-79). */

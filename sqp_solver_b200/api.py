@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "sqpb200_ipc_export", "sqpb200_ipc_import", "sqpb200_ipc_release", "sqpb200_qp_batch_get",
     "sqpb200_qp_batch_set_iterates", "sqpb200_qp_batch_device_view", "sqpb200_qp_batch_total_iters",
     "sqpb200_qp_solve_batch", "sqpb200_measure_fp64_peak", "sqpb200_qp_batch_setup_solve_to", "sqpb200_host_alloc", "sqpb200_host_free", "sqpb200_stream_create", "sqpb200_stream_destroy", "sqpb200_stream_sync", "sqpb200_qp_batch_setup_sparse",
-    "sqpb200_qp_batch_update_qp_sparse", "sqpb200_qp_batch_solve_sparse",
+    "sqpb200_qp_batch_update_qp_sparse", "sqpb200_qp_batch_solve_sparse", "sqpb200_staging_chunk_bounds",
 ]
 
 

@@ -751,6 +751,12 @@ static int run(sqpb200_qp_batch *b, const sqpb200_qp_settings *st, unsigned mode
 
 extern "C" {
 
+int sqpb200_staging_chunk_bounds(int count, int chunks, int wave, int *bound, int cap) {
+    if (count < 1 || chunks < 1 || wave < 1 || !bound || cap < chunks + 3) return -1;
+    if (chunks > count) chunks = count;
+    return chunk_bounds(count, chunks, wave, bound, cap);
+}
+
 int sqpb200_qp_batch_setup(sqpb200_qp_batch *b, const sqpb200_qp_settings *s, int count, const double *P, const double *q,
                            const double *A, const double *l, const double *u, unsigned flags, void *stream) {
     int rc = run(b, s, MODE_RESET | MODE_FACTOR | MODE_STORE_FACTOR, count, P, q, A, l, u, flags, stream);

@@ -57,6 +57,31 @@ def test_constr_type_init_host(api, golden, oracle):  # tests/qp_solver_test.cpp
     np.testing.assert_array_equal(api.constr_type_init(l, u), oracle.QPSolver.constr_type_init(l, u))
 
 
+def test_staging_chunk_bounds(api):
+    """The chunk schedule of a staged HOST_PTRS call (host-side logic, no GPU): strictly increasing boundaries from 0 to count, a fine
+    prefix (the first CTAs of the persistent launch start after a fraction of a per cent of the transfer), never more flags than fit."""
+    import ctypes as C
+
+    L = api.load_library()
+    L.sqpb200_staging_chunk_bounds.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.sqpb200_staging_chunk_bounds.restype = C.c_int
+    cap = 96
+    buf = (C.c_int * cap)()
+    rng = np.random.default_rng(5)
+    cases = [(8192, 16, 296), (8192, 64, 296), (1024, 16, 296), (100, 16, 296), (2048, 16, 37), (5, 5, 296), (1, 1, 1), (700, 7, 296)]
+    cases += [(int(rng.integers(1, 20000)), int(rng.integers(1, 65)), int(rng.integers(1, 600))) for _ in range(300)]
+    for count, chunks, wave in cases:
+        nb = L.sqpb200_staging_chunk_bounds(count, chunks, wave, buf, cap)
+        assert 1 <= nb <= cap - 1, (count, chunks, wave, nb)
+        b = np.array(buf[:nb + 1])
+        assert b[0] == 0 and b[-1] == count and (np.diff(b) > 0).all(), (count, chunks, wave, b)
+        assert np.diff(b).max() <= max(-(-count // min(chunks, count)), 1), (count, chunks, wave, b)  # never coarser than equal chunks
+    nb = L.sqpb200_staging_chunk_bounds(8192, 16, 296, buf, cap)
+    b = np.array(buf[:nb + 1])
+    assert b[1] <= 296 // 8 and (np.diff(b[b <= 8 * 296]) <= 296 // 2).all()  # ramp, then half-wave steps for eight waves
+    assert L.sqpb200_staging_chunk_bounds(0, 16, 296, buf, cap) < 0 and L.sqpb200_staging_chunk_bounds(100, 64, 296, buf, 10) < 0
+
+
 def test_no_cpu_fallback(api):
     import torch
 
