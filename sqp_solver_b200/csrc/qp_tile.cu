@@ -5,7 +5,9 @@
 //     owns an R x C tile (R rows, C interleaved column pairs).  Both per-iteration mat-vecs,
 //     g = A^T w (reduce over rows) and z~ = A x~ (reduce over columns), run from registers;
 //     partial sums are combined with warp-shuffle reduce-scatter trees, so after A x~ each row's
-//     z, y, l, u, rho live in the registers of the lane that owns the row.
+//     z, y, l, u, rho live in the registers of the lane that owns the row. The trees are select-free:
+//     the tiles sit in the registers in a lane-dependent permutation (HalveSF / sf_perm below), so a
+//     tree step is v[k] += shfl_xor(v[k + V/2]) with no send/keep selects.
 //   * H^-1 = (P_sym + sigma I + A^T diag(rho) A)^-1 lives in REGISTERS too (HR x HC entries per
 //     lane); x~ = H^-1 b is one dense symmetric mat-vec with a short shuffle tree.  (The first
 //     version kept H^-1 in shared memory; ncu showed the LSU/shared pipe, not fp64, was the bound --
@@ -67,8 +69,8 @@ struct TileCfg {
     static constexpr int IB = DMMA ? NP / (8 * NW) : 1, JB = NP / 8;
     // shared memory carve-up (doubles)
     // The padded staging copy of A (needed only while H is formed) and the padded copy of P (needed afterwards, for
-    // P*x at the checks) share one region: a second 34 KB region would shrink the L1 that backs the few register
-    // spills of the hot loop and measurably slows it (26.7 ms vs 24.9 ms on config 3).
+    // P*x at the checks) share one region unless SEPP: a second 34 KB region measurably slows iteration-dominated launches
+    // (round 1: 26.7 vs 24.9 ms on config 3; round 2: 23.04 vs 22.56 ms), while launches that refactor often win by it.
     static_assert(NP * HS <= NP * LS, "P must fit in the A staging region it aliases");
     static constexpr int OFF_STAGE = SEPP ? NP * HS : 0;
     static constexpr int OFF_P = 0;
