@@ -136,6 +136,24 @@ __device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p
     return (a0 + a1) + (a2 + a3);
 }
 
+// the same dot product over the ELL copy of a thread's entries: slot k of thread t at [k * CT + t]; `trips` groups of 4 slots
+__device__ __forceinline__ double ell_dot(const double *ev, const int *ei, int trips, const double *vec, int tid) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    ev += tid;
+    ei += tid;
+    for (int g = 0; g < trips; ++g) {
+        const int j0 = ei[0], j1 = ei[CT], j2 = ei[2 * CT], j3 = ei[3 * CT];
+        const double v0 = ev[0], v1 = ev[CT], v2 = ev[2 * CT], v3 = ev[3 * CT];
+        a0 = fma(v0, vec[j0], a0);
+        a1 = fma(v1, vec[j1], a1);
+        a2 = fma(v2, vec[j2], a2);
+        a3 = fma(v3, vec[j3], a3);
+        ev += 4 * CT;
+        ei += 4 * CT;
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
 // FUSED: the launch is setup + solve of fresh instances (MODE_RESET | MODE_FACTOR | MODE_SOLVE, the hot path): the mode tests fold away at
 // compile time and the kernel is the round-1 one, free of spills at its 255 registers. !FUSED: the object API's separate launches.
 template <int CS, bool FUSED>
@@ -182,6 +200,40 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
     }
     double *scr_base = scratch + (size_t)cid * cluster_scratch_doubles();
 
+    // ---- ELL copies of the two per-iteration sparse dot products --------------------------------------------------------------
+    // The compressed views the factorisation works on make poor operands for the iteration: a thread walks its few entries through
+    // three dependent shared-memory loads each (packed index -> value, vector operand), and neighbouring threads start 4-8 words apart
+    // (4- to 8-way bank conflicts on the first two). While no factorisation is running, the aliased region X therefore holds the
+    // entries thread by thread instead: entry k of thread t at [k * CT + t] (value and inner index in separate arrays), conflict-free
+    // and with no index -> value dependency. Same entries per thread, same order, same accumulators as packed_dot: identical sums.
+    // The split of a row / column over its threads is a property of the batch-shared pattern: computed once per launch.
+    const int TPC = CT / RS, bcol = tid / TPC, bpart = tid % TPC;
+    int ell_rlo = 0, ell_rcnt = 0, ell_clo = 0, ell_ccnt = 0;
+    if (has_row) {  // the TPR threads of a row split its entries; the first part is a multiple of 4 entries
+        const int p0 = __ldg(sp.row_outer + my_row), p1 = __ldg(sp.row_outer + my_row + 1);
+        const int pm = TPR == 2 ? p0 + (((p1 - p0 + 1) / 2 + 3) & ~3) : p1;
+        ell_rlo = row_half == 0 ? p0 : min(pm, p1);
+        ell_rcnt = (row_half == 0 ? min(pm, p1) : p1) - ell_rlo;
+    }
+    {
+        const int p0 = __ldg(sp.col_outer + min(n, RS * rank + bcol)), p1 = __ldg(sp.col_outer + min(n, RS * rank + bcol + 1));
+        const int chunk = (((p1 - p0) + TPC - 1) / TPC + 3) & ~3;
+        ell_clo = min(p0 + bpart * chunk, p1);
+        ell_ccnt = min(ell_clo + chunk, p1) - ell_clo;
+    }
+    __shared__ int s_ellk[2];
+    if (tid < 2) s_ellk[tid] = 0;
+    __syncthreads();
+    atomicMax(&s_ellk[0], ell_rcnt);
+    atomicMax(&s_ellk[1], ell_ccnt);
+    __syncthreads();
+    const int KR = (s_ellk[0] + 3) & ~3, KC = (s_ellk[1] + 3) & ~3;  // slots per thread (CTA-wide maxima, multiples of 4)
+    const bool use_ell = (size_t)(KR + KC) * CT * 12 <= sizeof(double) * cluster_x_doubles(np, m, nnz, ccap, CS);
+    double *ellv_r = s.X, *ellv_c = s.X + (size_t)KR * CT;
+    int *elli_r = reinterpret_cast<int *>(ellv_c + (size_t)KC * CT), *elli_c = elli_r + (size_t)KR * CT;
+    // loop trips of 4 entries: uniform per warp (the padding slots hold value 0)
+    const int trips_r = (__reduce_max_sync(0xffffffffu, ell_rcnt) + 3) >> 2, trips_c = (__reduce_max_sync(0xffffffffu, ell_ccnt) + 3) >> 2;
+
 #ifdef SQPB200_CLUSTER_TIMING
     long long tph[16] = {0}, tlast = 0;
 #endif
@@ -227,11 +279,48 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             for (int j = tid; j <= RS; j += CT) couter[j] = __ldg(sp.col_outer + min(n, RS * rank + j)) - cb;
             for (int i = tid; i <= m; i += CT) router[i] = __ldg(sp.row_outer + i);
         };
+        // the ELL copies (see the kernel prologue): slot k of this thread <- its k-th entry of the row / column view, zero-padded
+        // (a padding slot repeats the thread's first inner index, so that it multiplies 0 with an operand the dot product reads anyway)
+        auto stage_ell = [&]() {
+            {
+                const int jpad = ell_rcnt > 0 ? (int)(__ldg(sp.row_pack + ell_rlo) & PACK_MASK) : 0;
+#pragma unroll 4
+                for (int k = 0; k < KR; ++k) {
+                    double v = 0.0;
+                    int j = jpad;
+                    if (k < ell_rcnt) {
+                        const unsigned e = __ldg(sp.row_pack + ell_rlo + k);
+                        v = __ldg(gvals + (e >> PACK_BITS));
+                        j = (int)(e & PACK_MASK);
+                    }
+                    ellv_r[k * CT + tid] = v;
+                    elli_r[k * CT + tid] = j;
+                }
+            }
+            {
+                const int jpad = ell_ccnt > 0 ? (int)(__ldg(sp.col_pack + ell_clo) & PACK_MASK) : 0;
+#pragma unroll 4
+                for (int k = 0; k < KC; ++k) {
+                    double v = 0.0;
+                    int j = jpad;
+                    if (k < ell_ccnt) {
+                        const unsigned e = __ldg(sp.col_pack + ell_clo + k);
+                        v = __ldg(gvals + (e >> PACK_BITS));
+                        j = (int)(e & PACK_MASK);
+                    }
+                    ellv_c[k * CT + tid] = v;
+                    elli_c[k * CT + tid] = j;
+                }
+            }
+        };
+        bool ell_live = false;  // X holds the ELL copies (the compressed views must be restaged before a factorisation)
         stage_sparse();
         // (A v)_i for the owned row of this thread: the TPR threads of a row split its entries and add the halves
         auto own_rowdot = [&](const double *vec) -> double {
             double acc = 0.0;
-            if (has_row) {
+            if (use_ell) {
+                acc = ell_dot(ellv_r, elli_r, trips_r, vec, tid);  // (threads without a row hold zero slots)
+            } else if (has_row) {
                 const int p0 = router[my_row], p1 = router[my_row + 1];
                 const int pm = TPR == 2 ? p0 + (((p1 - p0 + 1) / 2 + 3) & ~3) : p1;  // first half: a multiple of 4 entries
                 const int lo_ = row_half == 0 ? p0 : min(pm, p1), hi_ = row_half == 0 ? min(pm, p1) : p1;
@@ -267,6 +356,12 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
 #ifdef SQPB200_CLUSTER_TIMING
             tlast = clock64();
 #endif
+            if (ell_live) {  // refactorisation: the compressed views come back first
+                __syncthreads();
+                stage_sparse();
+                __syncthreads();
+                ell_live = false;
+            }
             // rho of every row (form H touches all rows of a column): recomputed from the bounds, as classified at setup
             for (int i = tid; i < m; i += CT) s.sw[i] = rho_of(row_type(i), rho);
             // P_lowsym + sigma I (LDLT<Lower> reads the lower triangle only); padded variables get a unit diagonal
@@ -560,9 +655,14 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 TCK(4)
             }
             TCK(5)
-            // the instance's sparse data comes back into the aliased region
+            // the instance's sparse data comes back into the aliased region: as ELL copies for the iterations when they fit
             __syncthreads();
-            stage_sparse();
+            if (use_ell) {
+                stage_ell();
+                ell_live = true;
+            } else {
+                stage_sparse();
+            }
             __syncthreads();
             TCK(6)
             return ok;
@@ -589,12 +689,16 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
             }
         };
         // b (own slice) = sigma x - q + A^T w for the own columns: TPC threads per column split its stored entries
-        const int TPC = CT / RS, bcol = tid / TPC, bpart = tid % TPC;
         auto own_coldot = [&](const double *vec) -> double {
-            const int p0 = couter[bcol], p1 = couter[bcol + 1];
-            const int chunk = (((p1 - p0) + TPC - 1) / TPC + 3) & ~3;
-            const int lo_ = min(p0 + bpart * chunk, p1), hi_ = min(lo_ + chunk, p1);
-            double acc = packed_dot(cpack, lo_, hi_, vals, vec, dummy);
+            double acc;
+            if (use_ell) {
+                acc = ell_dot(ellv_c, elli_c, trips_c, vec, tid);
+            } else {
+                const int p0 = couter[bcol], p1 = couter[bcol + 1];
+                const int chunk = (((p1 - p0) + TPC - 1) / TPC + 3) & ~3;
+                const int lo_ = min(p0 + bpart * chunk, p1), hi_ = min(lo_ + chunk, p1);
+                acc = packed_dot(cpack, lo_, hi_, vals, vec, dummy);
+            }
             for (int o = 1; o < TPC; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             return acc;
         };
@@ -706,12 +810,17 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                         s.xp[kg * RS + r] = acc;
                     }
                     cluster.sync();
+                    if (use_ell) {  // A^T y of the own columns through the column dot of the iteration (s.sb is free here)
+                        const double g = own_coldot(s.sw);
+                        if (bpart == 0) s.sb[bcol] = g;
+                        __syncthreads();
+                    }
                     if (tid < RS) {
                         const int KG = CT / RS, j = RS * rank + tid;
                         if (j < n) {
                             double px = 0.0;
                             for (int g = 0; g < KG; ++g) px += s.xp[g * RS + tid];
-                            const double aty = packed_dot(cpack, couter[tid], couter[tid + 1], vals, s.sw, dummy);
+                            const double aty = use_ell ? s.sb[tid] : packed_dot(cpack, couter[tid], couter[tid + 1], vals, s.sw, dummy);
                             const double qv = s.sq[j];
                             mx[2] = fabs(px);
                             mx[3] = fabs(aty);
