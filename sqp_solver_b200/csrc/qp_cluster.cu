@@ -136,6 +136,43 @@ __device__ __forceinline__ double packed_dot(const unsigned *pack, int p0, int p
     return (a0 + a1) + (a2 + a3);
 }
 
+// ---- per-iteration exchanges without a cluster barrier: st.async into the peers' shared memory, completion counted on THEIR mbarrier ----
+// (cluster.sync costs ~400-900 cycles per use here: barrier.cluster with release/acquire semantics plus the wait for the slowest CTA;
+// the consumer of an all-gather only needs the bytes to have landed)
+__device__ __forceinline__ unsigned cl_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cl_mapa(unsigned local_addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cl_st_async(unsigned remote_addr, double v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote_addr), "d"(v), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void cl_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_arm(unsigned bar, unsigned bytes) {  // the one arrival of a phase + its transaction bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_wait(unsigned bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > (1LL << 32)) __trap();  // ~2 s: a lost transfer must not hang the device
+    }
+}
+
 // the same dot product over the ELL copy of a thread's entries: slot k of thread t at [k * CT + t]; `trips` groups of 4 slots
 __device__ __forceinline__ double ell_dot(const double *ev, const int *ei, int trips, const double *vec, int tid) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -220,6 +257,14 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
         const int chunk = (((p1 - p0) + TPC - 1) / TPC + 3) & ~3;
         ell_clo = min(p0 + bpart * chunk, p1);
         ell_ccnt = min(ell_clo + chunk, p1) - ell_clo;
+    }
+    __shared__ __align__(8) unsigned long long s_xbar[2];  // mbarriers of the two per-iteration exchanges (w all-gather, x~ partials)
+    const unsigned barA = cl_smem_u32(&s_xbar[0]), barB = cl_smem_u32(&s_xbar[1]);
+    unsigned parA = 0, parB = 0;  // phase parity of the next use (every CTA of the cluster runs the same sequence of exchanges)
+    if (tid == 0) {
+        cl_mbar_init(barA, 1);
+        cl_mbar_init(barB, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __shared__ int s_ellk[2];
     if (tid < 2) s_ellk[tid] = 0;
@@ -721,12 +766,26 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 tlast = clock64();
 #endif
                 // w = rho .* z - y for the owned rows -> every CTA's copy
+#ifdef SQPB200_CLUSTER_SYNC_EXCHANGE
                 if (row_writer) {
                     const double wv = rhor * zr - yr;
 #pragma unroll
                     for (int r = 0; r < CS; ++r) peer_sw[r][my_row] = wv;
                 }
                 cluster.sync();
+#else
+                // (a peer overwrites sw only after it has received this CTA's x~ partials of the previous iteration, which were sent
+                // after the last read of sw: no second buffer, no barrier)
+                if (tid == 0) cl_mbar_arm(barA, (unsigned)m * 8u);
+                if (row_writer) {
+                    const double wv = rhor * zr - yr;
+                    const unsigned dst = cl_smem_u32(s.sw + my_row);
+#pragma unroll
+                    for (int r = 0; r < CS; ++r) cl_st_async(cl_mapa(dst, r), wv, cl_mapa(barA, r));
+                }
+                cl_mbar_wait(barA, parA);
+                parA ^= 1;
+#endif
                 TCK(8)
                 // b (own columns) = sigma x - q + A^T w; padded entries stay 0
                 {
@@ -751,11 +810,25 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                         }
                     }
                     const double xpart = (a0 + a1) + (a2 + a3);
+#ifdef SQPB200_CLUSTER_SYNC_EXCHANGE
 #pragma unroll
                     for (int r = 0; r < CS; ++r) peer_xp[r][rank * np + tid] = xpart;
+#else
+                    const unsigned dst = cl_smem_u32(s.xp + rank * np + tid);
+#pragma unroll
+                    for (int r = 0; r < CS; ++r) cl_st_async(cl_mapa(dst, r), xpart, cl_mapa(barB, r));
+#endif
                 }
                 TCK(10)
+#ifdef SQPB200_CLUSTER_SYNC_EXCHANGE
                 cluster.sync();
+#else
+                // (the x~ slots are overwritten by a peer only after it has received this CTA's w of the next iteration, sent after
+                // the reads below)
+                if (tid == 0) cl_mbar_arm(barB, (unsigned)(CS * np) * 8u);
+                cl_mbar_wait(barB, parB);
+                parB ^= 1;
+#endif
                 TCK(11)
                 // x = alpha x~ + (1 - alpha) x (every CTA keeps all of x); z~ = A x~ and the z, y updates for the owned rows
                 if (tid < np) {
