@@ -426,34 +426,42 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 if (i < n && j < n && j > i) s.S[r + LD * j] = __ldg(P + j + (size_t)n * i);
             }
             __syncthreads();
-            // + A^T diag(rho) A: row i of H gathers, for every stored (k, i), rho_k A_ki times row k of A. One warp per row,
-            // the entries of row k over the lanes (distinct columns: no conflicts, fixed order)
-            // (the stored entries of column i are fetched by the lanes in one batch and handed round by shuffles, so the per-entry
-            // chain is only pattern -> value/accumulator -> store)
-            for (int r = warp; r < RS; r += CNW) {
-                const int i = RS * rank + r;
-                if (i >= n) continue;
-                const int c0 = couter[r], c1 = couter[r + 1];
-                for (int base = c0; base < c1; base += 32) {
-                    const int cnt = min(32, c1 - base);
-                    double f_l = 0.0;
-                    int r0_l = 0, r1_l = 0;
-                    if (lane < cnt) {
-                        const unsigned ec = cpack[base + lane];
-                        const int k = (int)(ec & PACK_MASK);
-                        f_l = s.sw[k] * vals[ec >> PACK_BITS];
-                        r0_l = router[k];
-                        r1_l = router[k + 1];
-                    }
-                    for (int t = 0; t < cnt; ++t) {
-                        const double f = __shfl_sync(0xffffffffu, f_l, t);
-                        const int r0 = __shfl_sync(0xffffffffu, r0_l, t), r1 = __shfl_sync(0xffffffffu, r1_l, t);
-                        for (int pr = r0 + lane; pr < r1; pr += 32) {
-                            const unsigned er = rpack[pr];
-                            double *dst = s.S + r + LD * (int)(er & PACK_MASK);
-                            *dst = fma(f, vals[er >> PACK_BITS], *dst);
+            // + A^T diag(rho) A: row i of H gathers, for every stored (k, i), rho_k A_ki times row k of A. A warp works on FOUR rows of
+            // the slice at once, eight lanes per row (a row of A holds ~8 entries here: a whole warp per row left three quarters of the
+            // lanes idle): the lanes of a group cover the entries of row k (distinct columns: no conflicts), the stored entries of
+            // column i are fetched by the group in batches of eight and handed round by shuffles. Every H entry receives its
+            // contributions in the order of the column's entries, whatever the grouping: the sums are those of a warp per row.
+            {
+                const int g8 = lane & 24, l8 = lane & 7;
+                for (int rb = 4 * warp; rb < RS; rb += 4 * CNW) {
+                    const int r = rb + (lane >> 3), i = RS * rank + r;
+                    const bool rvalid = r < RS && i < n;
+                    const int c0 = rvalid ? couter[r] : 0, c1 = rvalid ? couter[r + 1] : 0;
+                    const int len_max = __reduce_max_sync(0xffffffffu, c1 - c0);
+                    for (int base = 0; base < len_max; base += 8) {
+                        const int cnt = min(8, max(0, c1 - c0 - base));  // entries of this group's batch
+                        double f_l = 0.0;
+                        int r0_l = 0, r1_l = 0;
+                        if (l8 < cnt) {
+                            const unsigned ec = cpack[c0 + base + l8];
+                            const int k = (int)(ec & PACK_MASK);
+                            f_l = s.sw[k] * vals[ec >> PACK_BITS];
+                            r0_l = router[k];
+                            r1_l = router[k + 1];
                         }
-                        __syncwarp();
+                        const int cnt_max = __reduce_max_sync(0xffffffffu, cnt);
+                        for (int t = 0; t < cnt_max; ++t) {
+                            const double f = __shfl_sync(0xffffffffu, f_l, g8 | t);
+                            const int r0 = __shfl_sync(0xffffffffu, r0_l, g8 | t), r1 = __shfl_sync(0xffffffffu, r1_l, g8 | t);
+                            if (t < cnt) {
+                                for (int pr = r0 + l8; pr < r1; pr += 8) {
+                                    const unsigned er = rpack[pr];
+                                    double *dst = s.S + r + LD * (int)(er & PACK_MASK);
+                                    *dst = fma(f, vals[er >> PACK_BITS], *dst);
+                                }
+                            }
+                            __syncwarp();
+                        }
                     }
                 }
             }
