@@ -479,51 +479,88 @@ __global__ void __launch_bounds__(CT, 1) qp_cluster_kernel(KernelParams p, doubl
                 for (int e = t; e < KB * np; e += nthr) scrR[e] = s.S[(k0l + (e % KB)) + LD * (e / KB)];
                 __threadfence();  // belt and braces: the cluster barrier that ends the step is already a release/acquire at cluster scope
             };
-            // Symmetric sweep of the 32 x 32 pivot block of block kb by ONE warp, a row per lane in registers (the 32 pivots are a
-            // serial chain: a CTA-wide version pays a barrier per pivot), published as E^-1 with the failure flag. Per pivot the lanes
-            // exchange column p through shared memory; the reciprocal of the NEXT pivot is formed by every lane from the exchanged
-            // values (bit-identical to the owner lane's update) so it overlaps the row update instead of heading the next step.
+            // Symmetric sweep of the 32 x 32 pivot block of block kb by ONE warp, a row per lane in registers (the pivots are a
+            // serial chain: a CTA-wide version pays a barrier per pivot), published as E^-1 with the failure flag. Per step the lanes
+            // exchange the pivot columns through shared memory (details at the loop below).
             auto sweep_block = [&](int kb) {
                 const int k0 = kb * KB, k0l = k0 - (k0 / RS) * RS;
                 double *scrE = scr_base + (size_t)(kb & 1) * SCR1 + (size_t)KB * np, *scrF = scrE + KB * KB;
                 double row[KB];
 #pragma unroll
                 for (int j = 0; j < KB; ++j) row[j] = s.S[(k0l + lane) + LD * (k0 + j)];
-                double *cv = Eb;  // 2 x (KB + 2) doubles of exchange space (E^-1 of the current step is no longer needed)
+                // TWO pivots per step (16 steps instead of 32: the step is a serial chain of exchange -> multipliers -> row update). With
+                // K = {pv, pv + 1} and E = S[K][K]: S <- S - S[:,K] E^-1 S[K,:], S[:,K] <- S[:,K] E^-1, S[K,:] <- E^-1 S[K,:], S[K][K] <- -E^-1.
+                // The pivots of the unpivoted LDL^T are d_pv = E00 and d_pv+1 = det(E) / E00: a zero or NaN in either is a failure
+                // (Eigen::LDLT::info() != Success). The inverse of the NEXT pivot block is formed by every lane from the exchanged
+                // values with the very operations the owner lanes' update performs, so it overlaps the row update.
+                double *cv = Eb;  // 2 x (2 KB + 4) doubles of exchange space (E^-1 of the current step is no longer needed)
                 bool bad = false;
-                double inv_d = 0.0;
+                double e00 = 0.0, e01 = 0.0, e11 = 0.0;
                 {
-                    const double d = __shfl_sync(0xffffffffu, row[0], 0);
-                    if (!(fabs(d) > 0.0)) bad = true;  // zero or NaN pivot: Eigen::LDLT::info() != Success
-                    else inv_d = fast_rcp(d);
+                    const double a = __shfl_sync(0xffffffffu, row[0], 0), bq = __shfl_sync(0xffffffffu, row[0], 1);
+                    const double cq = __shfl_sync(0xffffffffu, row[1], 1);
+                    const double det = fma(a, cq, -(bq * bq));
+                    if (!(fabs(a) > 0.0) || !(fabs(det) > 0.0)) {
+                        bad = true;
+                    } else {
+                        const double id = fast_rcp(det);
+                        e00 = cq * id;
+                        e01 = -bq * id;
+                        e11 = a * id;
+                    }
                 }
 #pragma unroll
-                for (int pv = 0; pv < KB; ++pv) {
+                for (int pv = 0; pv < KB; pv += 2) {
                     if (bad) break;
-                    double *cvp = cv + (pv & 1) * (KB + 2);
-                    cvp[lane] = row[pv];
-                    if (pv + 1 < KB && lane == pv + 1) cvp[KB] = row[pv + 1];  // diagonal of the next pivot, before this update
+                    double *ca = cv + ((pv >> 1) & 1) * (2 * KB + 4), *cb = ca + KB;  // exchanged columns pv and pv + 1
+                    ca[lane] = row[pv];
+                    cb[lane] = row[pv + 1];
+                    if (pv + 2 < KB) {  // the next pivot block, before this update
+                        if (lane == pv + 2) cb[KB] = row[pv + 2];
+                        if (lane == pv + 3) {
+                            cb[KB + 1] = row[pv + 2];
+                            cb[KB + 2] = row[pv + 3];
+                        }
+                    }
                     __syncwarp();
-                    const double ti = row[pv] * inv_d;
-                    const bool piv = lane == pv;
-                    const double mult = piv ? inv_d : -ti;
-                    double d_next = 1.0, inv_next = 0.0;
-                    if (pv + 1 < KB) {
-                        const double cn = cvp[pv + 1];
-                        d_next = fma(-(cn * inv_d), cn, cvp[KB]);
-                        inv_next = fast_rcp(d_next);
+                    const bool pa = lane == pv, pb = lane == pv + 1, piv = pa || pb;
+                    const double xa = row[pv], xb = row[pv + 1];
+                    const double wA = fma(xa, e00, xb * e01), wB = fma(xa, e01, xb * e11);  // this row of S[:,K] E^-1
+                    const double mA = piv ? (pa ? e00 : e01) : -wA, mB = piv ? (pa ? e01 : e11) : -wB;
+                    double n00 = 0.0, n01 = 0.0, n11 = 0.0;
+                    bool bad_next = false;
+                    if (pv + 2 < KB) {
+                        const double a2 = ca[pv + 2], b2 = cb[pv + 2], a3 = ca[pv + 3], b3 = cb[pv + 3];
+                        const double wA2 = fma(a2, e00, b2 * e01), wB2 = fma(a2, e01, b2 * e11);
+                        const double wA3 = fma(a3, e00, b3 * e01), wB3 = fma(a3, e01, b3 * e11);
+                        const double f22 = fma(-wB2, b2, fma(-wA2, a2, cb[KB]));
+                        const double f32 = fma(-wB3, b2, fma(-wA3, a2, cb[KB + 1]));
+                        const double f33 = fma(-wB3, b3, fma(-wA3, a3, cb[KB + 2]));
+                        const double det = fma(f22, f33, -(f32 * f32));
+                        if (!(fabs(f22) > 0.0) || !(fabs(det) > 0.0)) {
+                            bad_next = true;
+                        } else {
+                            const double id = fast_rcp(det);
+                            n00 = f33 * id;
+                            n01 = -f32 * id;
+                            n11 = f22 * id;
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < KB; j += 2) {
-                        const double2 c2 = *reinterpret_cast<const double2 *>(cvp + j);
+                        const double2 a2 = *reinterpret_cast<const double2 *>(ca + j);
+                        const double2 b2 = *reinterpret_cast<const double2 *>(cb + j);
                         const double b0 = piv ? 0.0 : row[j], b1 = piv ? 0.0 : row[j + 1];
-                        row[j] = fma(mult, c2.x, b0);
-                        row[j + 1] = fma(mult, c2.y, b1);
+                        row[j] = fma(mB, b2.x, fma(mA, a2.x, b0));
+                        row[j + 1] = fma(mB, b2.y, fma(mA, a2.y, b1));
                     }
-                    row[pv] = piv ? -inv_d : ti;
-                    if (pv + 1 < KB) {
-                        if (!(fabs(d_next) > 0.0)) bad = true;
-                        inv_d = inv_next;
+                    row[pv] = piv ? (pa ? -e00 : -e01) : wA;
+                    row[pv + 1] = piv ? (pa ? -e01 : -e11) : wB;
+                    if (pv + 2 < KB) {
+                        if (bad_next) bad = true;
+                        e00 = n00;
+                        e01 = n01;
+                        e11 = n11;
                     }
                 }
                 // row holds row `lane` of -(E^-1): publish E^-1 (column-major, coalesced over the lanes)
